@@ -1,0 +1,297 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(zippy_b200 -> libzippy_b200.so), against the CPU oracle, the reference's golden fixtures
+and system zlib.  Mirrors tests/test.nim, test_levels.nim, test_known_bad.nim, fuzz.nim,
+stress.nim and stress2.nim of the reference.  Integer/byte work: every comparison is
+bit-exact."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+ALL_LEVELS = list(range(-2, 10))
+
+
+@pytest.fixture(scope="module")
+def z():
+    import zippy_b200
+    return zippy_b200
+
+
+@pytest.fixture(scope="module")
+def o():
+    from oracle import oracle
+    return oracle
+
+
+# ------------------------------------------------------------------ inflate (pinned)
+def test_inflate_golden_fixtures(z, golden):
+    # tests/test.nim:41-60, tests/test_known_bad.nim:3, tests/bench.nim:5-11
+    names = list(golden)
+    outs = z.uncompress_batch([golden[n][0] for n in names])
+    for n, out in zip(names, outs):
+        meta = golden[n][1]
+        assert not isinstance(out, Exception), (n, out)
+        assert len(out) == meta["len"], n
+        assert util.sha(out) == meta["sha256"], n
+    for n in ("alice29.txt.gz", "fixed.z", "empty.gz", "zerotest3.gz", "gzipfiletest.txt.gz"):
+        assert util.sha(z.uncompress(golden[n][0])) == golden[n][1]["sha256"]
+
+
+def test_inflate_matches_oracle_on_oracle_streams(z, o, corpus):
+    items, want = [], []
+    for name, raw in corpus.items():
+        for level in (-2, -1, 0, 1, 9):
+            for fmt in (o.dfGzip, o.dfZlib):
+                items.append(o.compress(raw, level, fmt, fname_len=level % 26))
+                want.append(raw)
+    for x in util.edge_inputs():
+        items.append(o.compress(x, 1, o.dfGzip))
+        want.append(x)
+        items.append(o.compress(x, -1, o.dfZlib))
+        want.append(x)
+    outs = z.uncompress_batch(items)
+    for i, (out, w) in enumerate(zip(outs, want)):
+        assert not isinstance(out, Exception), (i, out)
+        assert out == w, i
+    raws = [o.deflate(x, 6) for x in util.edge_inputs()[:20]]
+    outs = z.uncompress_batch(raws, z.dfDeflate)
+    for out, x in zip(outs, util.edge_inputs()[:20]):
+        assert out == x
+
+
+def test_inflate_zlib_streams(z, corpus):
+    # tests/stress2.nim:8-20 + block types zlib can be forced into
+    base = corpus["rfctest3.gold"]
+    items, want = [], []
+    for reps in (1, 2, 5, 17, 40):
+        data = base * reps
+        for lvl in (0, 1, 6, 9):
+            items.append(zlib.compress(data, lvl))
+            want.append(data)
+        co = zlib.compressobj(6, zlib.DEFLATED, 31)
+        items.append(co.compress(data) + co.flush())
+        want.append(data)
+        for strat in (zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+            co = zlib.compressobj(6, zlib.DEFLATED, 15, 9, strat)
+            items.append(co.compress(data) + co.flush())
+            want.append(data)
+        co = zlib.compressobj(9, zlib.DEFLATED, 15, 9)
+        parts = b"".join(co.compress(data[i:i + 5000]) + co.flush(zlib.Z_FULL_FLUSH) for i in range(0, len(data), 5000))
+        items.append(parts + co.flush())
+        want.append(data)
+    outs = z.uncompress_batch(items)
+    for i, (out, w) in enumerate(zip(outs, want)):
+        assert out == w, i
+
+
+def test_inflate_error_contract(z, o, golden):
+    # tests/fuzz.nim:16-33: flip a byte / truncate; each outcome must agree with the oracle:
+    # either both succeed with identical bytes or both report an error.
+    rng = random.Random(2024)
+    names = ["randtest1.gz", "randtest2.gz", "randtest3.gz", "rfctest1.gz", "rfctest2.gz", "rfctest3.gz",
+             "zerotest1.gz", "zerotest2.gz"]
+    items = []
+    for _ in range(1500):
+        comp = bytearray(golden[rng.choice(names)][0])
+        pos = rng.randrange(len(comp))
+        comp[pos] = rng.randrange(256)
+        items.append(bytes(comp))
+        items.append(bytes(comp[:pos]))
+    items += [b"", b"\x1f", b"\x1f\x8b\x08" + b"\0" * 20, b"\x78\x01", b"x" * 40, b"\x78\x9c\x03\x00\x00\x00\x00\x01"]
+    outs = z.uncompress_batch(items)
+    n_ok = n_bad = 0
+    for data, out in zip(items, outs):
+        try:
+            want = o.uncompress(data)
+        except o.ZippyError as e:
+            assert isinstance(out, z.ZippyError), (len(data), e)
+            n_bad += 1
+            continue
+        assert not isinstance(out, Exception), (len(data), out)
+        assert out == want
+        n_ok += 1
+    assert n_ok > 0 and n_bad > 0
+
+
+def test_inflate_wrapper_errors(z, o, corpus):
+    raw = corpus["html"]
+    good = o.compress(raw, 1, o.dfGzip)
+    cases = {
+        "bad id": bytes([0]) + good[1:],
+        "bad method": good[:2] + b"\x07" + good[3:],
+        "reserved flag": good[:3] + bytes([good[3] | 0x80]) + good[4:],
+        "fextra": good[:3] + bytes([good[3] | 0x04]) + good[4:],
+        "bad crc": good[:-8] + bytes([good[-8] ^ 1]) + good[-7:],
+        "bad isize": good[:-1] + bytes([good[-1] ^ 1]),
+    }
+    for name, data in cases.items():
+        with pytest.raises(o.ZippyError):
+            o.uncompress(data, o.dfGzip)
+        with pytest.raises(z.ZippyError):
+            z.uncompress(data, z.dfGzip)
+    zl = o.compress(raw, 1, o.dfZlib)
+    with pytest.raises(z.ZippyError):
+        z.uncompress(zl[:-1] + bytes([zl[-1] ^ 1]))
+    with pytest.raises(z.ZippyError):
+        z.uncompress(bytes([0x78, 0x20 | (31 - (0x7820 % 31))]) + zl[2:], z.dfZlib)  # FDICT
+
+
+# ------------------------------------------------------------------ deflate (round trip)
+@pytest.mark.parametrize("fmt_name", ["dfDeflate", "dfZlib", "dfGzip"])
+def test_compress_roundtrip_formats(z, o, corpus, fmt_name):
+    # tests/test.nim:62-85
+    fmt = getattr(z, fmt_name)
+    wb = {z.dfDeflate: -15, z.dfZlib: 15, z.dfGzip: 31}[fmt]
+    names = list(corpus)
+    comp = z.compress_batch([corpus[n] for n in names], z.DefaultCompression, fmt)
+    for n, c in zip(names, comp):
+        assert o.uncompress(c, o.dfDeflate if fmt == z.dfDeflate else o.dfDetect) == corpus[n], n
+        assert zlib.decompress(c, wb) == corpus[n], n
+    back = z.uncompress_batch(comp, z.dfDeflate if fmt == z.dfDeflate else z.dfDetect)
+    for n, b in zip(names, back):
+        assert b == corpus[n], n
+
+
+@pytest.mark.parametrize("level", ALL_LEVELS)
+def test_compress_roundtrip_levels(z, o, corpus, level):
+    # tests/test_levels.nim:18-25
+    names = ["randtest1.gold", "rfctest1.gold", "zerotest1.gold", "empty.gold", "alice29.txt", "asyoulik.txt",
+             "fireworks.jpg", "geo.protodata", "html", "kppkn.gtb", "paper-100k.pdf"]
+    for n in names:
+        c = z.compress(corpus[n], level)
+        assert c[:4] == b"\x1f\x8b\x08\x08"          # zippy.nim:23-26
+        assert o.uncompress(c) == corpus[n]
+        assert zlib.decompress(c, 31) == corpus[n]
+        assert z.uncompress(c) == corpus[n]
+
+
+def test_compress_edges(z, o):
+    xs = util.edge_inputs()
+    for level in (1, -2, 0):
+        comp = z.compress_batch(xs, level, z.dfZlib)
+        for x, c in zip(xs, comp):
+            assert zlib.decompress(c) == x
+            assert o.uncompress(c) == x
+    with pytest.raises(z.ZippyError):
+        z.compress(b"x", 10)
+    with pytest.raises(z.ZippyError):
+        z.compress(b"x", -3)
+    with pytest.raises(z.ZippyError):
+        z.compress(b"x", 1, z.dfDetect)
+
+
+def test_compress_gzip_framing(z, corpus):
+    # zippy.nim:21-58: FNAME flag, k letters + NUL, CRC32 + ISIZE trailer
+    raw = corpus["html"]
+    outs = z.compress_batch([raw] * 3, 1, z.dfGzip, fname_lens=[0, 1, 25])
+    for k, c in zip((0, 1, 25), outs):
+        assert c[:10] == bytes([31, 139, 8, 8, 0, 0, 0, 0, 0, 0])
+        assert c[10:11 + k] == bytes(range(97, 97 + k)) + b"\0"
+        assert int.from_bytes(c[-8:-4], "little") == zlib.crc32(raw)
+        assert int.from_bytes(c[-4:], "little") == len(raw)
+    zl = z.compress(raw, 1, z.dfZlib)
+    assert zl[:2] == b"\x78\x01" and int.from_bytes(zl[-4:], "big") == zlib.adler32(raw)   # zippy.nim:60-78
+
+
+def test_compress_c2_blocks_and_ratio(z, o, corpus):
+    # BASELINE config 2 at reduced count: seeded 64 KiB text blocks, level 1, gzip
+    T = util.text_corpus(corpus)
+    blocks = [util.c2_block(T, i) for i in range(256)]
+    comp = z.compress_batch(blocks, z.BestSpeed, z.dfGzip)
+    for b, c in zip(blocks[:64], comp[:64]):
+        assert o.uncompress(c) == b
+    back = z.uncompress_batch(comp)
+    assert all(r == b for r, b in zip(back, blocks))
+    gpu = sum(map(len, comp))
+    ref = sum(len(o.compress(b, 1, o.dfGzip)) for b in blocks[:64]) * 4
+    assert gpu < 1.10 * ref, (gpu, ref)   # ratio within 10% of the reference's level 1 on text
+
+
+def test_compress_large_members(z, o, corpus):
+    rng = random.Random(7)
+    big = [corpus["urls.10K"], corpus["plrabn12.txt"], b"\0" * (1 << 20), corpus["fireworks.jpg"] * 3,
+           bytes(rng.randrange(256) for _ in range(300001)), corpus["html_x_4"] + corpus["kppkn.gtb"]]
+    for fmt in (z.dfGzip, z.dfZlib, z.dfDeflate):
+        comp = z.compress_batch(big, 1, fmt)
+        for x, c in zip(big, comp):
+            assert o.uncompress(c, o.dfDeflate if fmt == z.dfDeflate else o.dfDetect) == x
+        back = z.uncompress_batch(comp, z.dfDeflate if fmt == z.dfDeflate else z.dfDetect)
+        assert all(b == x for b, x in zip(back, big))
+
+
+def test_stress_run_length_blobs(z, o):
+    # tests/stress.nim:10-58
+    rng = random.Random(4242)
+    xs = []
+    for _ in range(100):
+        x = util.run_length_blob(rng)
+        y = bytearray(x)
+        rng.shuffle(y)
+        xs += [x, bytes(y)]
+    comp = z.compress_batch(xs, z.DefaultCompression, z.dfZlib)
+    for x, c in zip(xs, comp):
+        assert zlib.decompress(c) == x
+    back = z.uncompress_batch(comp)
+    assert all(b == x for b, x in zip(back, xs))
+
+
+# ------------------------------------------------------------------ checksums + seam
+def test_checksums(z, corpus):
+    rng = random.Random(5)
+    xs = [b"", b"a", b"abc"] + [bytes(rng.randrange(256) for _ in range(n))
+                                 for n in (4, 5, 127, 128, 129, 255, 4095, 32767, 32768, 32769, 65536, 100003)]
+    xs += [corpus["alice29.txt"], corpus["urls.10K"], b"\xff" * 300000]
+    crcs = z.checksum_batch(xs, "crc32")
+    ads = z.checksum_batch(xs, "adler32")
+    for x, c, a in zip(xs, crcs, ads):
+        assert int(c) == zlib.crc32(x), len(x)
+        assert int(a) == zlib.adler32(x), len(x)
+    assert z.crc32(corpus["html"]) == zlib.crc32(corpus["html"])
+    assert z.adler32(corpus["html"]) == zlib.adler32(corpus["html"])
+
+
+def test_seam_deflate_inflate(z, o, corpus):
+    # deflate.nim:207 / inflate.nim:268 signatures: raw stream, inflate from byte `pos`
+    for name in ("alice29.txt", "html", "empty.gold", "fireworks.jpg"):
+        raw = corpus[name]
+        for level in (1, -1, 0, -2):
+            d = z.deflate(raw, level)
+            assert zlib.decompress(d, -15) == raw
+            assert o.inflate(d) == raw
+            assert z.inflate(d) == raw
+            assert z.inflate(b"\xaa\xbb\xcc" + d, pos=3) == raw
+    with pytest.raises(z.ZippyError):
+        z.inflate(b"\x07")          # BTYPE 3 (inflate.nim:289)
+    with pytest.raises(z.ZippyError):
+        z.inflate(b"")
+
+
+def test_device_resident_batch(z, o, corpus):
+    torch = pytest.importorskip("torch")
+    T = util.text_corpus(corpus)
+    n = 64
+    blocks = [util.c2_block(T, i) for i in range(n)]
+    host = np.frombuffer(b"".join(blocks), dtype=np.uint8)
+    d_src = torch.from_numpy(host.copy()).cuda()
+    offs = np.arange(n + 1, dtype=np.uint64) * 65536
+    cap = n * 70000
+    d_dst = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    ctx = z.Context()
+    oo = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfGzip, d_dst.data_ptr(), cap)
+    comp = d_dst.cpu().numpy()
+    for i in range(n):
+        assert o.uncompress(comp[int(oo[i]):int(oo[i + 1])].tobytes()) == blocks[i]
+    sizes, st = ctx.uncompressed_sizes_device(d_dst.data_ptr(), oo, z.dfDetect)
+    assert not st.any() and (sizes == 65536).all()
+    d_back = torch.empty(n * 65536, dtype=torch.uint8, device="cuda")
+    lens, st = ctx.uncompress_batch_device(d_dst.data_ptr(), oo, z.dfDetect, d_back.data_ptr(), offs)
+    assert not st.any() and (lens == 65536).all()
+    assert torch.equal(d_back, d_src)
+    t = ctx.timing()
+    assert t["kernel_launches"] >= 2
+    ctx.close()

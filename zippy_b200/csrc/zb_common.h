@@ -7,10 +7,10 @@
 
 #if defined(__CUDACC__)
 #define ZB_HD __host__ __device__ __forceinline__
-#define ZB_HD_NOINLINE __host__ __device__
+#define ZB_HD_NOINLINE __host__ __device__ inline
 #else
 #define ZB_HD inline
-#define ZB_HD_NOINLINE
+#define ZB_HD_NOINLINE inline
 #endif
 
 // ---- geometry of the compress pipeline (see DESIGN.md "Data layout") ----

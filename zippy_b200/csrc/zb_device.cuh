@@ -1,0 +1,163 @@
+// zb_device.cuh -- device-side helpers shared by the sm_100a kernels:
+// TMA 1-D bulk staging + mbarrier, unaligned shared-memory reads, the warp-level
+// lane-strided CRC-32 / Adler-32 body (algebra in zb_crc.h, CPU-checked in
+// tests/test_host_units.py::test_crc_math).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "zb_common.h"
+#include "zb_crc.h"
+
+#define ZB_FULL 0xffffffffu
+
+__device__ __forceinline__ uint32_t zb_smem_addr(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ int zb_lane() { return (int)(threadIdx.x & 31u); }
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ----
+__device__ __forceinline__ void zb_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zb_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void zb_fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void zb_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zb_smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void zb_mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "ZB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra ZB_DONE_%=;\n"
+      "bra ZB_WAIT_%=;\n"
+      "ZB_DONE_%=:\n"
+      "}\n" ::"r"(zb_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; src, dst 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void zb_tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                               uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          zb_smem_addr(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(zb_smem_addr(bar))
+      : "memory");
+}
+
+// Stage `len` bytes starting at global `src` (any alignment) into `buf` so that byte i
+// of the input lives at buf[mis + i], mis = src & 15.  buf must be 16-byte aligned and
+// hold round_up(mis + len, 16) bytes.  Called by one thread; everyone then waits on bar.
+// Reads up to 15 bytes either side of [src, src+len) inside the same 16-byte granules,
+// which is always inside the caller's allocation (cudaMalloc granularity >= 256 B).
+__device__ __forceinline__ uint32_t zb_stage_chunk(uint8_t *buf, const uint8_t *src, uint32_t len,
+                                                   uint64_t *bar) {
+  uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
+  uint32_t bytes = (mis + len + 15u) & ~15u;
+  if (bytes == 0) bytes = 16;
+  zb_mbar_expect_tx(bar, bytes);
+  // a single bulk copy is limited by the mbarrier tx-count width; split into 32 KiB pieces
+  const uint8_t *g = src - mis;
+  uint32_t done = 0;
+  while (done < bytes) {
+    uint32_t n = bytes - done;
+    if (n > 32768u) n = 32768u;
+    zb_tma_load_1d(buf + done, g + done, n, bar);
+    done += n;
+  }
+  return mis;
+}
+
+// ---- unaligned little-endian reads from shared memory ----
+__device__ __forceinline__ uint32_t zb_ld32_unaligned(const uint8_t *base, uint32_t off) {
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(base) + (off >> 2);
+  uint32_t lo = w[0], hi = w[1];
+  return __funnelshift_r(lo, hi, (off & 3u) * 8u);
+}
+
+// ---- warp XOR / add reductions ----
+__device__ __forceinline__ uint32_t zb_warp_xor(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(ZB_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ uint64_t zb_warp_sum64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ZB_FULL, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t zb_mul1024(const uint32_t *tab /*[4][256] in smem*/, uint32_t r) {
+  return tab[r & 255u] ^ tab[256 + ((r >> 8) & 255u)] ^ tab[512 + ((r >> 16) & 255u)] ^ tab[768 + (r >> 24)];
+}
+
+// Raw (init-0) CRC-32 and Adler sums of bytes [off, off+n) of a shared-memory buffer,
+// computed by one warp: lane i takes 32-bit words i, i+32, ... of each 128-byte row,
+// advances its state by x^1024 per row (4 table lookups), then the lane states are
+// shifted by x^(32*(32-i)) and XOR-reduced.  Result is uniform across the warp.
+// a_sum = sum of bytes, b_sum = sum (n - i) * b_i  (exact, 64-bit).
+struct ZbCheck {
+  uint32_t crc_raw;
+  uint64_t a_sum, b_sum;
+};
+__device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32_t off, uint32_t n,
+                                                     const uint32_t *tab, const uint32_t *lane_mul) {
+  const int lane = zb_lane();
+  const uint32_t rows = n >> 7, tail = n & 127u;
+  uint32_t r = 0;
+  uint32_t a = 0;
+  uint64_t b = 0;
+  uint32_t o = off + 4u * (uint32_t)lane;  // byte offset of this lane's word in row 0
+  uint32_t rel = 4u * (uint32_t)lane;      // offset relative to the piece start
+  for (uint32_t k = 0; k < rows; k++) {
+    uint32_t w = zb_ld32_unaligned(base, o);
+    if (k) r = zb_mul1024(tab, r);
+    r ^= w;
+    uint32_t s = __dp4a(w, 0x01010101u, 0u);
+    uint32_t ws = __dp4a(w, 0x03020100u, 0u);
+    a += s;
+    b += (uint64_t)(n - rel) * s - ws;
+    o += 128u;
+    rel += 128u;
+  }
+  uint32_t crc = rows ? zb_gf2_mul(r, lane_mul[32 - lane]) : 0u;
+  // tail: < 128 bytes = tw full words (one per lane) + rem bytes (lane 0, bitwise)
+  const uint32_t tw = tail >> 2, rem = tail & 3u;
+  uint32_t crc_tail = 0;
+  if ((uint32_t)lane < tw) {
+    uint32_t w = zb_ld32_unaligned(base, o);
+    crc_tail = zb_gf2_mul(w, lane_mul[tw - (uint32_t)lane]);
+    uint32_t s = __dp4a(w, 0x01010101u, 0u);
+    uint32_t ws = __dp4a(w, 0x03020100u, 0u);
+    a += s;
+    b += (uint64_t)(n - rel) * s - ws;
+  }
+  uint32_t crc_rem = 0;
+  if (lane == 0) {
+    for (uint32_t i = 0; i < rem; i++) {
+      uint32_t byte = base[off + (rows << 7) + 4u * tw + i];
+      crc_rem = zb_crc_raw_byte(crc_rem, byte);
+      a += byte;
+      b += (uint64_t)(rem - i) * byte;
+    }
+  }
+  crc = zb_warp_xor(crc);
+  crc_tail = zb_warp_xor(crc_tail);
+  crc_rem = __shfl_sync(ZB_FULL, crc_rem, 0);
+  ZbCheck out;
+  uint32_t raw = crc;
+  if (tail) {
+    raw = zb_gf2_mul(crc, zb_xpow8(tail));
+    if (rem) raw ^= zb_gf2_mul(crc_tail, zb_xpow8(rem)) ^ crc_rem;
+    else raw ^= crc_tail;
+  }
+  out.crc_raw = raw;
+  out.a_sum = zb_warp_sum64((uint64_t)a);
+  out.b_sum = zb_warp_sum64(b);
+  return out;
+}

@@ -1,0 +1,83 @@
+// zb_kernels.h -- launch interface between the C-ABI layer (zb_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "zb_common.h"
+#include "zb_crc.h"
+#include "zb_huff.h"
+
+// One unit of compress work: <= 64 KiB of one member, one DEFLATE block.
+struct ZbChunkDesc {
+  uint64_t src_off;   // byte offset of the chunk in the source buffer
+  uint32_t len;       // 0..65536
+  uint32_t member;    // index of the input this chunk belongs to
+  uint32_t flags;     // bit0: first chunk of its member, bit1: last chunk
+  uint32_t pad;
+};
+#define ZB_CHUNK_FIRST 1u
+#define ZB_CHUNK_LAST 2u
+
+struct ZbChunkCheck {
+  uint32_t crc_raw;   // init-0 CRC of the chunk bytes
+  uint32_t adler;     // Adler-32 of the chunk bytes as a standalone message
+};
+
+// All device scratch for one compress batch (arrays sized by n_chunks / n_members).
+struct ZbCompressWork {
+  const uint8_t *src;          // device
+  uint8_t *dst;                // device, zero-filled up to the batch's total before packing
+  const ZbChunkDesc *desc;     // [n_chunks]
+  const uint32_t *member_first;// [n_members + 1] first chunk index of each member
+  const uint8_t *fname_len;    // [n_members] gzip FNAME letters (0..25) or nullptr
+  uint2 *masks;                // [n_chunks][2048] (token-start mask, is-match mask) per 32-byte window
+  uint32_t *recs;              // [n_chunks][2048][8] match records
+  uint16_t *hist;              // [n_chunks][8][316]
+  ZbChunkCheck *chk;           // [n_chunks]
+  ZbCodebook *cb;              // [n_chunks]
+  uint64_t *chunk_off;         // [n_chunks] byte offset of each chunk's deflate bytes in dst
+  uint64_t *member_off;        // [n_members + 1] output offsets (member_off[n] = total)
+  uint32_t *member_check;      // [n_members] crc32 (gzip) or adler32 (zlib) of the whole member
+  uint32_t *member_isize;      // [n_members] input size mod 2^32 (gzip ISIZE)
+  uint64_t out_base;           // byte offset in dst where this group's first member starts
+  const ZbCrcTables *tabs;     // device
+  uint32_t n_chunks, n_members;
+  int level, data_format;
+};
+
+cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s);
+cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s);
+cudaError_t zb_launch_scan(const ZbCompressWork &w, cudaStream_t s);
+cudaError_t zb_launch_pack(const ZbCompressWork &w, cudaStream_t s);
+
+// ---- inflate ----
+struct ZbInflateWork {
+  const uint8_t *src;          // device
+  const uint64_t *src_off;     // device [n+1]
+  uint8_t *dst;                // device (unused when count_only)
+  const uint64_t *dst_off;     // device [n+1]; capacity of member i = dst_off[i+1]-dst_off[i]
+  uint64_t *out_len;           // device [n]
+  int *status;                 // device [n]
+  uint32_t *expect;            // device [n] trailer checksum
+  uint32_t *kind;              // device [n] resolved format (ZB_DF_*) per member
+  uint32_t *counter;           // device work-queue counter (zeroed before launch)
+  const ZbCrcTables *tabs;
+  uint32_t n;
+  int data_format;             // requested (may be ZB_DF_DETECT)
+  uint64_t pos;                // payload start for raw ZB_DF_DEFLATE members (zb200_inflate's `pos`)
+  int count_only;
+};
+cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s);
+cudaError_t zb_launch_verify(const ZbInflateWork &w, cudaStream_t s);
+
+// ---- standalone checksums over a batch of buffers ----
+// kind: 0 crc32, 1 adler32.  piece arrays are scratch of size n_pieces.
+struct ZbChecksumWork {
+  const uint8_t *src;
+  const uint64_t *off;         // device [n+1]
+  uint32_t *out;               // device [n]
+  const ZbCrcTables *tabs;
+  uint32_t n;
+  int kind;
+};
+cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s);
