@@ -72,6 +72,9 @@ int zb200_init(int device, zb200_ctx **out);  /* device < 0: current device */
 void zb200_shutdown(zb200_ctx *ctx);
 const char *zb200_strerror(int status);       /* the reference's message for 1..18 */
 const char *zb200_last_cuda_error(zb200_ctx *ctx);
+/* run this ctx's work on a caller-owned CUDA stream (a cudaStream_t passed as void*;
+ * NULL restores the ctx's own stream) so callers can order and time it with their events */
+int zb200_set_stream(zb200_ctx *ctx, void *cuda_stream);
 int zb200_device_count(void);
 
 /* ---- sizing ---- */

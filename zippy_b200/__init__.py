@@ -72,6 +72,10 @@ class Context:
             raise ZippyError(rc, "zb200_init failed: %s (zippy_b200 needs a CUDA device; there is no CPU fallback)"
                              % L.zb200_strerror(rc).decode())
 
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned cudaStream_t (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(self._h, _native.lib().zb200_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
     def close(self):
         if self._h:
             _native.lib().zb200_shutdown(self._h)
@@ -123,6 +127,10 @@ class Context:
         n = len(offsets) - 1
         sizes, st0 = self.uncompressed_sizes(base, offsets, dataFormat)
         sizes = np.where(st0 == 0, sizes, 0).astype(np.uint64)
+        # a gzip ISIZE is a claim, not a fact: DEFLATE cannot expand more than 1032:1, so a
+        # larger claim can only end in a size/checksum failure -- never allocate for it.
+        comp_lens = offsets[1:] - offsets[:-1]
+        sizes = np.minimum(sizes, comp_lens * np.uint64(1032) + np.uint64(1024))
         if max_total is not None and int(sizes.sum()) > max_total:
             raise ZippyError(19)
         dst_offs = np.zeros(n + 1, dtype=np.uint64)

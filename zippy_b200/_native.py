@@ -28,6 +28,7 @@ SYMBOLS = {
     "zb200_strerror": (ctypes.c_char_p, [c_int]),
     "zb200_last_cuda_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "zb200_device_count": (c_int, []),
+    "zb200_set_stream": (c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "zb200_deflate_bound": (c_size_t, [c_size_t]),
     "zb200_compress_bound": (c_size_t, [c_size_t, c_int]),
     "zb200_deflate": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, c_int, c_u8p, c_size_t, ctypes.POINTER(c_size_t)]),

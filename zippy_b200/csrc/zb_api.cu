@@ -28,6 +28,7 @@ constexpr size_t kMaxChunksPerGroup = 131072;  // 8 GiB of input per launch grou
 struct zb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   ZbCrcTables *d_tabs = nullptr;
   DevBuf desc, member_first, fname, masks, recs, hist, chk, cb, chunk_off, member_off, member_check, member_isize;
   DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out;
@@ -357,7 +358,8 @@ int zb200_init(int device, zb200_ctx **out) {
   ctx->device = device;
   memset(&ctx->timing, 0, sizeof(ctx->timing));
   DeviceGuard g(device);
-  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->stream = ctx->own_stream;
   for (int i = 0; ok && i < 10; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   if (ok) ok = cudaMalloc((void **)&ctx->d_tabs, sizeof(ZbCrcTables)) == cudaSuccess;
   if (ok) {
@@ -386,8 +388,15 @@ void zb200_shutdown(zb200_ctx *ctx) {
     if (b->p) cudaFree(b->p);
   if (ctx->d_tabs) cudaFree(ctx->d_tabs);
   for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
+}
+
+int zb200_set_stream(zb200_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return ZB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return ZB200_OK;
 }
 
 const char *zb200_last_cuda_error(zb200_ctx *ctx) { return ctx ? ctx->last_err.c_str() : ""; }

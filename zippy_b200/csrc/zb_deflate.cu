@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
         c = table[h];
         __syncwarp();
         if (can) table[h] = (uint16_t)p;
-        if (can && c < p && p - c <= ZB_MAX_DIST && p >= entry && p < b1) {
+        // a match may not cross the sub-chunk end (the next warp starts its own parse there)
+        const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
+        if (can && c < p && p - c <= ZB_MAX_DIST && p >= entry && limit >= ZB_MIN_MATCH) {
           if (zb_ld32_unaligned(data, mis + c) == v) {
             m = 4;
             while (m < LZ_PAR_CAP) {
@@ -133,9 +135,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
               }
               m += 4;
             }
-            uint32_t limit = min((uint32_t)ZB_MAX_MATCH, b1 - p);
             if (m < LZ_PAR_CAP) m = min(m, limit);  // a capped match is clamped after extension
-            if (m < ZB_MIN_MATCH) m = 0;
           }
         }
       }
