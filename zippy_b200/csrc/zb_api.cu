@@ -89,11 +89,6 @@ struct DeviceGuard {
   }
 };
 
-uint32_t head_bytes(int fmt, const uint8_t *fname_lens, size_t m) {
-  if (fmt == ZB200_DF_GZIP) return 10u + (fname_lens ? fname_lens[m] : 0u) + 1u;
-  if (fmt == ZB200_DF_ZLIB) return 2u;
-  return 0u;
-}
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
