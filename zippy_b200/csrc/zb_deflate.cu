@@ -19,23 +19,37 @@
 #define LZ_HASH_BITS 11
 #define LZ_TABLE_ENTRIES (1 << LZ_HASH_BITS)
 #define LZ_PRESEED 4096
-#define LZ_PAR_CAP 32  // bytes a lane extends on its own; longer matches finish cooperatively
+#define LZ_LANE_CAP 16  // bytes a lane extends on its own; longer matches finish warp-cooperatively
 
-// shared-memory layout of k_lz (bytes)
+// shared-memory layout of k_lz (bytes).  The CRC step table (4 KiB) is loaded by each warp
+// into its own hash-table region for the checksum phase and overwritten afterwards.
 #define LZ_SM_DATA 0
 #define LZ_SM_DATA_BYTES (ZB_CHUNK_BYTES + 64)
 #define LZ_SM_TABLE (LZ_SM_DATA + LZ_SM_DATA_BYTES)
 #define LZ_SM_TABLE_BYTES (ZB_WARPS_PER_CHUNK * LZ_TABLE_ENTRIES * 2)
 #define LZ_SM_HIST (LZ_SM_TABLE + LZ_SM_TABLE_BYTES)
 #define LZ_SM_HIST_BYTES (ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS * 4)
-#define LZ_SM_CRC (LZ_SM_HIST + LZ_SM_HIST_BYTES)
-#define LZ_SM_CRC_BYTES (4 * 256 * 4 + 36 * 4)
-#define LZ_SM_PART (LZ_SM_CRC + LZ_SM_CRC_BYTES)
+#define LZ_SM_RING (LZ_SM_HIST + LZ_SM_HIST_BYTES)
+#define LZ_SM_RING_BYTES (ZB_WARPS_PER_CHUNK * 32 * ZB_MATCH_SLOTS * 4)
+#define LZ_SM_LMUL (LZ_SM_RING + LZ_SM_RING_BYTES)
+#define LZ_SM_LMUL_BYTES (36 * 4)
+#define LZ_SM_PART (LZ_SM_LMUL + LZ_SM_LMUL_BYTES)
 #define LZ_SM_PART_BYTES (ZB_WARPS_PER_CHUNK * 24)
 #define LZ_SM_BAR (LZ_SM_PART + LZ_SM_PART_BYTES)
 #define LZ_SM_TOTAL (LZ_SM_BAR + 16)
+static_assert(LZ_TABLE_ENTRIES * 2 >= 4096, "a warp's table region must hold the CRC step table");
+static_assert(2 * (LZ_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
 
 __device__ __forceinline__ uint32_t lz_hash(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
+__device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32 ? ~0u : ((1u << n) - 1u); }
+
+// Final match record consumed by k_pack: length code | length extra value << 5 |
+// distance code << 10 | distance extra value << 15.
+__device__ __forceinline__ uint32_t lz_final_rec(uint32_t mlen, uint32_t dist, int &lc, int &dc) {
+  lc = zb_len_code(mlen);
+  dc = zb_dist_code(dist);
+  return (uint32_t)lc | ((mlen - zb_len_base(lc)) << 5) | ((uint32_t)dc << 10) | ((dist - zb_dist_base(dc)) << 15);
+}
 
 template <int MODE>  // 1: hash-table matcher (level 1 and, for now, the LZ levels); 0: literals only
 __global__ void __launch_bounds__(LZ_THREADS, 2)
@@ -46,8 +60,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
   uint8_t *data = smem + LZ_SM_DATA;
   uint16_t *table_all = reinterpret_cast<uint16_t *>(smem + LZ_SM_TABLE);
   uint32_t *hist_all = reinterpret_cast<uint32_t *>(smem + LZ_SM_HIST);
-  uint32_t *crc_tab = reinterpret_cast<uint32_t *>(smem + LZ_SM_CRC);
-  uint32_t *lane_mul = crc_tab + 1024;
+  uint32_t *ring_all = reinterpret_cast<uint32_t *>(smem + LZ_SM_RING);
+  uint32_t *lane_mul = reinterpret_cast<uint32_t *>(smem + LZ_SM_LMUL);
   uint64_t *part = reinterpret_cast<uint64_t *>(smem + LZ_SM_PART);
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + LZ_SM_BAR);
 
@@ -61,25 +75,24 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     zb_fence_mbar_init();
   }
   __syncthreads();
-  uint32_t mis = (uint32_t)((uintptr_t)(src + d.src_off) & 15u);
+  const uint32_t mis = (uint32_t)((uintptr_t)(src + d.src_off) & 15u);
   if (tid == 0 && len) zb_stage_chunk(data, src + d.src_off, len, bar);
 
-  // while the bulk copy is in flight: clear histograms, empty the hash tables, load CRC tables
+  uint16_t *table = table_all + warp * LZ_TABLE_ENTRIES;
+  uint32_t *whist = hist_all + warp * ZB_HIST_WORDS;
+  uint32_t *ring = ring_all + warp * 32 * ZB_MATCH_SLOTS;
+  // while the bulk copy is in flight: clear histograms, load the CRC tables
   for (int i = tid; i < ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS; i += LZ_THREADS) hist_all[i] = 0;
   {
-    uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u);
-    uint4 *t4 = reinterpret_cast<uint4 *>(table_all);
-    for (int i = tid; i < LZ_SM_TABLE_BYTES / 16; i += LZ_THREADS) t4[i] = ff;
+    uint32_t *crc_tab = reinterpret_cast<uint32_t *>(table);
+    for (int i = lane; i < 1024; i += 32) crc_tab[i] = (&tabs->mul1024[0][0])[i];
   }
-  for (int i = tid; i < 1024; i += LZ_THREADS) crc_tab[i] = (&tabs->mul1024[0][0])[i];
   if (tid < 33) lane_mul[tid] = tabs->lane_mul[tid];
   __syncthreads();
   if (len) zb_mbar_wait(bar, 0);
 
   const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES;
   const uint32_t b1 = min(b0 + ZB_SUB_BYTES, len);
-  uint16_t *table = table_all + warp * LZ_TABLE_ENTRIES;
-  uint32_t *whist = hist_all + warp * ZB_HIST_WORDS;
 
   // ---- checksums of this warp's piece (CRC raw + Adler sums) ----
   {
@@ -87,113 +100,154 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     c.crc_raw = 0;
     c.a_sum = c.b_sum = 0;
     uint32_t n = b0 < len ? b1 - b0 : 0;
-    if (n) c = zb_warp_checksums(data, mis + b0, n, crc_tab, lane_mul);
+    if (n) c = zb_warp_checksums(data, mis + b0, n, reinterpret_cast<const uint32_t *>(table), lane_mul);
     if (lane == 0) {
       part[warp * 3 + 0] = c.crc_raw;
       part[warp * 3 + 1] = c.a_sum;
       part[warp * 3 + 2] = c.b_sum;
     }
+    __syncwarp();
   }
 
   if (b0 < len) {
-    if (MODE == 1 && warp > 0) {
-      // pre-seed the private table with the positions just before this sub-chunk
-      for (uint32_t s = b0 - LZ_PRESEED; s < b0; s += 32) {
-        uint32_t p = s + (uint32_t)lane;
-        if (p + 4 <= len) table[lz_hash(zb_ld32_unaligned(data, mis + p))] = (uint16_t)p;
-      }
+    if (MODE == 1) {
+      // the table region held the CRC step table until now: empty it
+      uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u);
+      uint4 *t4 = reinterpret_cast<uint4 *>(table);
+      for (int i = lane; i < LZ_TABLE_ENTRIES * 2 / 16; i += 32) t4[i] = ff;
       __syncwarp();
+      if (warp > 0) {
+        // pre-seed the private table with the positions just before this sub-chunk
+        for (uint32_t s = b0 - LZ_PRESEED; s < b0; s += 32) {
+          uint32_t p = s + (uint32_t)lane;
+          if (p + 4 <= len) table[lz_hash(zb_ld32_unaligned(data, mis + p))] = (uint16_t)p;
+        }
+        __syncwarp();
+      }
     }
     uint32_t entry = b0;
-    const size_t win_base = (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
+    uint32_t ksel = 0, kism = 0;  // lane i keeps the masks of window i of the current batch of 32
+    uint2 *gmask = masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
+    uint32_t *grecs = recs + (size_t)chunk * ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS;
     for (uint32_t wb = b0; wb < b1; wb += 32) {
-      const uint32_t win = wb >> 5;
-      if (entry >= wb + 32) {  // whole window already covered by a long match
-        if (lane == 0) masks[win_base + win] = make_uint2(0u, 0u);
-        continue;
-      }
-      const uint32_t p = wb + (uint32_t)lane;
-      const uint32_t nvalid = min(32u, b1 - wb);
-      const uint32_t v = zb_ld32_unaligned(data, mis + p);
-      uint32_t m = 0, c = 0;
-      if (MODE == 1) {
-        const bool can = (p + 4 <= len);
-        const uint32_t h = lz_hash(v);
-        c = table[h];
-        __syncwarp();
-        if (can) table[h] = (uint16_t)p;
-        // a match may not cross the sub-chunk end (the next warp starts its own parse there)
-        const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
-        if (can && c < p && p - c <= ZB_MAX_DIST && p >= entry && limit >= ZB_MIN_MATCH) {
-          if (zb_ld32_unaligned(data, mis + c) == v) {
-            m = 4;
-            while (m < LZ_PAR_CAP) {
-              uint32_t x = zb_ld32_unaligned(data, mis + p + m) ^ zb_ld32_unaligned(data, mis + c + m);
-              if (x) {
-                m += (uint32_t)(__ffs((int)x) - 1) >> 3;
-                break;
+      const uint32_t win = wb >> 5, slot = win & 31u;
+      uint32_t sel = 0, ism = 0;
+      if (entry < wb + 32) {
+        const uint32_t p = wb + (uint32_t)lane;
+        const uint32_t nvalid = min(32u, b1 - wb);
+        const uint32_t cur = entry - wb;
+        uint32_t m = 0, c = 0;
+        if (MODE == 1) {
+          const uint32_t v = zb_ld32_unaligned(data, mis + p);
+          const bool can = (p + 4 <= len);
+          const uint32_t h = lz_hash(v);
+          c = table[h];
+          __syncwarp();
+          if (can) table[h] = (uint16_t)p;
+          // a match may not cross the sub-chunk end (the next warp starts its own parse there)
+          const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
+          if (can && c < p && p - c <= ZB_MAX_DIST && p >= entry && limit >= ZB_MIN_MATCH) {
+            if (zb_ld32_unaligned(data, mis + c) == v) {
+              m = 4;
+#pragma unroll 1
+              while (m < LZ_LANE_CAP) {
+                uint32_t x = zb_ld32_unaligned(data, mis + p + m) ^ zb_ld32_unaligned(data, mis + c + m);
+                if (x) {
+                  m += (uint32_t)(__ffs((int)x) - 1) >> 3;
+                  break;
+                }
+                m += 4;
               }
-              m += 4;
+              if (m < LZ_LANE_CAP) m = min(m, limit);
             }
-            if (m < LZ_PAR_CAP) m = min(m, limit);  // a capped match is clamped after extension
+          }
+          // matches that reached the lane cap are extended by the whole warp, 8 bytes per lane
+          uint32_t longm = __ballot_sync(ZB_FULL, m >= LZ_LANE_CAP);
+          while (longm) {
+            const int L = __ffs((int)longm) - 1;
+            longm &= longm - 1;
+            const uint32_t mc = __shfl_sync(ZB_FULL, c, L);
+            const uint32_t pos = wb + (uint32_t)L;
+            const uint32_t off = LZ_LANE_CAP + 8u * (uint32_t)lane;
+            uint32_t x0 = zb_ld32_unaligned(data, mis + pos + off) ^ zb_ld32_unaligned(data, mis + mc + off);
+            uint32_t x1 = zb_ld32_unaligned(data, mis + pos + off + 4) ^ zb_ld32_unaligned(data, mis + mc + off + 4);
+            uint32_t nm = x0 ? ((uint32_t)(__ffs((int)x0) - 1) >> 3) : 4u + (x1 ? ((uint32_t)(__ffs((int)x1) - 1) >> 3) : 4u);
+            uint32_t stop = __ballot_sync(ZB_FULL, nm < 8u);
+            uint32_t ml;
+            if (stop) {
+              int first = __ffs((int)stop) - 1;
+              ml = LZ_LANE_CAP + 8u * (uint32_t)first + __shfl_sync(ZB_FULL, nm, first);
+            } else {
+              ml = LZ_LANE_CAP + 256u;
+            }
+            ml = min(ml, min((uint32_t)ZB_MAX_MATCH, b1 - pos));
+            if (lane == L) m = ml;
           }
         }
-      }
-      // ---- greedy selection inside the window (uniform control flow) ----
-      uint32_t mm = __ballot_sync(ZB_FULL, m != 0);
-      uint32_t sel = 0, ism = 0, cur = entry - wb;
-      uint32_t my_len = 0;
-      while (cur < nvalid) {
-        uint32_t rest = mm >> cur;
-        uint32_t upto = rest ? cur + (uint32_t)(__ffs((int)rest) - 1) : nvalid;
-        // literals [cur, upto)
-        uint32_t lit_bits = (upto >= 32 ? ~0u : ((1u << upto) - 1u)) & ~((1u << cur) - 1u);
-        sel |= lit_bits;
-        if (!rest || upto >= nvalid) {
-          cur = nvalid;
-          break;
+        // ---- greedy selection: follow the chain "candidate -> first candidate at/after its end" ----
+        const uint32_t mm = __ballot_sync(ZB_FULL, m != 0);
+        uint32_t endw = 0;
+        if (mm) {
+          const uint32_t endp = (uint32_t)lane + m;
+          const uint32_t rest = endp < 32 ? (mm >> endp) : 0u;
+          uint32_t nc = rest ? endp + (uint32_t)(__ffs((int)rest) - 1) : 32u;
+          uint32_t vis = 1u << (cur + (uint32_t)(__ffs((int)(mm >> cur)) - 1));
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            uint32_t contrib = (((vis >> lane) & 1u) && nc < 32u) ? (1u << nc) : 0u;
+            vis |= __reduce_or_sync(ZB_FULL, contrib);
+            uint32_t t = __shfl_sync(ZB_FULL, nc, (int)(nc & 31u));
+            nc = nc < 32u ? t : 32u;
+          }
+          ism = vis;
+          const uint32_t cov = ((ism >> lane) & 1u) ? (low_mask(endp) & ~low_mask((uint32_t)lane)) : 0u;
+          const uint32_t covered = __reduce_or_sync(ZB_FULL, cov);
+          sel = ism | (~covered & ~low_mask(cur) & low_mask(nvalid));
+          const int lastm = 31 - __clz((int)ism);
+          endw = (uint32_t)lastm + __shfl_sync(ZB_FULL, m, lastm);
+          if ((ism >> lane) & 1u) {
+            uint32_t rank = (uint32_t)__popc(ism & low_mask((uint32_t)lane));
+            ring[slot * ZB_MATCH_SLOTS + rank] = (m - 3u) | ((p - c - 1u) << 9);
+          }
+        } else {
+          sel = low_mask(nvalid) & ~low_mask(cur);
         }
-        const uint32_t nx = upto;
-        uint32_t mlen = __shfl_sync(ZB_FULL, m, (int)nx);
-        if (mlen >= LZ_PAR_CAP) {
-          // cooperative extension: lane j checks bytes [32 + 8j, 40 + 8j) of the match
-          const uint32_t mc = __shfl_sync(ZB_FULL, c, (int)nx);
-          const uint32_t pos = wb + nx;
-          const uint32_t off = LZ_PAR_CAP + 8u * (uint32_t)lane;
-          uint32_t x0 = zb_ld32_unaligned(data, mis + pos + off) ^ zb_ld32_unaligned(data, mis + mc + off);
-          uint32_t x1 = zb_ld32_unaligned(data, mis + pos + off + 4) ^ zb_ld32_unaligned(data, mis + mc + off + 4);
-          uint32_t nm = x0 ? ((uint32_t)(__ffs((int)x0) - 1) >> 3) : 4u + (x1 ? ((uint32_t)(__ffs((int)x1) - 1) >> 3) : 4u);
-          uint32_t stop = __ballot_sync(ZB_FULL, nm < 8u);
-          if (stop) {
-            int first = __ffs((int)stop) - 1;
-            mlen = LZ_PAR_CAP + 8u * (uint32_t)first + __shfl_sync(ZB_FULL, nm, first);
+        entry = wb + max(endw, nvalid);
+      }
+      if ((uint32_t)lane == slot) {
+        ksel = sel;
+        kism = ism;
+      }
+      // ---- every 32 windows (or at the end): one lane per window walks its tokens ----
+      if (slot == 31u || wb + 32 >= b1) {
+        __syncwarp();
+        const uint32_t bwin = win - slot + (uint32_t)lane;  // this lane's window
+        const bool active = (uint32_t)lane <= slot;
+        if (active) gmask[bwin] = make_uint2(ksel, kism);
+        uint32_t s = active ? ksel : 0u;
+        const uint32_t im = kism;
+        const uint8_t *wdata = data + mis + (bwin << 5);
+        uint32_t mcnt = 0;
+        while (s) {
+          const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
+          s &= s - 1;
+          if ((im >> bit) & 1u) {
+            const uint32_t raw = ring[(uint32_t)lane * ZB_MATCH_SLOTS + mcnt];
+            int lc, dc;
+            const uint32_t fin = lz_final_rec((raw & 511u) + 3u, (raw >> 9) + 1u, lc, dc);
+            grecs[bwin * ZB_MATCH_SLOTS + mcnt] = fin;
+            mcnt++;
+            const uint32_t s1 = 257u + (uint32_t)lc, s2 = (uint32_t)ZB_NUM_LITLEN + (uint32_t)dc;
+            atomicAdd(&whist[s1 >> 1], 1u << ((s1 & 1u) * 16u));
+            atomicAdd(&whist[s2 >> 1], 1u << ((s2 & 1u) * 16u));
           } else {
-            mlen = LZ_PAR_CAP + 256u;
+            const uint32_t sy = wdata[bit];
+            atomicAdd(&whist[sy >> 1], 1u << ((sy & 1u) * 16u));
           }
-          mlen = min(mlen, min((uint32_t)ZB_MAX_MATCH, b1 - pos));
         }
-        sel |= 1u << nx;
-        ism |= 1u << nx;
-        if ((uint32_t)lane == nx) my_len = mlen;
-        cur = nx + mlen;
+        ksel = kism = 0;
+        __syncwarp();
       }
-      entry = wb + cur;
-
-      // ---- per-warp histogram + token records ----
-      const bool is_sel = (sel >> lane) & 1u, is_m = (ism >> lane) & 1u;
-      if (is_m) {
-        uint32_t dist = p - c;
-        uint32_t s1 = 257u + (uint32_t)zb_len_code(my_len);
-        uint32_t s2 = (uint32_t)ZB_NUM_LITLEN + (uint32_t)zb_dist_code(dist);
-        atomicAdd(&whist[s1 >> 1], 1u << ((s1 & 1u) * 16u));
-        atomicAdd(&whist[s2 >> 1], 1u << ((s2 & 1u) * 16u));
-        uint32_t rank = (uint32_t)__popc(ism & ((1u << lane) - 1u));
-        recs[(win_base + win) * ZB_MATCH_SLOTS + rank] = (my_len - 3u) | ((dist - 1u) << 9);
-      } else if (is_sel) {
-        uint32_t s = v & 255u;
-        atomicAdd(&whist[s >> 1], 1u << ((s & 1u) * 16u));
-      }
-      if (lane == 0) masks[win_base + win] = make_uint2(sel, ism);
     }
   }
   __syncthreads();
@@ -316,15 +370,9 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 }
 
 // ------------------------------------------------------------------------------------
-#define PK_SM_DATA 0
-#define PK_SM_DATA_BYTES (ZB_CHUNK_BYTES + 64)
-#define PK_SM_CODES (PK_SM_DATA + PK_SM_DATA_BYTES)
+#define PK_ROW_WORDS 17   // a 32-byte window encodes to at most 32 x 15 bits = 15 words (+ partial)
 #define PK_SM_CODES_BYTES ((288 + 32) * 4)
-#define PK_SM_STAGE (PK_SM_CODES + PK_SM_CODES_BYTES)
-#define PK_STAGE_WORDS 64
-#define PK_SM_STAGE_BYTES (ZB_WARPS_PER_CHUNK * PK_STAGE_WORDS * 4)
-#define PK_SM_BAR (PK_SM_STAGE + PK_SM_STAGE_BYTES)
-#define PK_SM_TOTAL (PK_SM_BAR + 16)
+#define PK_SM_ROWS_BYTES (ZB_WARPS_PER_CHUNK * PK_ROW_WORDS * 32 * 4)
 
 // OR `nbits` (<= 32) bits of v into the global bitstream at absolute bit position gb.
 __device__ __forceinline__ void or_bits_global(uint32_t *dstw, uint64_t gb, uint32_t v, uint32_t nbits) {
@@ -336,13 +384,14 @@ __device__ __forceinline__ void or_bits_global(uint32_t *dstw, uint64_t gb, uint
   if (sh && sh + nbits > 32) atomicOr(&dstw[word + 1], v >> (32u - sh));
 }
 
-__global__ void __launch_bounds__(LZ_THREADS, 3)
+// Token -> bits.  One LANE per 32-byte window: the lane walks the window's tokens,
+// concatenating codes into its private row of shared memory; a warp prefix sum of the
+// 32 row lengths gives every row its bit offset (the sub-chunk's own offset was fixed by
+// k_huff), and the rows are OR-ed into the zero-filled output stream.
+__global__ void __launch_bounds__(LZ_THREADS)
     k_pack(ZbCompressWork w) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t *data = smem + PK_SM_DATA;
-  uint32_t *codes = reinterpret_cast<uint32_t *>(smem + PK_SM_CODES);  // [0,288) litlen, [288,320) dist
-  uint32_t *stage_all = reinterpret_cast<uint32_t *>(smem + PK_SM_STAGE);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + PK_SM_BAR);
+  __shared__ uint32_t codes[288 + 32];  // [0,288) litlen, [288,320) dist: code | len << 16
+  __shared__ uint32_t rows_all[ZB_WARPS_PER_CHUNK * PK_ROW_WORDS * 32];
 
   const uint32_t chunk = blockIdx.x;
   const ZbChunkDesc d = w.desc[chunk];
@@ -352,16 +401,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 3)
   const uint32_t btype = cb->block_type;
   const uint64_t out0 = w.chunk_off[chunk];  // byte offset of this chunk's deflate bytes
   uint32_t *dstw = reinterpret_cast<uint32_t *>(w.dst);
+  const uint8_t *src = w.src + d.src_off;
 
-  if (tid == 0) {
-    zb_mbar_init(bar, 1);
-    zb_fence_mbar_init();
-  }
-  __syncthreads();
-  const uint32_t mis = (uint32_t)((uintptr_t)(w.src + d.src_off) & 15u);
-  if (tid == 0 && len) zb_stage_chunk(data, w.src + d.src_off, len, bar);
   for (int i = tid; i < 320; i += LZ_THREADS) codes[i] = i < 288 ? cb->ll[i] : cb->dd[i - 288];
-  for (int i = tid; i < ZB_WARPS_PER_CHUNK * PK_STAGE_WORDS; i += LZ_THREADS) stage_all[i] = 0;
 
   // ---- framing bytes (zippy.nim:21-42, 50-58, 60-78) ----
   if (tid == 32 && (d.flags & ZB_CHUNK_FIRST)) {
@@ -386,7 +428,6 @@ __global__ void __launch_bounds__(LZ_THREADS, 3)
     }
   }
   __syncthreads();
-  if (len) zb_mbar_wait(bar, 0);
 
   if (btype == 0) {
     // stored blocks (deflate.nim:179-205): 1 header byte, LEN, NLEN, bytes
@@ -400,7 +441,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 3)
         ob[1] = (uint8_t)n; ob[2] = (uint8_t)(n >> 8);
         ob[3] = (uint8_t)~n; ob[4] = (uint8_t)((~n) >> 8);
       }
-      for (uint32_t i = (uint32_t)tid; i < n; i += LZ_THREADS) ob[5 + i] = data[mis + s0 + i];
+      for (uint32_t i = (uint32_t)tid; i < n; i += LZ_THREADS) ob[5 + i] = src[s0 + i];
     }
     return;
   }
@@ -433,60 +474,70 @@ __global__ void __launch_bounds__(LZ_THREADS, 3)
   const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES;
   if (b0 >= len) return;
   const uint32_t b1 = min(b0 + ZB_SUB_BYTES, len);
-  uint32_t *stage = stage_all + warp * PK_STAGE_WORDS;
+  uint32_t *rows = rows_all + warp * PK_ROW_WORDS * 32;  // word k of lane i at rows[k * 32 + i]
   uint64_t bitpos = gbit0 + cb->warp_bit_start[warp];
-  const size_t win_base = (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
-  for (uint32_t wb = b0; wb < b1; wb += 32) {
-    const uint32_t win = wb >> 5;
-    const uint2 mk = w.masks[win_base + win];
-    if (mk.x == 0) continue;
-    const bool is_sel = (mk.x >> lane) & 1u, is_m = (mk.y >> lane) & 1u;
-    uint64_t bits = 0;
-    uint32_t nb = 0;
-    if (is_m) {
-      uint32_t rank = (uint32_t)__popc(mk.y & ((1u << lane) - 1u));
-      uint32_t rec = w.recs[(win_base + win) * ZB_MATCH_SLOTS + rank];
-      uint32_t mlen = (rec & 511u) + 3u, dist = (rec >> 9) + 1u;
-      int lc = zb_len_code(mlen), dc = zb_dist_code(dist);
-      uint32_t e1 = codes[257 + lc], e2 = codes[288 + dc];
-      bits = e1 & 0xffffu;
-      nb = e1 >> 16;
-      bits |= (uint64_t)(mlen - zb_len_base(lc)) << nb;
-      nb += (uint32_t)zb_len_extra_bits(lc);
-      bits |= (uint64_t)(e2 & 0xffffu) << nb;
-      nb += e2 >> 16;
-      bits |= (uint64_t)(dist - zb_dist_base(dc)) << nb;
-      nb += (uint32_t)zb_dist_extra_bits(dc);
-    } else if (is_sel) {
-      uint32_t e = codes[data[mis + wb + (uint32_t)lane]];
-      bits = e & 0xffffu;
-      nb = e >> 16;
+  const uint2 *gmask = w.masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
+  const uint32_t *grecs = w.recs + (size_t)chunk * ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS;
+  const uint32_t nwin = (b1 - b0 + 31u) >> 5;
+  for (uint32_t wbase = 0; wbase < nwin; wbase += 32) {
+    const uint32_t widx = wbase + (uint32_t)lane;      // window within the sub-chunk
+    const uint32_t win = (b0 >> 5) + widx;              // window within the chunk
+    uint2 mk = make_uint2(0u, 0u);
+    if (widx < nwin) mk = gmask[win];
+    uint32_t s = mk.x;
+    const uint32_t im = mk.y;
+    const uint8_t *wdata = src + ((size_t)win << 5);
+    const uint32_t *wrec = grecs + (size_t)win * ZB_MATCH_SLOTS;
+    uint64_t acc = 0;
+    uint32_t accn = 0, nw = 0, mcnt = 0;
+    while (s) {
+      const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
+      s &= s - 1;
+      uint32_t v1, n1;
+      if ((im >> bit) & 1u) {
+        const uint32_t rec = wrec[mcnt++];
+        const uint32_t lc = rec & 31u, dc = (rec >> 10) & 31u;
+        const uint32_t e1 = codes[257 + lc], e2 = codes[288 + dc];
+        v1 = (e1 & 0xffffu) | (((rec >> 5) & 31u) << (e1 >> 16));
+        n1 = (e1 >> 16) + (uint32_t)zb_len_extra_bits((int)lc);
+        acc |= (uint64_t)v1 << accn;
+        accn += n1;
+        if (accn >= 32) {
+          rows[nw * 32 + lane] = (uint32_t)acc;
+          nw++;
+          acc >>= 32;
+          accn -= 32;
+        }
+        v1 = (e2 & 0xffffu) | ((rec >> 15) << (e2 >> 16));
+        n1 = (e2 >> 16) + (uint32_t)zb_dist_extra_bits((int)dc);
+      } else {
+        const uint32_t e = codes[wdata[bit]];
+        v1 = e & 0xffffu;
+        n1 = e >> 16;
+      }
+      acc |= (uint64_t)v1 << accn;
+      accn += n1;
+      if (accn >= 32) {
+        rows[nw * 32 + lane] = (uint32_t)acc;
+        nw++;
+        acc >>= 32;
+        accn -= 32;
+      }
     }
-    uint32_t incl = nb;
+    if (accn) rows[nw * 32 + lane] = (uint32_t)acc;
+    const uint32_t mybits = nw * 32u + accn;
+    uint32_t incl = mybits;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(ZB_FULL, incl, o);
       if (lane >= o) incl += t;
     }
     const uint32_t total = __shfl_sync(ZB_FULL, incl, 31);
-    const uint32_t lead = (uint32_t)(bitpos & 31u);
-    if (nb) {
-      uint32_t lb = lead + incl - nb;  // local bit offset in the staging words
-      uint32_t wd = lb >> 5, sh = lb & 31u;
-      uint64_t lo = bits << sh;
-      atomicOr(&stage[wd], (uint32_t)lo);
-      if (sh + nb > 32) atomicOr(&stage[wd + 1], (uint32_t)(lo >> 32));
-      if (sh + nb > 64) atomicOr(&stage[wd + 2], (uint32_t)(bits >> (64u - sh)));
+    uint64_t gb = bitpos + (incl - mybits);
+    for (uint32_t k = 0; k * 32u < mybits; k++) {
+      or_bits_global(dstw, gb, rows[k * 32 + lane], min(32u, mybits - k * 32u));
+      gb += 32;
     }
-    __syncwarp();
-    const uint32_t nwords = (lead + total + 31u) >> 5;
-    const uint64_t word0 = bitpos >> 5;
-    for (uint32_t j = (uint32_t)lane; j < nwords; j += 32) {
-      uint32_t sv = stage[j];
-      if (sv) atomicOr(&dstw[word0 + j], sv);
-      stage[j] = 0;
-    }
-    __syncwarp();
     bitpos += total;
   }
 }
@@ -497,7 +548,6 @@ cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s) {
   if (!attr_set) {
     cudaFuncSetAttribute(k_lz<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
     cudaFuncSetAttribute(k_lz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
-    cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SM_TOTAL);
     attr_set = true;
   }
   if (w.n_chunks == 0) return cudaSuccess;
@@ -518,6 +568,6 @@ cudaError_t zb_launch_scan(const ZbCompressWork &w, cudaStream_t s) {
 }
 cudaError_t zb_launch_pack(const ZbCompressWork &w, cudaStream_t s) {
   if (w.n_chunks == 0) return cudaSuccess;
-  k_pack<<<w.n_chunks, LZ_THREADS, PK_SM_TOTAL, s>>>(w);
+  k_pack<<<w.n_chunks, LZ_THREADS, 0, s>>>(w);
   return cudaGetLastError();
 }
