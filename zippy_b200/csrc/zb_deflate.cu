@@ -18,8 +18,8 @@
 #define LZ_THREADS (ZB_WARPS_PER_CHUNK * 32)
 #define LZ_HASH_BITS 11
 #define LZ_TABLE_ENTRIES (1 << LZ_HASH_BITS)
-#define LZ_PRESEED 4096
-#define LZ_LANE_CAP 16  // bytes a lane extends on its own; longer matches finish warp-cooperatively
+#define LZ_PRESEED 2048
+#define LZ_LANE_CAP 32  // bytes a lane extends on its own; a selected match that hit the cap finishes warp-cooperatively
 
 // shared-memory layout of k_lz (bytes).  The CRC step table (4 KiB) is loaded by each warp
 // into its own hash-table region for the checksum phase and overwritten afterwards.
@@ -32,7 +32,7 @@
 #define LZ_SM_RING (LZ_SM_HIST + LZ_SM_HIST_BYTES)
 #define LZ_SM_RING_BYTES (ZB_WARPS_PER_CHUNK * 32 * ZB_MATCH_SLOTS * 4)
 #define LZ_SM_LMUL (LZ_SM_RING + LZ_SM_RING_BYTES)
-#define LZ_SM_LMUL_BYTES (36 * 4)
+#define LZ_SM_LMUL_BYTES (44 * 4)
 #define LZ_SM_PART (LZ_SM_LMUL + LZ_SM_LMUL_BYTES)
 #define LZ_SM_PART_BYTES (ZB_WARPS_PER_CHUNK * 24)
 #define LZ_SM_BAR (LZ_SM_PART + LZ_SM_PART_BYTES)
@@ -41,7 +41,13 @@ static_assert(LZ_TABLE_ENTRIES * 2 >= 4096, "a warp's table region must hold the
 static_assert(2 * (LZ_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
 
 __device__ __forceinline__ uint32_t lz_hash(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
-__device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32 ? ~0u : ((1u << n) - 1u); }
+// PTX shifts clamp (a shift by >= 32 gives 0), unlike C++ shifts
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) {
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+  return r;
+}
+__device__ __forceinline__ uint32_t low_mask(uint32_t n) { return shl_clamp(1u, n) - 1u; }  // n >= 32 -> all ones
 
 // Final match record consumed by k_pack: length code | length extra value << 5 |
 // distance code << 10 | distance extra value << 15.
@@ -88,19 +94,28 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     for (int i = lane; i < 1024; i += 32) crc_tab[i] = (&tabs->mul1024[0][0])[i];
   }
   if (tid < 33) lane_mul[tid] = tabs->lane_mul[tid];
+  if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = tabs->sub_mul[tid - 64];
   __syncthreads();
   if (len) zb_mbar_wait(bar, 0);
 
   const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES;
   const uint32_t b1 = min(b0 + ZB_SUB_BYTES, len);
 
-  // ---- checksums of this warp's piece (CRC raw + Adler sums) ----
+  // ---- checksums of this warp's piece, already shifted to the end of the chunk ----
   {
     ZbCheck c;
     c.crc_raw = 0;
     c.a_sum = c.b_sum = 0;
     uint32_t n = b0 < len ? b1 - b0 : 0;
-    if (n) c = zb_warp_checksums(data, mis + b0, n, reinterpret_cast<const uint32_t *>(table), lane_mul);
+    if (n) {
+      c = zb_warp_checksums(data, mis + b0, n, reinterpret_cast<const uint32_t *>(table), lane_mul);
+      const uint32_t after = len - b1;
+      if (after) {
+        const uint32_t shift = ((after & (ZB_SUB_BYTES - 1)) == 0) ? lane_mul[33 + after / ZB_SUB_BYTES] : zb_xpow8(after);
+        c.crc_raw = zb_gf2_mul(c.crc_raw, shift);
+        c.b_sum += (uint64_t)after * c.a_sum;
+      }
+    }
     if (lane == 0) {
       part[warp * 3 + 0] = c.crc_raw;
       part[warp * 3 + 1] = c.a_sum;
@@ -147,66 +162,72 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           // a match may not cross the sub-chunk end (the next warp starts its own parse there)
           const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
           if (can && c < p && p - c <= ZB_MAX_DIST && p >= entry && limit >= ZB_MIN_MATCH) {
-            if (zb_ld32_unaligned(data, mis + c) == v) {
+            // unaligned compare, 4 bytes per step, carrying the upper word of each side
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(data) + ((mis + p) >> 2);
+            const uint32_t *wc = reinterpret_cast<const uint32_t *>(data) + ((mis + c) >> 2);
+            const uint32_t sp = ((mis + p) & 3u) * 8u, sc = ((mis + c) & 3u) * 8u;
+            uint32_t hp = wp[1], hc = wc[1];
+            if (__funnelshift_r(wc[0], hc, sc) == v) {
               m = 4;
 #pragma unroll 1
-              while (m < LZ_LANE_CAP) {
-                uint32_t x = zb_ld32_unaligned(data, mis + p + m) ^ zb_ld32_unaligned(data, mis + c + m);
+              for (int k = 2; k <= LZ_LANE_CAP / 4; k++) {
+                const uint32_t np = wp[k], nq = wc[k];
+                const uint32_t x = __funnelshift_r(hp, np, sp) ^ __funnelshift_r(hc, nq, sc);
                 if (x) {
                   m += (uint32_t)(__ffs((int)x) - 1) >> 3;
                   break;
                 }
                 m += 4;
+                hp = np;
+                hc = nq;
               }
               if (m < LZ_LANE_CAP) m = min(m, limit);
             }
-          }
-          // matches that reached the lane cap are extended by the whole warp, 8 bytes per lane
-          uint32_t longm = __ballot_sync(ZB_FULL, m >= LZ_LANE_CAP);
-          while (longm) {
-            const int L = __ffs((int)longm) - 1;
-            longm &= longm - 1;
-            const uint32_t mc = __shfl_sync(ZB_FULL, c, L);
-            const uint32_t pos = wb + (uint32_t)L;
-            const uint32_t off = LZ_LANE_CAP + 8u * (uint32_t)lane;
-            uint32_t x0 = zb_ld32_unaligned(data, mis + pos + off) ^ zb_ld32_unaligned(data, mis + mc + off);
-            uint32_t x1 = zb_ld32_unaligned(data, mis + pos + off + 4) ^ zb_ld32_unaligned(data, mis + mc + off + 4);
-            uint32_t nm = x0 ? ((uint32_t)(__ffs((int)x0) - 1) >> 3) : 4u + (x1 ? ((uint32_t)(__ffs((int)x1) - 1) >> 3) : 4u);
-            uint32_t stop = __ballot_sync(ZB_FULL, nm < 8u);
-            uint32_t ml;
-            if (stop) {
-              int first = __ffs((int)stop) - 1;
-              ml = LZ_LANE_CAP + 8u * (uint32_t)first + __shfl_sync(ZB_FULL, nm, first);
-            } else {
-              ml = LZ_LANE_CAP + 256u;
-            }
-            ml = min(ml, min((uint32_t)ZB_MAX_MATCH, b1 - pos));
-            if (lane == L) m = ml;
           }
         }
         // ---- greedy selection: follow the chain "candidate -> first candidate at/after its end" ----
         const uint32_t mm = __ballot_sync(ZB_FULL, m != 0);
         uint32_t endw = 0;
         if (mm) {
+          const uint32_t lbit = 1u << lane;
           const uint32_t endp = (uint32_t)lane + m;
-          const uint32_t rest = endp < 32 ? (mm >> endp) : 0u;
+          const uint32_t rest = shl_clamp(1u, endp) ? (mm >> endp) : 0u;
           uint32_t nc = rest ? endp + (uint32_t)(__ffs((int)rest) - 1) : 32u;
           uint32_t vis = 1u << (cur + (uint32_t)(__ffs((int)(mm >> cur)) - 1));
 #pragma unroll
           for (int r = 0; r < 3; r++) {
-            uint32_t contrib = (((vis >> lane) & 1u) && nc < 32u) ? (1u << nc) : 0u;
-            vis |= __reduce_or_sync(ZB_FULL, contrib);
-            uint32_t t = __shfl_sync(ZB_FULL, nc, (int)(nc & 31u));
+            vis |= __reduce_or_sync(ZB_FULL, (vis & lbit) ? shl_clamp(1u, nc) : 0u);
+            const uint32_t t = __shfl_sync(ZB_FULL, nc, (int)(nc & 31u));
             nc = nc < 32u ? t : 32u;
           }
           ism = vis;
-          const uint32_t cov = ((ism >> lane) & 1u) ? (low_mask(endp) & ~low_mask((uint32_t)lane)) : 0u;
+          const int lastm = 31 - __clz((int)ism);
+          uint32_t mlast = __shfl_sync(ZB_FULL, m, lastm);
+          if (mlast >= LZ_LANE_CAP) {
+            // the last selected match hit the lane cap (so it leaves the window): the whole
+            // warp extends it, 8 bytes per lane
+            const uint32_t mc = __shfl_sync(ZB_FULL, c, lastm);
+            const uint32_t pos = wb + (uint32_t)lastm;
+            const uint32_t off = LZ_LANE_CAP + 8u * (uint32_t)lane;
+            uint32_t x0 = zb_ld32_unaligned(data, mis + pos + off) ^ zb_ld32_unaligned(data, mis + mc + off);
+            uint32_t x1 = zb_ld32_unaligned(data, mis + pos + off + 4) ^ zb_ld32_unaligned(data, mis + mc + off + 4);
+            uint32_t nm = x0 ? ((uint32_t)(__ffs((int)x0) - 1) >> 3) : 4u + (x1 ? ((uint32_t)(__ffs((int)x1) - 1) >> 3) : 4u);
+            uint32_t stop = __ballot_sync(ZB_FULL, nm < 8u);
+            if (stop) {
+              int first = __ffs((int)stop) - 1;
+              mlast = LZ_LANE_CAP + 8u * (uint32_t)first + __shfl_sync(ZB_FULL, nm, first);
+            } else {
+              mlast = LZ_LANE_CAP + 256u;
+            }
+            mlast = min(mlast, min((uint32_t)ZB_MAX_MATCH, b1 - pos));
+            if (lane == lastm) m = mlast;
+          }
+          const uint32_t cov = (ism & lbit) ? (low_mask((uint32_t)lane + m) & ~low_mask((uint32_t)lane)) : 0u;
           const uint32_t covered = __reduce_or_sync(ZB_FULL, cov);
           sel = ism | (~covered & ~low_mask(cur) & low_mask(nvalid));
-          const int lastm = 31 - __clz((int)ism);
-          endw = (uint32_t)lastm + __shfl_sync(ZB_FULL, m, lastm);
-          if ((ism >> lane) & 1u) {
-            uint32_t rank = (uint32_t)__popc(ism & low_mask((uint32_t)lane));
+          endw = (uint32_t)lastm + mlast;
+          if (ism & lbit) {
+            uint32_t rank = (uint32_t)__popc(ism & (lbit - 1u));
             ring[slot * ZB_MATCH_SLOTS + rank] = (m - 3u) | ((p - c - 1u) << 9);
           }
         } else {
@@ -224,26 +245,24 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
         const uint32_t bwin = win - slot + (uint32_t)lane;  // this lane's window
         const bool active = (uint32_t)lane <= slot;
         if (active) gmask[bwin] = make_uint2(ksel, kism);
-        uint32_t s = active ? ksel : 0u;
-        const uint32_t im = kism;
+        const uint32_t im = active ? kism : 0u;
+        uint32_t s = active ? (ksel & ~kism) : 0u;  // literal tokens
         const uint8_t *wdata = data + mis + (bwin << 5);
-        uint32_t mcnt = 0;
         while (s) {
           const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
           s &= s - 1;
-          if ((im >> bit) & 1u) {
-            const uint32_t raw = ring[(uint32_t)lane * ZB_MATCH_SLOTS + mcnt];
-            int lc, dc;
-            const uint32_t fin = lz_final_rec((raw & 511u) + 3u, (raw >> 9) + 1u, lc, dc);
-            grecs[bwin * ZB_MATCH_SLOTS + mcnt] = fin;
-            mcnt++;
-            const uint32_t s1 = 257u + (uint32_t)lc, s2 = (uint32_t)ZB_NUM_LITLEN + (uint32_t)dc;
-            atomicAdd(&whist[s1 >> 1], 1u << ((s1 & 1u) * 16u));
-            atomicAdd(&whist[s2 >> 1], 1u << ((s2 & 1u) * 16u));
-          } else {
-            const uint32_t sy = wdata[bit];
-            atomicAdd(&whist[sy >> 1], 1u << ((sy & 1u) * 16u));
-          }
+          const uint32_t sy = wdata[bit];
+          atomicAdd(&whist[sy >> 1], 1u << ((sy & 1u) * 16u));
+        }
+        const uint32_t nmatch = (uint32_t)__popc(im);
+        for (uint32_t k = 0; k < nmatch; k++) {
+          const uint32_t raw = ring[(uint32_t)lane * ZB_MATCH_SLOTS + k];
+          int lc, dc;
+          const uint32_t fin = lz_final_rec((raw & 511u) + 3u, (raw >> 9) + 1u, lc, dc);
+          grecs[bwin * ZB_MATCH_SLOTS + k] = fin;
+          const uint32_t s1 = 257u + (uint32_t)lc, s2 = (uint32_t)ZB_NUM_LITLEN + (uint32_t)dc;
+          atomicAdd(&whist[s1 >> 1], 1u << ((s1 & 1u) * 16u));
+          atomicAdd(&whist[s2 >> 1], 1u << ((s2 & 1u) * 16u));
         }
         ksel = kism = 0;
         __syncwarp();
@@ -260,14 +279,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     uint32_t raw = 0;
     uint64_t a = 0, b = 0;
     for (int w = 0; w < ZB_WARPS_PER_CHUNK; w++) {
-      uint32_t wb0 = (uint32_t)w * ZB_SUB_BYTES;
-      if (wb0 >= len) break;
-      uint32_t wb1 = min(wb0 + ZB_SUB_BYTES, len);
-      uint32_t after = len - wb1;
-      uint32_t r = (uint32_t)part[w * 3 + 0];
-      raw ^= after ? zb_gf2_mul(r, zb_xpow8(after)) : r;
+      raw ^= (uint32_t)part[w * 3 + 0];
       a += part[w * 3 + 1];
-      b += part[w * 3 + 2] + (uint64_t)after * part[w * 3 + 1];
+      b += part[w * 3 + 2];
     }
     ZbChunkCheck cc;
     cc.crc_raw = raw;

@@ -19,13 +19,18 @@
 
 #define INF_WARPS 8
 #define INF_THREADS (INF_WARPS * 32)
+#define LL_BITS 10   // literal/length codes up to this long decode with one table lookup
+#define D_BITS 9     // same for distance codes
 
 struct WarpSmem {
-  uint8_t lens[320];      // code lengths of the current block (lit/len then distance)
-  uint16_t syms_ll[288];  // symbols sorted by (length, symbol)
+  uint16_t lut_ll[1 << LL_BITS];  // symbol | code length << 9; 0 = longer code or no code: slow path
+  uint16_t lut_d[1 << D_BITS];
+  uint16_t syms_ll[288];          // symbols sorted by (length, symbol) for the canonical slow path
   uint16_t syms_d[32];
-  uint16_t cnt[16];       // per-length counts / running ranks while building
+  uint8_t lens[320];              // code lengths of the current block (lit/len then distance)
+  uint16_t cnt[16];               // per-length counts / running ranks while building
   uint16_t offs[16];
+  uint16_t first[16];
 };
 
 struct Tree {  // lane L holds the entries for code length L
@@ -39,24 +44,32 @@ struct BitReader {
   uint32_t widx;          // next word to feed into the bit buffer
   uint64_t buf;
   int cnt;                // valid bits in buf
-  int64_t left;           // bits of the member not yet consumed (negative = ran past the end)
+  uint64_t end_bit;       // absolute bit (from gbase) one past the member's last byte
+  bool overrun;           // set when the reader is found to have consumed bits past end_bit
 };
 
 __device__ __forceinline__ uint32_t br_load_line(const BitReader &b, uint32_t line) {
   uint32_t idx = line * 32u + (uint32_t)zb_lane();
   return idx < b.nwords ? __ldg(b.gbase + idx) : 0u;
 }
+__device__ __forceinline__ uint64_t br_consumed_abs(const BitReader &b) {
+  return (uint64_t)b.widx * 32ull - (uint64_t)b.cnt;
+}
+__device__ __forceinline__ bool br_past_end(const BitReader &b) { return br_consumed_abs(b) > b.end_bit; }
 __device__ __forceinline__ uint32_t br_next_word(BitReader &b) {
   uint32_t w = __shfl_sync(ZB_FULL, b.cur, (int)(b.widx & 31u));
   b.widx++;
   if ((b.widx & 31u) == 0) {
     b.cur = b.nxt;
     b.nxt = br_load_line(b, (b.widx >> 5) + 1u);
+    // bits past the end read as zero; a reader that is a whole line past the end can only be
+    // decoding garbage: flag it here so that no decode loop runs away (checked by the callers)
+    if ((uint64_t)b.widx * 32ull > b.end_bit + 64ull) b.overrun = true;
   }
   return w;
 }
 // position the reader at byte `byte_off` of the member (shift0 = member start & 3)
-__device__ __forceinline__ void br_seek(BitReader &b, uint32_t shift0, uint64_t byte_off, uint64_t member_len) {
+__device__ __forceinline__ void br_seek(BitReader &b, uint32_t shift0, uint64_t byte_off) {
   uint64_t abit = (shift0 + byte_off) * 8ull;
   b.widx = (uint32_t)(abit >> 5);
   uint32_t skip = (uint32_t)(abit & 31u);
@@ -66,7 +79,6 @@ __device__ __forceinline__ void br_seek(BitReader &b, uint32_t shift0, uint64_t 
   uint32_t w = br_next_word(b);
   b.buf = (uint64_t)(w >> skip);
   b.cnt = 32 - (int)skip;
-  b.left = (int64_t)(member_len - byte_off) * 8;
 }
 __device__ __forceinline__ void br_refill(BitReader &b) {  // afterwards cnt >= 32
   if (b.cnt < 32) {
@@ -78,15 +90,22 @@ __device__ __forceinline__ uint32_t br_take(BitReader &b, int n) {  // n <= 32, 
   uint32_t v = (uint32_t)b.buf & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
   b.buf >>= n;
   b.cnt -= n;
-  b.left -= n;
   return v;
 }
 
-// Build the canonical decode state from n code lengths (inflate.nim:24-65 initHuffman).
-// Returns false for an over-subscribed set (inflate.nim:32-34, 45-46).
-__device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t *syms, WarpSmem *ws, Tree &t) {
+// Build the decode state from n code lengths (inflate.nim:24-65 initHuffman): the per-length
+// canonical ranges (for the lane-parallel slow path), the sorted symbols, and a direct lookup
+// table for codes of at most lut_bits.  Returns false for an over-subscribed set
+// (inflate.nim:32-34, 45-46).
+__device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t *syms, uint16_t *lut, int lut_bits,
+                                           WarpSmem *ws, Tree &t) {
   const int lane = zb_lane();
   if (lane < 16) ws->cnt[lane] = 0;
+  {
+    uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4 *l4 = reinterpret_cast<uint4 *>(lut);
+    for (int i = lane; i < ((1 << lut_bits) * 2) / 16; i += 32) l4[i] = z;
+  }
   __syncwarp();
   for (int base = 0; base < n; base += 32) {
     int s = base + lane;
@@ -113,6 +132,7 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
   __syncwarp();
   if (lane < 16) {
     ws->offs[lane] = (uint16_t)my_offs;
+    ws->first[lane] = (uint16_t)my_first;
     ws->cnt[lane] = 0;  // becomes the running rank per length
   }
   __syncwarp();
@@ -122,8 +142,14 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
     uint32_t l = s < n ? lens[s] : 0u;
     uint32_t grp = __match_any_sync(ZB_FULL, l);
     if (l) {
-      uint32_t slot = (uint32_t)ws->offs[l] + ws->cnt[l] + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-      syms[slot] = (uint16_t)s;
+      uint32_t rank = ws->cnt[l] + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+      syms[(uint32_t)ws->offs[l] + rank] = (uint16_t)s;
+      if ((int)l <= lut_bits) {
+        uint32_t c = (uint32_t)ws->first[l] + rank;          // canonical code, MSB first
+        uint32_t rev = __brev(c) >> (32 - l);                // as it appears in the LSB-first stream
+        uint16_t e = (uint16_t)((uint32_t)s | (l << 9));
+        for (uint32_t idx = rev; idx < (1u << lut_bits); idx += (1u << l)) lut[idx] = e;
+      }
     }
     __syncwarp();
     if (l && lane == __ffs((int)grp) - 1) ws->cnt[l] = (uint16_t)(ws->cnt[l] + __popc(grp));
@@ -135,10 +161,9 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
   return true;
 }
 
-// Decode one symbol with the next bits of b (needs >= 15 buffered bits; bits past the
-// end of the member read as zero and are caught by the caller through b.left).
-// Returns 0xffff when no code matches (inflate.nim:77-82).
-__device__ __forceinline__ uint32_t decode_sym(BitReader &b, const Tree &t, const uint16_t *syms) {
+// Lane-parallel canonical decode (codes longer than the lookup table, and the
+// "no code matches" case, which returns 0xffff: inflate.nim:77-82).
+__device__ __forceinline__ uint32_t decode_slow(BitReader &b, const Tree &t, const uint16_t *syms) {
   const int lane = zb_lane();
   uint32_t rev = __brev((uint32_t)b.buf);
   uint32_t code = lane ? (rev >> (32 - lane)) : 0u;
@@ -149,8 +174,20 @@ __device__ __forceinline__ uint32_t decode_sym(BitReader &b, const Tree &t, cons
   uint32_t idx = __shfl_sync(ZB_FULL, t.offs + rel, L);
   b.buf >>= L;
   b.cnt -= L;
-  b.left -= L;
   return syms[idx];
+}
+// One symbol (needs >= 15 buffered bits; bits past the end of the member read as zero).
+template <int BITS>
+__device__ __forceinline__ uint32_t decode_sym(BitReader &b, const uint16_t *lut, const Tree &t,
+                                               const uint16_t *syms) {
+  uint32_t e = lut[(uint32_t)b.buf & ((1u << BITS) - 1u)];
+  uint32_t l = e >> 9;
+  if (l) {
+    b.buf >>= l;
+    b.cnt -= (int)l;
+    return e & 511u;
+  }
+  return decode_slow(b, t, syms);
 }
 
 __device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
@@ -216,22 +253,27 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
 
 template <bool COUNT_ONLY>
 __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, uint64_t pos, uint8_t *out,
-                                              uint64_t cap, WarpSmem *ws, uint64_t &out_len) {
+                                              uint64_t cap64, WarpSmem *ws, const uint32_t *len_tab,
+                                              const uint32_t *dist_tab, uint64_t &out_len) {
   const int lane = zb_lane();
   const uint8_t clcl_order[19] = ZB_CLCL_ORDER;
   BitReader b;
   const uint32_t shift0 = (uint32_t)((uintptr_t)src & 3u);
   b.gbase = reinterpret_cast<const uint32_t *>(src - shift0);
   b.nwords = (uint32_t)((shift0 + len + 3u) >> 2);
-  br_seek(b, shift0, pos, len);
-  uint64_t op = 0;
+  b.end_bit = (shift0 + len) * 8ull;
+  b.overrun = false;
+  br_seek(b, shift0, pos);
+  // positions are 32-bit inside a member (a single member's output is limited to 4 GiB - 1)
+  const uint32_t cap = COUNT_ONLY ? 0xffffffffu : (uint32_t)min(cap64, (uint64_t)0xffffffffu);
+  uint32_t op = 0;
   Tree tl, td;
   bool final_block = false;
   while (!final_block) {
     br_refill(b);
     uint32_t bfinal = br_take(b, 1);
     uint32_t btype = br_take(b, 2);
-    if (b.left < 0) return ZB_ERR_END_OF_BUFFER;
+    if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
     if (bfinal) final_block = true;
     if (btype == 0) {
       // ---- stored (inflate.nim:252-266) ----
@@ -240,17 +282,19 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
       uint32_t l = br_take(b, 16);
       br_refill(b);
       uint32_t nl = br_take(b, 16);
-      if (b.left < 0) return ZB_ERR_END_OF_BUFFER;
+      if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
       if (l + nl != 65535u) return ZB_ERR_UNCOMPRESS;
       if (l > 0) {
-        uint64_t byte_pos = len - (uint64_t)(b.left >> 3);
+        uint64_t byte_pos = (br_consumed_abs(b) >> 3) - shift0;
         if (byte_pos + l > len) return ZB_ERR_END_OF_BUFFER;
         if (!COUNT_ONLY) {
-          if (op + l > cap) return ZB_ERR_DST_TOO_SMALL;
+          if (l > cap - op) return ZB_ERR_DST_TOO_SMALL;
           for (uint32_t i = (uint32_t)lane; i < l; i += 32) out[op + i] = src[byte_pos + i];
+        } else if (l > cap - op) {
+          return ZB_ERR_DST_TOO_SMALL;
         }
         op += l;
-        br_seek(b, shift0, byte_pos + l, len);
+        br_seek(b, shift0, byte_pos + l);
       }
       continue;
     }
@@ -279,17 +323,17 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
       }
       __syncwarp();
       Tree tc;
-      if (!build_tree(ws->lens, 19, ws->syms_d, ws, tc)) return ZB_ERR_UNCOMPRESS;
+      if (!build_tree(ws->lens, 19, ws->syms_d, ws->lut_d, 7, ws, tc)) return ZB_ERR_UNCOMPRESS;
       __syncwarp();
-      // the 19 code-length-code symbols now live in syms_d[0..19); lens[] is rewritten below,
-      // so keep decoding against syms_d and write the unpacked lengths into lens[].
+      // the code-length code now lives in syms_d / lut_d; lens[] is rewritten with the
+      // unpacked literal/length + distance code lengths.
       int i = 0;
       const int total = hlit + hdist;
       uint32_t prev = 0;
       while (i != total) {
         br_refill(b);
-        uint32_t sym = decode_sym(b, tc, ws->syms_d);
-        if (b.left < 0) return ZB_ERR_END_OF_BUFFER;
+        uint32_t sym = decode_sym<7>(b, ws->lut_d, tc, ws->syms_d);
+        if (b.overrun) return ZB_ERR_END_OF_BUFFER;
         if (sym <= 15) {
           if (lane == 0) ws->lens[i] = (uint8_t)sym;
           prev = sym;
@@ -311,24 +355,26 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
           i += rep;
           prev = 0;
         } else {
+          if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
           return ZB_ERR_INVALID_SYMBOL;  // also the undecodable-code case (0xffff)
         }
         if (i > total) return ZB_ERR_UNCOMPRESS;
       }
+      if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
       __syncwarp();
     }
-    if (!build_tree(ws->lens, hlit, ws->syms_ll, ws, tl)) return ZB_ERR_UNCOMPRESS;
-    if (!build_tree(ws->lens + hlit, hdist, ws->syms_d, ws, td)) return ZB_ERR_UNCOMPRESS;
+    if (!build_tree(ws->lens, hlit, ws->syms_ll, ws->lut_ll, LL_BITS, ws, tl)) return ZB_ERR_UNCOMPRESS;
+    if (!build_tree(ws->lens + hlit, hdist, ws->syms_d, ws->lut_d, D_BITS, ws, td)) return ZB_ERR_UNCOMPRESS;
     __syncwarp();
 
     // ---- symbol loop (inflate.nim:173-250) ----
     for (;;) {
       br_refill(b);
-      uint32_t sym = decode_sym(b, tl, ws->syms_ll);
-      if (b.left < 0) return ZB_ERR_END_OF_BUFFER;
+      if (b.overrun) return ZB_ERR_END_OF_BUFFER;  // a whole line past the end: stop decoding zeros
+      uint32_t sym = decode_sym<LL_BITS>(b, ws->lut_ll, tl, ws->syms_ll);
       if (sym < 256) {
+        if (op >= cap) return b.overrun ? ZB_ERR_END_OF_BUFFER : ZB_ERR_DST_TOO_SMALL;
         if (!COUNT_ONLY) {
-          if (op >= cap) return ZB_ERR_DST_TOO_SMALL;
           if (lane == 0) out[op] = (uint8_t)sym;
         }
         op++;
@@ -336,18 +382,28 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
       }
       if (sym == 256) break;
       uint32_t lidx = sym - 257u;
-      if (lidx >= 29u) return ZB_ERR_UNCOMPRESS;  // includes the undecodable-code case
-      uint32_t mlen = zb_len_base((int)lidx) + br_take(b, zb_len_extra_bits((int)lidx));
+      if (lidx >= 29u) {  // includes the undecodable-code case
+        if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+        return ZB_ERR_UNCOMPRESS;
+      }
+      const uint32_t lt = len_tab[lidx];
+      uint32_t mlen = (lt & 0xffffu) + br_take(b, (int)(lt >> 16));
       br_refill(b);
-      uint32_t didx = decode_sym(b, td, ws->syms_d);
-      if (didx >= 30u) return ZB_ERR_UNCOMPRESS;
-      uint32_t dist = zb_dist_base((int)didx) + br_take(b, zb_dist_extra_bits((int)didx));
-      if (b.left < 0) return ZB_ERR_END_OF_BUFFER;
-      if (dist > op) return ZB_ERR_UNCOMPRESS;
+      uint32_t didx = decode_sym<D_BITS>(b, ws->lut_d, td, ws->syms_d);
+      if (didx >= 30u) {
+        if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+        return ZB_ERR_UNCOMPRESS;
+      }
+      const uint32_t dt = dist_tab[didx];
+      uint32_t dist = (dt & 0xffffu) + br_take(b, (int)(dt >> 16));
+      if (dist > op) {
+        if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+        return ZB_ERR_UNCOMPRESS;
+      }
+      if (mlen > cap - op) return b.overrun ? ZB_ERR_END_OF_BUFFER : ZB_ERR_DST_TOO_SMALL;
       if (!COUNT_ONLY) {
-        if (op + mlen > cap) return ZB_ERR_DST_TOO_SMALL;
         __syncwarp();  // earlier stores by any lane are visible to every lane from here on
-        const uint8_t *from = out + op - dist;
+        const uint8_t *from = out + (op - dist);
         uint8_t *to = out + op;
         if (dist >= mlen) {
           for (uint32_t i = (uint32_t)lane; i < mlen; i += 32) to[i] = from[i];
@@ -358,6 +414,7 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
       }
       op += mlen;
     }
+    if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
   }
   out_len = op;
   return ZB_OK;
@@ -366,9 +423,16 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(INF_THREADS)
     k_inflate(ZbInflateWork w) {
-  __shared__ WarpSmem wsm[INF_WARPS];
+  __shared__ __align__(16) WarpSmem wsm[INF_WARPS];
+  __shared__ uint32_t len_tab[32], dist_tab[32];  // base | extra bits << 16 (RFC 1951 3.2.5)
   const int lane = zb_lane(), warp = (int)(threadIdx.x >> 5);
   WarpSmem *ws = &wsm[warp];
+  if (threadIdx.x < 29) len_tab[threadIdx.x] = zb_len_base((int)threadIdx.x) | ((uint32_t)zb_len_extra_bits((int)threadIdx.x) << 16);
+  if (threadIdx.x >= 32 && threadIdx.x < 62) {
+    int c = (int)threadIdx.x - 32;
+    dist_tab[c] = zb_dist_base(c) | ((uint32_t)zb_dist_extra_bits(c) << 16);
+  }
+  __syncthreads();
   for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(w.counter, 1u);
@@ -384,7 +448,7 @@ __global__ void __launch_bounds__(INF_THREADS)
       uint8_t *out = COUNT_ONLY ? nullptr : w.dst + w.dst_off[i];
       uint64_t cap = COUNT_ONLY ? 0 : w.dst_off[i + 1] - w.dst_off[i];
       if (COUNT_ONLY && kind == ZB_DF_GZIP) out_len = isize;  // gzip.nim:66 (trustSize's source)
-      else st = inflate_member<COUNT_ONLY>(src, len, pos, out, cap, ws, out_len);
+      else st = inflate_member<COUNT_ONLY>(src, len, pos, out, cap, ws, len_tab, dist_tab, out_len);
     }
     __syncwarp();
     if (lane == 0) {
