@@ -1,0 +1,55 @@
+"""Multi-GPU sharding of a batch of independent members.
+
+One process per GPU.  Members are partitioned by contiguous index range; every rank
+compresses (or inflates) its own range with no data-path collective.  The path's single
+exchange is one all_gather of the per-member output sizes, after which every rank knows
+where each member lands in the concatenated stream.  Works with any torch.distributed
+backend (NCCL on the GPUs; gloo in the CPU tests)."""
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """Contiguous [lo, hi) of member indices for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_range_by_bytes(lens, rank, world):
+    """Contiguous ranges balanced by input bytes (for skewed member sizes)."""
+    lens = np.asarray(lens, dtype=np.uint64)
+    csum = np.concatenate([[0], np.cumsum(lens)])
+    total = int(csum[-1])
+    cuts = [int(np.searchsorted(csum, total * r // world, side="left")) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, len(lens)
+    for i in range(1, world + 1):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts[rank], cuts[rank + 1]
+
+
+def gather_sizes(local_sizes, n_total, device=None, group=None):
+    """all_gather the per-member output sizes of every rank.
+
+    local_sizes: int64 array for this rank's shard (shard_range order).  Returns
+    (all_sizes int64[n_total], global_offsets int64[n_total + 1]).  Shards may differ in
+    length by one, so sizes are padded to the longest shard for the collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        sizes = np.asarray(local_sizes, dtype=np.int64)
+        return sizes, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    longest = (n_total + world - 1) // world
+    pad = torch.full((longest,), -1, dtype=torch.int64, device=device)
+    ls = torch.as_tensor(np.asarray(local_sizes, dtype=np.int64), device=device)
+    pad[:ls.numel()] = ls
+    out = torch.empty(world * longest, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    out = out.cpu().numpy().reshape(world, longest)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(out[r, :hi - lo])
+    sizes = np.concatenate(parts)
+    assert (sizes >= 0).all()
+    return sizes, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
