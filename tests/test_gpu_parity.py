@@ -295,3 +295,35 @@ def test_device_resident_batch(z, o, corpus):
     t = ctx.timing()
     assert t["kernel_launches"] >= 2
     ctx.close()
+
+
+def test_launch_groups_and_tight_capacity(z, o, corpus, monkeypatch):
+    """Batches are processed in launch groups whose output offsets are chained on the device;
+    force tiny groups, and give the device variant a destination smaller than the worst-case
+    bound (the path that sizes the zero-fill from the real extent)."""
+    torch = pytest.importorskip("torch")
+    monkeypatch.setenv("ZB200_GROUP_CHUNKS", "3")
+    ctx = z.Context()
+    monkeypatch.delenv("ZB200_GROUP_CHUNKS")
+    rng = random.Random(11)
+    items = [corpus["alice29.txt"], b"", corpus["html"], corpus["urls.10K"], b"x" * 70000, corpus["geo.protodata"],
+             bytes(rng.randrange(256) for _ in range(200000)), corpus["kppkn.gtb"][:65536], b"abc"]
+    base = np.frombuffer(b"".join(items), dtype=np.uint8)
+    offs = np.zeros(len(items) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(x) for x in items])
+    for fmt in (z.dfGzip, z.dfZlib):
+        out, oo = ctx.compress_batch(base, offs, 1, fmt, fname_lens=[i % 26 for i in range(len(items))])
+        for i, x in enumerate(items):
+            assert o.uncompress(out[int(oo[i]):int(oo[i + 1])].tobytes()) == x, i
+    # device variant with a tight destination
+    d_src = torch.from_numpy(base.copy()).cuda()
+    total = int(oo[-1])
+    cap = (total + 64 + 3) & ~3
+    d_dst = torch.full((cap,), 0xAB, dtype=torch.uint8, device="cuda")   # dirty buffer: must be zero-filled by the call
+    o2 = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfZlib, d_dst.data_ptr(), cap)
+    host = d_dst.cpu().numpy()
+    for i, x in enumerate(items):
+        assert zlib.decompress(host[int(o2[i]):int(o2[i + 1])].tobytes()) == x, i
+    with pytest.raises(z.ZippyError):
+        ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfZlib, d_dst.data_ptr(), 1000)
+    ctx.close()

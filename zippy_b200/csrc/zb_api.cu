@@ -4,6 +4,7 @@
 // zb_inflate.cu.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -21,7 +22,8 @@ struct DevBuf {
   size_t cap = 0;
 };
 
-constexpr size_t kMaxChunksPerGroup = 131072;  // 8 GiB of input per launch group
+constexpr size_t kMaxChunksPerGroup = 32768;  // device-resident batches: 2 GiB of input per launch group
+constexpr size_t kHostGroupChunks = 4096;     // host batches: 256 MiB groups so transfers overlap the kernels
 
 }  // namespace
 
@@ -34,6 +36,12 @@ struct zb200_ctx {
   DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out;
   DevBuf in_stage, out_stage;
   cudaEvent_t ev[10];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> gev;   // per-group events (H2D done, compute done, offsets ready)
+  void *pin = nullptr;            // pinned host scratch for descriptors / offsets
+  size_t pin_cap = 0;
+  DevBuf group_end;               // device u64 per group: end offset of the group's output
+  size_t dev_group_chunks = kMaxChunksPerGroup, host_group_chunks = kHostGroupChunks;
   zb200_timing timing;
   std::string last_err;
   std::mutex mu;
@@ -99,10 +107,46 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
-// ---- compress, device-resident src/dst ----
-int compress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n, int level,
-                           int data_format, const uint8_t *fname_lens, uint8_t *d_dst, size_t dst_cap,
-                           uint64_t *dst_offsets, int *statuses) {
+int ensure_pinned(zb200_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->pin_cap) return ZB200_OK;
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  ctx->pin = nullptr;
+  ctx->pin_cap = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  if (cudaMallocHost(&ctx->pin, want) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->last_err = "cudaMallocHost failed";
+    return ZB200_ERR_NOMEM;
+  }
+  ctx->pin_cap = want;
+  return ZB200_OK;
+}
+
+int ensure_group_events(zb200_ctx *ctx, size_t n) {
+  while (ctx->gev.size() < n) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return ZB200_ERR_CUDA;
+    ctx->gev.push_back(e);
+  }
+  return ZB200_OK;
+}
+
+struct Group {
+  size_t m0, m1;        // members [m0, m1)
+  size_t c0, nc;        // chunks [c0, c0 + nc) in the batch-wide descriptor array
+  size_t first0;        // start of this group's (nm + 1) entries in the member_first / member_off arrays
+  uint64_t in_lo, in_hi;  // source byte range
+  uint64_t bound;       // output bound of the group
+};
+
+// ---- compress: device-resident (h_src == h_dst == nullptr) or pipelined host buffers ----
+// With host buffers the batch is cut into groups and H2D(g+1) || kernels(g) || D2H(g-1) run
+// on three streams; each group's output offset is chained on the device (out_base_ptr), so
+// the only host waits are for the small per-group offset arrays that size the D2H copies.
+int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, const uint64_t *src_offsets,
+                    size_t n, int level, int data_format, const uint8_t *fname_lens, uint8_t *d_dst,
+                    size_t dst_cap, uint8_t *h_dst, size_t h_dst_cap, uint64_t *dst_offsets, int *statuses,
+                    size_t max_group_chunks) {
   if (level < -2 || level > 9) return ZB200_ERR_INVALID_LEVEL;
   if (data_format != ZB200_DF_GZIP && data_format != ZB200_DF_ZLIB && data_format != ZB200_DF_DEFLATE)
     return ZB200_ERR_INVALID_FORMAT;
@@ -110,119 +154,208 @@ int compress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
     for (size_t i = 0; i < n; i++)
       if (fname_lens[i] > 25) return ZB200_ERR_ARG;
   if (((uintptr_t)d_dst & 3u) != 0) return ZB200_ERR_ARG;
-  for (size_t i = 0; i < n; i++)
+  for (size_t i = 0; i < n; i++) {
+    if (src_offsets[i + 1] < src_offsets[i]) return ZB200_ERR_ARG;
     if (statuses) statuses[i] = ZB200_OK;
+  }
   ctx->timing.lz_ms = ctx->timing.huff_ms = ctx->timing.scan_ms = ctx->timing.pack_ms = 0.f;
   ctx->timing.n_chunks = 0;
   dst_offsets[0] = 0;
   if (n == 0) return ZB200_OK;
+  const uint64_t src_lo = src_offsets[0];  // d_src holds [src_lo, src_hi) rebased to 0 when staging from the host
 
-  uint64_t out_base = 0;
-  size_t m0 = 0;
+  // ---- plan: groups, descriptors ----
+  std::vector<Group> groups;
   std::vector<ZbChunkDesc> desc;
   std::vector<uint32_t> first;
-  while (m0 < n) {
-    // ---- carve a group of members with a bounded number of chunks ----
-    desc.clear();
-    first.clear();
+  size_t max_nc = 0, max_nm = 0;
+  for (size_t m0 = 0; m0 < n;) {
+    Group g;
+    g.m0 = m0;
+    g.c0 = desc.size();
+    g.first0 = first.size();
+    g.bound = 0;
     size_t m1 = m0;
-    uint64_t bound_total = 0;
     while (m1 < n) {
       uint64_t len = src_offsets[m1 + 1] - src_offsets[m1];
       size_t nc = len == 0 ? 1 : (size_t)((len + ZB_CHUNK_BYTES - 1) / ZB_CHUNK_BYTES);
-      if (!desc.empty() && desc.size() + nc > kMaxChunksPerGroup) break;
-      first.push_back((uint32_t)desc.size());
+      if (desc.size() > g.c0 && desc.size() - g.c0 + nc > max_group_chunks) break;
+      first.push_back((uint32_t)(desc.size() - g.c0));
       for (size_t k = 0; k < nc; k++) {
         ZbChunkDesc d;
-        d.src_off = src_offsets[m1] + (uint64_t)k * ZB_CHUNK_BYTES;
+        d.src_off = src_offsets[m1] - (h_src ? src_lo : 0) + (uint64_t)k * ZB_CHUNK_BYTES;
         d.len = (uint32_t)std::min<uint64_t>(ZB_CHUNK_BYTES, len - (uint64_t)k * ZB_CHUNK_BYTES);
         d.member = (uint32_t)(m1 - m0);
         d.flags = (k == 0 ? ZB_CHUNK_FIRST : 0u) | (k == nc - 1 ? ZB_CHUNK_LAST : 0u);
         d.pad = 0;
         desc.push_back(d);
       }
-      bound_total += zb200_compress_bound((size_t)len, data_format) + 64;
+      g.bound += zb200_compress_bound((size_t)len, data_format) + 64;
       m1++;
     }
-    first.push_back((uint32_t)desc.size());
-    const size_t nm = m1 - m0, nc = desc.size();
+    g.m1 = m1;
+    g.nc = desc.size() - g.c0;
+    first.push_back((uint32_t)g.nc);
+    g.in_lo = src_offsets[m0] - src_lo;
+    g.in_hi = src_offsets[m1] - src_lo;
+    max_nc = std::max(max_nc, g.nc);
+    max_nm = std::max(max_nm, g.m1 - g.m0);
+    groups.push_back(g);
+    m0 = m1;
+  }
+  const size_t ng = groups.size(), nc_all = desc.size(), nfirst = first.size();
+  uint64_t bound_total = 0;
+  for (auto &g : groups) bound_total += g.bound;
+  const bool known_fit = bound_total <= dst_cap;
 
-    ENSURE(ctx->desc, nc * sizeof(ZbChunkDesc));
-    ENSURE(ctx->member_first, (nm + 1) * sizeof(uint32_t));
-    ENSURE(ctx->fname, nm + 16);
-    ENSURE(ctx->masks, nc * ZB_WINDOWS_PER_CHUNK * sizeof(uint2));
-    ENSURE(ctx->recs, nc * (size_t)ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS * sizeof(uint32_t));
-    ENSURE(ctx->hist, nc * (size_t)ZB_WARPS_PER_CHUNK * ZB_HIST_SYMS * sizeof(uint16_t));
-    ENSURE(ctx->chk, nc * sizeof(ZbChunkCheck));
-    ENSURE(ctx->cb, nc * sizeof(ZbCodebook));
-    ENSURE(ctx->chunk_off, nc * sizeof(uint64_t));
-    ENSURE(ctx->member_off, (nm + 1) * sizeof(uint64_t));
-    ENSURE(ctx->member_check, nm * sizeof(uint32_t));
-    ENSURE(ctx->member_isize, nm * sizeof(uint32_t));
+  ENSURE(ctx->desc, nc_all * sizeof(ZbChunkDesc));
+  ENSURE(ctx->member_first, nfirst * sizeof(uint32_t));
+  ENSURE(ctx->member_off, nfirst * sizeof(uint64_t));
+  ENSURE(ctx->fname, n + 16);
+  ENSURE(ctx->group_end, (ng + 1) * sizeof(uint64_t));
+  ENSURE(ctx->masks, max_nc * ZB_WINDOWS_PER_CHUNK * sizeof(uint2));
+  ENSURE(ctx->recs, max_nc * (size_t)ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS * sizeof(uint32_t));
+  ENSURE(ctx->hist, max_nc * (size_t)ZB_WARPS_PER_CHUNK * ZB_HIST_SYMS * sizeof(uint16_t));
+  ENSURE(ctx->chk, max_nc * sizeof(ZbChunkCheck));
+  ENSURE(ctx->cb, max_nc * sizeof(ZbCodebook));
+  ENSURE(ctx->chunk_off, max_nc * sizeof(uint64_t));
+  ENSURE(ctx->member_check, max_nm * sizeof(uint32_t));
+  ENSURE(ctx->member_isize, max_nm * sizeof(uint32_t));
+  {
+    int rc = ensure_pinned(ctx, nfirst * sizeof(uint64_t) + 64);
+    if (rc) return rc;
+    rc = ensure_group_events(ctx, 3 * ng + 1);
+    if (rc) return rc;
+  }
+  uint64_t *pin_off = (uint64_t *)ctx->pin;
 
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->desc.p, desc.data(), nc * sizeof(ZbChunkDesc), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->member_first.p, first.data(), (nm + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    if (fname_lens && data_format == ZB200_DF_GZIP)
-      CK(cudaMemcpyAsync(ctx->fname.p, fname_lens + m0, nm, cudaMemcpyHostToDevice, s));
+  cudaStream_t s = ctx->stream;
+  cudaStream_t sh = h_src ? ctx->h2d_stream : s, sd = h_dst ? ctx->d2h_stream : s;
+  CK(cudaMemcpyAsync(ctx->desc.p, desc.data(), nc_all * sizeof(ZbChunkDesc), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->member_first.p, first.data(), nfirst * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  if (fname_lens && data_format == ZB200_DF_GZIP)
+    CK(cudaMemcpyAsync(ctx->fname.p, fname_lens, n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ctx->group_end.p, 0, sizeof(uint64_t), s));
+  if (known_fit) CK(cudaMemsetAsync(d_dst, 0, (size_t)bound_total, s));  // the packer ORs bits into zeros
+  if (h_src || h_dst) {
+    // the transfer streams must not run ahead of the setup above
+    CK(cudaEventRecord(ctx->gev[3 * ng], s));
+    if (h_src) CK(cudaStreamWaitEvent(sh, ctx->gev[3 * ng], 0));
+    if (h_dst) CK(cudaStreamWaitEvent(sd, ctx->gev[3 * ng], 0));
+  }
+  CK(cudaEventRecord(ctx->ev[6], sh));
 
+  auto make_work = [&](const Group &g, size_t gi) {
     ZbCompressWork w;
     w.src = d_src;
     w.dst = d_dst;
-    w.desc = (const ZbChunkDesc *)ctx->desc.p;
-    w.member_first = (const uint32_t *)ctx->member_first.p;
-    w.fname_len = (fname_lens && data_format == ZB200_DF_GZIP) ? (const uint8_t *)ctx->fname.p : nullptr;
+    w.desc = (const ZbChunkDesc *)ctx->desc.p + g.c0;
+    w.member_first = (const uint32_t *)ctx->member_first.p + g.first0;
+    w.fname_len = (fname_lens && data_format == ZB200_DF_GZIP) ? (const uint8_t *)ctx->fname.p + g.m0 : nullptr;
     w.masks = (uint2 *)ctx->masks.p;
     w.recs = (uint32_t *)ctx->recs.p;
     w.hist = (uint16_t *)ctx->hist.p;
     w.chk = (ZbChunkCheck *)ctx->chk.p;
     w.cb = (ZbCodebook *)ctx->cb.p;
     w.chunk_off = (uint64_t *)ctx->chunk_off.p;
-    w.member_off = (uint64_t *)ctx->member_off.p;
+    w.member_off = (uint64_t *)ctx->member_off.p + g.first0;
     w.member_check = (uint32_t *)ctx->member_check.p;
     w.member_isize = (uint32_t *)ctx->member_isize.p;
     w.tabs = ctx->d_tabs;
-    w.n_chunks = (uint32_t)nc;
-    w.n_members = (uint32_t)nm;
+    w.n_chunks = (uint32_t)g.nc;
+    w.n_members = (uint32_t)(g.m1 - g.m0);
     w.level = level;
     w.data_format = data_format;
-    w.out_base = out_base;
+    w.out_base = 0;
+    w.out_base_ptr = (const uint64_t *)ctx->group_end.p + gi;
+    return w;
+  };
 
-    CK(cudaEventRecord(ctx->ev[0], s));
-    CK(zb_launch_lz(w, s));
-    CK(cudaEventRecord(ctx->ev[1], s));
-    CK(zb_launch_huff(w, s));
-    CK(cudaEventRecord(ctx->ev[2], s));
-    CK(zb_launch_scan(w, s));
-    CK(cudaEventRecord(ctx->ev[3], s));
-    // the packer ORs bits into a zero-filled stream
-    uint64_t total_end = 0;
-    bool known_fit = out_base + bound_total <= dst_cap;
-    if (known_fit) {
-      CK(cudaMemsetAsync(d_dst + out_base, 0, bound_total, s));
-    } else {
-      CK(cudaMemcpyAsync(&total_end, (uint64_t *)ctx->member_off.p + nm, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      if (total_end > dst_cap) return ZB200_ERR_DST_TOO_SMALL;
-      size_t z0 = out_base & ~(size_t)3;
-      size_t z1 = std::min<size_t>((total_end + 3) & ~(size_t)3, dst_cap);
-      CK(cudaMemsetAsync(d_dst + z0, 0, z1 - z0, s));
+  // ---- enqueue every group ----
+  size_t zeroed_upto = 0;
+  size_t d2h_done = 0;  // groups whose output has been handed to the D2H stream
+  uint64_t total_out = 0;
+  auto drain_d2h = [&](size_t upto) -> int {  // enqueue D2H for groups [d2h_done, upto)
+    for (; d2h_done < upto; d2h_done++) {
+      const Group &g = groups[d2h_done];
+      CK(cudaEventSynchronize(ctx->gev[3 * d2h_done + 2]));  // offsets of this group are in pin_off
+      const size_t nm = g.m1 - g.m0;
+      const uint64_t lo = pin_off[g.first0], hi = pin_off[g.first0 + nm];
+      for (size_t j = 0; j <= nm; j++) dst_offsets[g.m0 + j] = pin_off[g.first0 + j];
+      total_out = hi;
+      if (h_dst) {
+        if (hi > h_dst_cap) return ZB200_ERR_DST_TOO_SMALL;
+        CK(cudaStreamWaitEvent(sd, ctx->gev[3 * d2h_done + 1], 0));
+        if (d2h_done == 0) CK(cudaEventRecord(ctx->ev[8], sd));
+        if (hi > lo) CK(cudaMemcpyAsync(h_dst + lo, d_dst + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, sd));
+      }
     }
-    CK(cudaEventRecord(ctx->ev[4], s));
+    return ZB200_OK;
+  };
+
+  for (size_t gi = 0; gi < ng; gi++) {
+    const Group &g = groups[gi];
+    if (h_src) {
+      if (g.in_hi > g.in_lo)
+        CK(cudaMemcpyAsync((uint8_t *)d_src + g.in_lo, h_src + src_lo + g.in_lo, (size_t)(g.in_hi - g.in_lo),
+                           cudaMemcpyHostToDevice, sh));
+      CK(cudaEventRecord(ctx->gev[3 * gi + 0], sh));
+      CK(cudaStreamWaitEvent(s, ctx->gev[3 * gi + 0], 0));
+    }
+    ZbCompressWork w = make_work(g, gi);
+    const bool timed = (gi == 0);  // per-kernel events on the first group; totals are scaled by chunk count
+    if (timed) CK(cudaEventRecord(ctx->ev[0], s));
+    CK(zb_launch_lz(w, s));
+    if (timed) CK(cudaEventRecord(ctx->ev[1], s));
+    CK(zb_launch_huff(w, s));
+    if (timed) CK(cudaEventRecord(ctx->ev[2], s));
+    CK(zb_launch_scan(w, s));
+    if (timed) CK(cudaEventRecord(ctx->ev[3], s));
+    // chain: the next group starts where this one ended
+    CK(cudaMemcpyAsync((uint64_t *)ctx->group_end.p + gi + 1, w.member_off + w.n_members, sizeof(uint64_t),
+                       cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(pin_off + g.first0, w.member_off, (w.n_members + 1) * sizeof(uint64_t),
+                       cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->gev[3 * gi + 2], s));
+    if (!known_fit) {
+      // caller's buffer is smaller than the worst case: learn the real extent before zeroing it
+      CK(cudaEventSynchronize(ctx->gev[3 * gi + 2]));
+      const uint64_t lo = pin_off[g.first0], hi = pin_off[g.first0 + w.n_members];
+      if (hi > dst_cap) return ZB200_ERR_DST_TOO_SMALL;
+      const size_t z0 = (size_t)lo & ~(size_t)3, z1 = std::min<size_t>(((size_t)hi + 3) & ~(size_t)3, dst_cap);
+      // a word shared with the previous group was zeroed (and possibly written) already
+      const size_t zs = std::max(z0, zeroed_upto);
+      if (z1 > zs) CK(cudaMemsetAsync(d_dst + zs, 0, z1 - zs, s));
+      zeroed_upto = std::max(zeroed_upto, z1);
+    }
+    if (timed) CK(cudaEventRecord(ctx->ev[4], s));
     CK(zb_launch_pack(w, s));
-    CK(cudaEventRecord(ctx->ev[5], s));
-    CK(cudaMemcpyAsync(dst_offsets + m0, ctx->member_off.p, (nm + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    ctx->timing.lz_ms += ev_ms(ctx->ev[0], ctx->ev[1]);
-    ctx->timing.huff_ms += ev_ms(ctx->ev[1], ctx->ev[2]);
-    ctx->timing.scan_ms += ev_ms(ctx->ev[2], ctx->ev[3]);
-    ctx->timing.pack_ms += ev_ms(ctx->ev[3], ctx->ev[5]);
-    ctx->timing.kernel_launches += 4;
-    ctx->timing.n_chunks += (uint32_t)nc;
-    out_base = dst_offsets[m1];
-    if (out_base > dst_cap) return ZB200_ERR_DST_TOO_SMALL;
-    m0 = m1;
+    if (timed) CK(cudaEventRecord(ctx->ev[5], s));
+    CK(cudaEventRecord(ctx->gev[3 * gi + 1], s));
+    ctx->timing.kernel_launches += 5;
+    ctx->timing.n_chunks += (uint32_t)g.nc;
+    // keep at most two groups of output waiting on the device before draining to the host
+    if (h_dst && gi >= 2) {
+      int rc = drain_d2h(gi - 1);
+      if (rc) return rc;
+    }
   }
+  if (h_src) CK(cudaEventRecord(ctx->ev[7], sh));
+  {
+    int rc = drain_d2h(ng);
+    if (rc) return rc;
+  }
+  if (h_dst) CK(cudaEventRecord(ctx->ev[9], sd));
+  CK(cudaStreamSynchronize(s));
+  if (h_src) CK(cudaStreamSynchronize(sh));
+  if (h_dst) CK(cudaStreamSynchronize(sd));
+  if (total_out > dst_cap) return ZB200_ERR_DST_TOO_SMALL;
+  // per-kernel times: measured on the first group, scaled to the batch by chunk count
+  const float scale = groups[0].nc ? (float)nc_all / (float)groups[0].nc : 1.f;
+  ctx->timing.lz_ms = ev_ms(ctx->ev[0], ctx->ev[1]) * scale;
+  ctx->timing.huff_ms = ev_ms(ctx->ev[1], ctx->ev[2]) * scale;
+  ctx->timing.scan_ms = ev_ms(ctx->ev[2], ctx->ev[3]) * scale;
+  ctx->timing.pack_ms = ev_ms(ctx->ev[4], ctx->ev[5]) * scale;
   return ZB200_OK;
 }
 
@@ -352,9 +485,15 @@ int zb200_init(int device, zb200_ctx **out) {
   zb200_ctx *ctx = new zb200_ctx();
   ctx->device = device;
   memset(&ctx->timing, 0, sizeof(ctx->timing));
+  if (const char *e = getenv("ZB200_GROUP_CHUNKS")) {  // test hook: force small launch groups
+    long v = atol(e);
+    if (v > 0) ctx->dev_group_chunks = ctx->host_group_chunks = (size_t)v;
+  }
   DeviceGuard g(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
+  if (ok) ok = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) == cudaSuccess;
+  if (ok) ok = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; ok && i < 10; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   if (ok) ok = cudaMalloc((void **)&ctx->d_tabs, sizeof(ZbCrcTables)) == cudaSuccess;
   if (ok) {
@@ -383,7 +522,12 @@ void zb200_shutdown(zb200_ctx *ctx) {
     if (b->p) cudaFree(b->p);
   if (ctx->d_tabs) cudaFree(ctx->d_tabs);
   for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->gev) cudaEventDestroy(e);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  if (ctx->group_end.p) cudaFree(ctx->group_end.p);
   cudaStreamDestroy(ctx->own_stream);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   delete ctx;
 }
 
@@ -443,8 +587,8 @@ int zb200_compress_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   ctx->timing.kernel_launches = 0;
-  return compress_device_locked(ctx, d_src, src_offsets, n, level, data_format, fname_lens, d_dst, dst_cap,
-                                dst_offsets, statuses);
+  return compress_locked(ctx, d_src, nullptr, src_offsets, n, level, data_format, fname_lens, d_dst, dst_cap, nullptr,
+                         0, dst_offsets, statuses, ctx->dev_group_chunks);
 }
 
 int zb200_compress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offsets, size_t n, int level,
@@ -454,24 +598,26 @@ int zb200_compress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   memset(&ctx->timing, 0, sizeof(ctx->timing));
-  std::vector<uint64_t> reb;
-  int rc = stage_in(ctx, src_base, src_offsets, n, reb);
-  if (rc) return rc;
+  if (n == 0) {
+    dst_offsets[0] = 0;
+    return ZB200_OK;
+  }
+  for (size_t i = 0; i < n; i++)
+    if (src_offsets[i + 1] < src_offsets[i]) return ZB200_ERR_ARG;
+  const uint64_t in_bytes = src_offsets[n] - src_offsets[0];
   uint64_t bound = 0;
-  for (size_t i = 0; i < n; i++) bound += zb200_compress_bound((size_t)(reb[i + 1] - reb[i]), data_format) + 64;
+  for (size_t i = 0; i < n; i++)
+    bound += zb200_compress_bound((size_t)(src_offsets[i + 1] - src_offsets[i]), data_format) + 64;
+  ENSURE(ctx->in_stage, (size_t)in_bytes + 64);
   ENSURE(ctx->out_stage, (size_t)bound + 64);
-  rc = compress_device_locked(ctx, (const uint8_t *)ctx->in_stage.p, reb.data(), n, level, data_format, fname_lens,
-                              (uint8_t *)ctx->out_stage.p, ctx->out_stage.cap & ~(size_t)3, dst_offsets, statuses);
+  int rc = compress_locked(ctx, (const uint8_t *)ctx->in_stage.p, src_base, src_offsets, n, level, data_format,
+                           fname_lens, (uint8_t *)ctx->out_stage.p, ctx->out_stage.cap & ~(size_t)3, dst_base,
+                           dst_cap, dst_offsets, statuses, ctx->host_group_chunks);
   if (rc) return rc;
-  uint64_t total = dst_offsets[n];
-  if (total > dst_cap) return ZB200_ERR_DST_TOO_SMALL;
-  CK(cudaEventRecord(ctx->ev[8], ctx->stream));
-  if (total) CK(cudaMemcpyAsync(dst_base, ctx->out_stage.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[9], ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
   ctx->timing.h2d_ms = ev_ms(ctx->ev[6], ctx->ev[7]);
   ctx->timing.d2h_ms = ev_ms(ctx->ev[8], ctx->ev[9]);
-  ctx->timing.d2h_bytes = total;
+  ctx->timing.h2d_bytes = in_bytes;
+  ctx->timing.d2h_bytes = dst_offsets[n];
   return ZB200_OK;
 }
 

@@ -82,7 +82,8 @@ ZB_HD uint32_t zb_adler32_combine(uint32_t ad_a, uint32_t ad_b, uint64_t len_b) 
 struct ZbCrcTables {
   uint32_t mul1024[4][256];
   uint32_t lane_mul[33];
-  uint32_t sub_mul[8];  // x^(8 * 8192 * k) mod P, k = 0..7: shifts a sub-chunk's CRC to the chunk end
+  uint32_t sub_mul[8];  // [k] = x^(8 * 8192 * k) mod P, k = 1..7: shifts a sub-chunk's CRC to the chunk end;
+                        // [0] = x^(8 * 65536) mod P: shifts by one whole chunk
 };
 
 inline void zb_crc_build_tables(ZbCrcTables *t) {
@@ -90,5 +91,6 @@ inline void zb_crc_build_tables(ZbCrcTables *t) {
   for (int k = 0; k < 4; k++)
     for (uint32_t b = 0; b < 256; b++) t->mul1024[k][b] = zb_gf2_mul(b << (8 * k), x1024);
   for (int j = 0; j <= 32; j++) t->lane_mul[j] = zb_xpow8(4ull * (uint64_t)j);
-  for (int k = 0; k < 8; k++) t->sub_mul[k] = zb_xpow8(8192ull * (uint64_t)k);
+  for (int k = 1; k < 8; k++) t->sub_mul[k] = zb_xpow8(8192ull * (uint64_t)k);
+  t->sub_mul[0] = zb_xpow8(65536ull);
 }

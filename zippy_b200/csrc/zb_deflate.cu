@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   __shared__ uint64_t warp_tot[32];
   __shared__ uint64_t carry_s;
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = w.out_base;
+  if (tid == 0) carry_s = w.out_base_ptr ? *w.out_base_ptr : w.out_base;
   __syncthreads();
   for (uint32_t base = 0; base < w.n_chunks; base += SCAN_THREADS) {
     uint32_t c = base + (uint32_t)tid;
@@ -363,24 +363,32 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     __syncthreads();
   }
   if (tid == 0) w.member_off[w.n_members] = carry_s;
-  // whole-member checksums: sequential combine over each member's chunks
-  for (uint32_t m = (uint32_t)tid; m < w.n_members; m += SCAN_THREADS) {
-    uint32_t c0 = w.member_first[m], c1 = w.member_first[m + 1];
-    uint32_t raw = 0, ad = 1;
-    uint64_t total = 0;
-    for (uint32_t c = c0; c < c1; c++) {
-      uint32_t l = w.desc[c].len;
-      ZbChunkCheck cc = w.chk[c];
-      if (w.data_format == ZB_DF_ZLIB) {
-        ad = zb_adler32_combine(ad, cc.adler, l);
-      } else {
-        raw = (c == c0) ? cc.crc_raw : (zb_gf2_mul(raw, zb_xpow8(l)) ^ cc.crc_raw);
-      }
-      total += l;
+}
+
+// whole-member checksums: sequential combine over each member's chunks, one thread per member
+__global__ void __launch_bounds__(128)
+    k_member_check(ZbCompressWork w) {
+  uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= w.n_members) return;
+  uint32_t c0 = w.member_first[m], c1 = w.member_first[m + 1];
+  uint32_t raw = 0, ad = 1;
+  uint64_t total = 0;
+  for (uint32_t c = c0; c < c1; c++) {
+    uint32_t l = w.desc[c].len;
+    ZbChunkCheck cc = w.chk[c];
+    if (w.data_format == ZB_DF_ZLIB) {
+      ad = zb_adler32_combine(ad, cc.adler, l);
+    } else if (w.data_format == ZB_DF_GZIP) {
+      raw = (c == c0) ? cc.crc_raw : (zb_gf2_mul(raw, l == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8(l)) ^ cc.crc_raw);
     }
-    w.member_check[m] = (w.data_format == ZB_DF_ZLIB) ? ad : zb_crc32_finalize(raw, total);
-    w.member_isize[m] = (uint32_t)total;
+    total += l;
   }
+  uint32_t v = 0;
+  if (w.data_format == ZB_DF_ZLIB) v = ad;
+  else if (w.data_format == ZB_DF_GZIP)
+    v = ~(zb_gf2_mul(total == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8(total), 0xffffffffu) ^ raw);
+  w.member_check[m] = v;
+  w.member_isize[m] = (uint32_t)total;
 }
 
 // ------------------------------------------------------------------------------------
@@ -578,6 +586,7 @@ cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s) {
 }
 cudaError_t zb_launch_scan(const ZbCompressWork &w, cudaStream_t s) {
   k_scan<<<1, SCAN_THREADS, 0, s>>>(w);
+  if (w.n_members) k_member_check<<<(w.n_members + 127) / 128, 128, 0, s>>>(w);
   return cudaGetLastError();
 }
 cudaError_t zb_launch_pack(const ZbCompressWork &w, cudaStream_t s) {

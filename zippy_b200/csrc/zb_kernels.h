@@ -39,7 +39,9 @@ struct ZbCompressWork {
   uint64_t *member_off;        // [n_members + 1] output offsets (member_off[n] = total)
   uint32_t *member_check;      // [n_members] crc32 (gzip) or adler32 (zlib) of the whole member
   uint32_t *member_isize;      // [n_members] input size mod 2^32 (gzip ISIZE)
-  uint64_t out_base;           // byte offset in dst where this group's first member starts
+  uint64_t out_base;           // byte offset in dst where this group's first member starts ...
+  const uint64_t *out_base_ptr;// ... or, when non-null, a device word holding it (the previous group's end),
+                               // so consecutive groups can be enqueued without a host round trip
   const ZbCrcTables *tabs;     // device
   uint32_t n_chunks, n_members;
   int level, data_format;
