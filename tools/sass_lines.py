@@ -5,6 +5,7 @@ usage: sass_lines.py <report.ncu-rep> <cubin> <kernel-substring> [top]
 Joins `ncu --page source --csv` (per-instruction executed counts / stall samples, in
 address order) with `nvdisasm -g` (the same instructions with //## File/line markers)."""
 import csv
+import os
 import io
 import re
 import subprocess
@@ -51,7 +52,7 @@ srcs = {}
 for (f, l), (ex, sm) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top]:
     if f not in srcs:
         try:
-            srcs[f] = open("/root/repo/zippy_b200/csrc/" + f).read().split("\n")
+            srcs[f] = open(os.environ.get("ZB_SRC", "/root/repo/zippy_b200/csrc/") + f).read().split("\n")
         except Exception:
             srcs[f] = []
     text = srcs[f][l - 1].strip() if 0 < l <= len(srcs[f]) else ""

@@ -251,6 +251,51 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
   return ZB_ERR_INVALID_FORMAT;
 }
 
+// Materialise a batch of up to 32 decoded tokens (lane i holds token i):
+//   literal: the byte;  match: 1 << 31 | (dist - 1) << 9 | len.
+// One lane per token: a warp prefix sum of the lengths places every token; literals and
+// matches whose source lies wholly before the batch are copied by their own lane, in
+// parallel; the few matches that read bytes produced inside the batch follow in stream
+// order, each copied by the whole warp (reads only touch finished output: i % dist).
+__device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, uint32_t tok, uint32_t ntok) {
+  const int lane = zb_lane();
+  __syncwarp();  // stores of earlier batches are visible to every lane from here on
+  const bool act = (uint32_t)lane < ntok;
+  const bool is_m = act && (tok >> 31);
+  const uint32_t len = act ? (is_m ? (tok & 511u) : 1u) : 0u;
+  const uint32_t dist = ((tok >> 9) & 0x7fffu) + 1u;
+  uint32_t incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(ZB_FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const uint32_t rel = incl - len;           // output offset inside the batch
+  uint8_t *to = out + batch_op + rel;
+  const bool dep = is_m && dist < rel + len;  // source overlaps this batch's own output
+  if (act && !is_m) {
+    *to = (uint8_t)tok;
+  } else if (is_m && !dep) {
+    const uint8_t *from = to - dist;
+    for (uint32_t k = 0; k < len; k++) to[k] = from[k];
+  }
+  uint32_t depmask = __ballot_sync(ZB_FULL, dep);
+  while (depmask) {
+    const int j = __ffs((int)depmask) - 1;
+    depmask &= depmask - 1;
+    const uint32_t rj = __shfl_sync(ZB_FULL, rel, j), lj = __shfl_sync(ZB_FULL, len, j);
+    const uint32_t dj = __shfl_sync(ZB_FULL, dist, j);
+    __syncwarp();
+    uint8_t *tj = out + batch_op + rj;
+    const uint8_t *fj = tj - dj;
+    if (dj >= lj) {
+      for (uint32_t i = (uint32_t)lane; i < lj; i += 32) tj[i] = fj[i];
+    } else {
+      for (uint32_t i = (uint32_t)lane; i < lj; i += 32) tj[i] = fj[i % dj];
+    }
+  }
+}
+
 template <bool COUNT_ONLY>
 __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, uint64_t pos, uint8_t *out,
                                               uint64_t cap64, WarpSmem *ws, const uint32_t *len_tab,
@@ -367,53 +412,50 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
     if (!build_tree(ws->lens + hlit, hdist, ws->syms_d, ws->lut_d, D_BITS, ws, td)) return ZB_ERR_UNCOMPRESS;
     __syncwarp();
 
-    // ---- symbol loop (inflate.nim:173-250) ----
+    // ---- symbol loop (inflate.nim:173-250): decode into a 32-token batch, then flush ----
+    uint32_t tok = 0, ntok = 0, batch_op = op;
     for (;;) {
       br_refill(b);
       if (b.overrun) return ZB_ERR_END_OF_BUFFER;  // a whole line past the end: stop decoding zeros
       uint32_t sym = decode_sym<LL_BITS>(b, ws->lut_ll, tl, ws->syms_ll);
+      uint32_t t, tlen;
       if (sym < 256) {
-        if (op >= cap) return b.overrun ? ZB_ERR_END_OF_BUFFER : ZB_ERR_DST_TOO_SMALL;
-        if (!COUNT_ONLY) {
-          if (lane == 0) out[op] = (uint8_t)sym;
+        t = sym;
+        tlen = 1;
+      } else {
+        if (sym == 256) break;
+        uint32_t lidx = sym - 257u;
+        if (lidx >= 29u) {  // includes the undecodable-code case
+          if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+          return ZB_ERR_UNCOMPRESS;
         }
-        op++;
-        continue;
-      }
-      if (sym == 256) break;
-      uint32_t lidx = sym - 257u;
-      if (lidx >= 29u) {  // includes the undecodable-code case
-        if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-        return ZB_ERR_UNCOMPRESS;
-      }
-      const uint32_t lt = len_tab[lidx];
-      uint32_t mlen = (lt & 0xffffu) + br_take(b, (int)(lt >> 16));
-      br_refill(b);
-      uint32_t didx = decode_sym<D_BITS>(b, ws->lut_d, td, ws->syms_d);
-      if (didx >= 30u) {
-        if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-        return ZB_ERR_UNCOMPRESS;
-      }
-      const uint32_t dt = dist_tab[didx];
-      uint32_t dist = (dt & 0xffffu) + br_take(b, (int)(dt >> 16));
-      if (dist > op) {
-        if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-        return ZB_ERR_UNCOMPRESS;
-      }
-      if (mlen > cap - op) return b.overrun ? ZB_ERR_END_OF_BUFFER : ZB_ERR_DST_TOO_SMALL;
-      if (!COUNT_ONLY) {
-        __syncwarp();  // earlier stores by any lane are visible to every lane from here on
-        const uint8_t *from = out + (op - dist);
-        uint8_t *to = out + op;
-        if (dist >= mlen) {
-          for (uint32_t i = (uint32_t)lane; i < mlen; i += 32) to[i] = from[i];
-        } else {
-          for (uint32_t i = (uint32_t)lane; i < mlen; i += 32) to[i] = from[i % dist];
+        const uint32_t lt = len_tab[lidx];
+        tlen = (lt & 0xffffu) + br_take(b, (int)(lt >> 16));
+        br_refill(b);
+        uint32_t didx = decode_sym<D_BITS>(b, ws->lut_d, td, ws->syms_d);
+        if (didx >= 30u) {
+          if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+          return ZB_ERR_UNCOMPRESS;
         }
-        __syncwarp();
+        const uint32_t dt = dist_tab[didx];
+        const uint32_t dist = (dt & 0xffffu) + br_take(b, (int)(dt >> 16));
+        if (dist > op) {
+          if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+          return ZB_ERR_UNCOMPRESS;
+        }
+        t = (1u << 31) | ((dist - 1u) << 9) | tlen;
       }
-      op += mlen;
+      if (tlen > cap - op) return (b.overrun || br_past_end(b)) ? ZB_ERR_END_OF_BUFFER : ZB_ERR_DST_TOO_SMALL;
+      if ((uint32_t)lane == ntok) tok = t;
+      ntok++;
+      op += tlen;
+      if (ntok == 32) {
+        if (!COUNT_ONLY) flush_tokens(out, batch_op, tok, 32);
+        ntok = 0;
+        batch_op = op;
+      }
     }
+    if (!COUNT_ONLY && ntok) flush_tokens(out, batch_op, tok, ntok);
     if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
   }
   out_len = op;
