@@ -327,3 +327,22 @@ def test_launch_groups_and_tight_capacity(z, o, corpus, monkeypatch):
     with pytest.raises(z.ZippyError):
         ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfZlib, d_dst.data_ptr(), 1000)
     ctx.close()
+
+
+def test_default_level_ratio_vs_reference(z, o, corpus):
+    """BASELINE config 4: at level=Default the total compressed size on the urls.10K corpus must
+    stay within 3 % of the reference's (oracle port, hash-chain level 6, deflate.nim:262-272)."""
+    raw = corpus["urls.10K"]
+    for data in (raw, raw[:65536], corpus["alice29.txt"], corpus["html_x_4"]):
+        ref = len(o.deflate(data, o.DefaultCompression))
+        got = z.deflate(data, z.DefaultCompression)
+        assert zlib.decompress(got, -15) == data and o.inflate(got) == data
+        if data is raw:
+            assert len(got) <= 1.03 * ref, (len(got), ref)
+        assert len(got) <= 1.08 * ref, (len(got), ref)
+    tiles = [raw] * 6
+    comp = z.compress_batch(tiles, z.DefaultCompression, z.dfGzip)
+    assert all(o.uncompress(c) == raw for c in comp)
+    assert sum(map(len, comp)) <= 1.03 * 6 * len(o.compress(raw, o.DefaultCompression, o.dfGzip))
+    lvl1 = len(z.deflate(raw, 1))
+    assert len(z.deflate(raw, 9)) < lvl1 and len(z.deflate(raw, 2)) < lvl1

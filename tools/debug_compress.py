@@ -32,3 +32,12 @@ for name, raw in cases.items():
         mism = next((i for i in range(min(len(out), len(raw))) if out[i] != raw[i]), None)
         print("%-12s len=%7d comp=%7d ratio=%.3f decoded=%7d firstmismatch=%s err=%s" %
               (name, len(raw), len(d), len(d) / max(1, len(raw)), len(out), mism, err))
+
+print("---- default level vs oracle")
+from oracle import oracle as o
+for name in ("urls", "alice29", "html_x_4", "kppkn", "geo", "zeros1M"):
+    raw = cases[name]
+    d = z.deflate(raw, -1)
+    ok = zlib.decompress(d, -15) == raw
+    ref = len(o.deflate(raw, -1))
+    print("%-10s gpu=%8d oracle(-1)=%8d ratio_to_ref=%.4f ok=%s lvl1=%d" % (name, len(d), ref, len(d) / ref, ok, len(z.deflate(raw, 1))))

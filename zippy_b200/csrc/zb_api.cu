@@ -34,7 +34,7 @@ struct zb200_ctx {
   ZbCrcTables *d_tabs = nullptr;
   DevBuf desc, member_first, fname, masks, recs, hist, chk, cb, chunk_off, member_off, member_check, member_isize;
   DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out;
-  DevBuf in_stage, out_stage;
+  DevBuf in_stage, out_stage, lz2_tables;
   cudaEvent_t ev[10];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> gev;   // per-group events (H2D done, compute done, offsets ready)
@@ -187,7 +187,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
         d.len = (uint32_t)std::min<uint64_t>(ZB_CHUNK_BYTES, len - (uint64_t)k * ZB_CHUNK_BYTES);
         d.member = (uint32_t)(m1 - m0);
         d.flags = (k == 0 ? ZB_CHUNK_FIRST : 0u) | (k == nc - 1 ? ZB_CHUNK_LAST : 0u);
-        d.pad = 0;
+        d.pad = (level == -1 || level >= 2) ? (uint32_t)std::min<uint64_t>(32768, (uint64_t)k * ZB_CHUNK_BYTES) : 0u;
         desc.push_back(d);
       }
       g.bound += zb200_compress_bound((size_t)len, data_format) + 64;
@@ -221,6 +221,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   ENSURE(ctx->chunk_off, max_nc * sizeof(uint64_t));
   ENSURE(ctx->member_check, max_nm * sizeof(uint32_t));
   ENSURE(ctx->member_isize, max_nm * sizeof(uint32_t));
+  if (level == -1 || level >= 2) ENSURE(ctx->lz2_tables, zb_lz2_table_bytes(nullptr));
   {
     int rc = ensure_pinned(ctx, nfirst * sizeof(uint64_t) + 64);
     if (rc) return rc;
@@ -262,6 +263,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
     w.member_check = (uint32_t *)ctx->member_check.p;
     w.member_isize = (uint32_t *)ctx->member_isize.p;
     w.tabs = ctx->d_tabs;
+    w.lz2_tables = (uint4 *)ctx->lz2_tables.p;
     w.n_chunks = (uint32_t)g.nc;
     w.n_members = (uint32_t)(g.m1 - g.m0);
     w.level = level;
@@ -517,7 +519,7 @@ void zb200_shutdown(zb200_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->desc, &ctx->member_first, &ctx->fname, &ctx->masks, &ctx->recs, &ctx->hist, &ctx->chk,
                     &ctx->cb, &ctx->chunk_off, &ctx->member_off, &ctx->member_check, &ctx->member_isize,
                     &ctx->src_off, &ctx->dst_off, &ctx->out_len, &ctx->status, &ctx->expect, &ctx->kind,
-                    &ctx->counter, &ctx->ck_out, &ctx->in_stage, &ctx->out_stage};
+                    &ctx->counter, &ctx->ck_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_tabs) cudaFree(ctx->d_tabs);

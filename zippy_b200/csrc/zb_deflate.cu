@@ -57,7 +57,92 @@ __device__ __forceinline__ uint32_t lz_final_rec(uint32_t mlen, uint32_t dist, i
   return (uint32_t)lc | ((mlen - zb_len_base(lc)) << 5) | ((uint32_t)dc << 10) | ((dist - zb_dist_base(dc)) << 15);
 }
 
-template <int MODE>  // 1: hash-table matcher (level 1 and, for now, the LZ levels); 0: literals only
+
+// Greedy selection inside one 32-position window, uniform control flow.  Lane i holds the
+// match found at position wb + i (m = 0: none; m == LZ_LANE_CAP: at least that long) and its
+// distance.  Candidates are followed as a chain "match -> first candidate at or after its
+// end" (3 doubling rounds cover the at most 8 matches a window can start); a last match that
+// hit the lane cap necessarily leaves the window and is extended by the whole warp, 8 bytes
+// per lane.  Position x of the sub-chunk lives at data[off0 + x].
+__device__ __forceinline__ void lz_select(const uint8_t *data, uint32_t off0, uint32_t wb, uint32_t b1, uint32_t cur,
+                                          uint32_t nvalid, uint32_t &m, uint32_t dist, uint32_t *ring_slot,
+                                          uint32_t &sel, uint32_t &ism, uint32_t &endw) {
+  const int lane = zb_lane();
+  const uint32_t mm = __ballot_sync(ZB_FULL, m != 0);
+  endw = 0;
+  ism = 0;
+  if (mm) {
+    const uint32_t lbit = 1u << lane;
+    const uint32_t endp = (uint32_t)lane + m;
+    const uint32_t rest = shl_clamp(1u, endp) ? (mm >> endp) : 0u;
+    uint32_t nc = rest ? endp + (uint32_t)(__ffs((int)rest) - 1) : 32u;
+    uint32_t vis = 1u << (cur + (uint32_t)(__ffs((int)(mm >> cur)) - 1));
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      vis |= __reduce_or_sync(ZB_FULL, (vis & lbit) ? shl_clamp(1u, nc) : 0u);
+      const uint32_t t = __shfl_sync(ZB_FULL, nc, (int)(nc & 31u));
+      nc = nc < 32u ? t : 32u;
+    }
+    ism = vis;
+    const int lastm = 31 - __clz((int)ism);
+    uint32_t mlast = __shfl_sync(ZB_FULL, m, lastm);
+    if (mlast >= LZ_LANE_CAP) {
+      const uint32_t md = __shfl_sync(ZB_FULL, dist, lastm);
+      const uint32_t pos = wb + (uint32_t)lastm;
+      const uint32_t off = off0 + pos + LZ_LANE_CAP + 8u * (uint32_t)lane;
+      uint32_t x0 = zb_ld32_unaligned(data, off) ^ zb_ld32_unaligned(data, off - md);
+      uint32_t x1 = zb_ld32_unaligned(data, off + 4) ^ zb_ld32_unaligned(data, off + 4 - md);
+      uint32_t nm = x0 ? ((uint32_t)(__ffs((int)x0) - 1) >> 3) : 4u + (x1 ? ((uint32_t)(__ffs((int)x1) - 1) >> 3) : 4u);
+      uint32_t stop = __ballot_sync(ZB_FULL, nm < 8u);
+      if (stop) {
+        int first = __ffs((int)stop) - 1;
+        mlast = LZ_LANE_CAP + 8u * (uint32_t)first + __shfl_sync(ZB_FULL, nm, first);
+      } else {
+        mlast = LZ_LANE_CAP + 256u;
+      }
+      mlast = min(mlast, min((uint32_t)ZB_MAX_MATCH, b1 - pos));
+      if (lane == lastm) m = mlast;
+    }
+    const uint32_t cov = (ism & lbit) ? (low_mask((uint32_t)lane + m) & ~low_mask((uint32_t)lane)) : 0u;
+    const uint32_t covered = __reduce_or_sync(ZB_FULL, cov);
+    sel = ism | (~covered & ~low_mask(cur) & low_mask(nvalid));
+    endw = (uint32_t)lastm + mlast;
+    if (ism & lbit) {
+      uint32_t rank = (uint32_t)__popc(ism & (lbit - 1u));
+      ring_slot[rank] = (m - 3u) | ((dist - 1u) << 9);
+    }
+  } else {
+    sel = low_mask(nvalid) & ~low_mask(cur);
+  }
+}
+
+// One lane per window: publish the window's masks, turn its raw match records into the
+// packer's records and count every token in the sub-chunk histogram.
+__device__ __forceinline__ void lz_batch_pass(const uint8_t *wdata, bool active, uint32_t ksel, uint32_t kism,
+                                              const uint32_t *ring_lane, uint32_t *whist, uint2 *gmask_w,
+                                              uint32_t *grecs_w) {
+  if (active) *gmask_w = make_uint2(ksel, kism);
+  const uint32_t im = active ? kism : 0u;
+  uint32_t s = active ? (ksel & ~kism) : 0u;  // literal tokens
+  while (s) {
+    const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
+    s &= s - 1;
+    const uint32_t sy = wdata[bit];
+    atomicAdd(&whist[sy >> 1], 1u << ((sy & 1u) * 16u));
+  }
+  const uint32_t nmatch = (uint32_t)__popc(im);
+  for (uint32_t k = 0; k < nmatch; k++) {
+    const uint32_t raw = ring_lane[k];
+    int lc, dc;
+    const uint32_t fin = lz_final_rec((raw & 511u) + 3u, (raw >> 9) + 1u, lc, dc);
+    grecs_w[k] = fin;
+    const uint32_t s1 = 257u + (uint32_t)lc, s2 = (uint32_t)ZB_NUM_LITLEN + (uint32_t)dc;
+    atomicAdd(&whist[s1 >> 1], 1u << ((s1 & 1u) * 16u));
+    atomicAdd(&whist[s2 >> 1], 1u << ((s2 & 1u) * 16u));
+  }
+}
+
+template <int MODE>  // 1: single-probe hash matcher (level 1); 0: literals only (levels 0, -2)
 __global__ void __launch_bounds__(LZ_THREADS, 2)
     k_lz(const uint8_t *__restrict__ src, const ZbChunkDesc *__restrict__ desc, uint2 *__restrict__ masks,
          uint32_t *__restrict__ recs, uint16_t *__restrict__ hist, ZbChunkCheck *__restrict__ chk,
@@ -185,54 +270,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
             }
           }
         }
-        // ---- greedy selection: follow the chain "candidate -> first candidate at/after its end" ----
-        const uint32_t mm = __ballot_sync(ZB_FULL, m != 0);
-        uint32_t endw = 0;
-        if (mm) {
-          const uint32_t lbit = 1u << lane;
-          const uint32_t endp = (uint32_t)lane + m;
-          const uint32_t rest = shl_clamp(1u, endp) ? (mm >> endp) : 0u;
-          uint32_t nc = rest ? endp + (uint32_t)(__ffs((int)rest) - 1) : 32u;
-          uint32_t vis = 1u << (cur + (uint32_t)(__ffs((int)(mm >> cur)) - 1));
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            vis |= __reduce_or_sync(ZB_FULL, (vis & lbit) ? shl_clamp(1u, nc) : 0u);
-            const uint32_t t = __shfl_sync(ZB_FULL, nc, (int)(nc & 31u));
-            nc = nc < 32u ? t : 32u;
-          }
-          ism = vis;
-          const int lastm = 31 - __clz((int)ism);
-          uint32_t mlast = __shfl_sync(ZB_FULL, m, lastm);
-          if (mlast >= LZ_LANE_CAP) {
-            // the last selected match hit the lane cap (so it leaves the window): the whole
-            // warp extends it, 8 bytes per lane
-            const uint32_t mc = __shfl_sync(ZB_FULL, c, lastm);
-            const uint32_t pos = wb + (uint32_t)lastm;
-            const uint32_t off = LZ_LANE_CAP + 8u * (uint32_t)lane;
-            uint32_t x0 = zb_ld32_unaligned(data, mis + pos + off) ^ zb_ld32_unaligned(data, mis + mc + off);
-            uint32_t x1 = zb_ld32_unaligned(data, mis + pos + off + 4) ^ zb_ld32_unaligned(data, mis + mc + off + 4);
-            uint32_t nm = x0 ? ((uint32_t)(__ffs((int)x0) - 1) >> 3) : 4u + (x1 ? ((uint32_t)(__ffs((int)x1) - 1) >> 3) : 4u);
-            uint32_t stop = __ballot_sync(ZB_FULL, nm < 8u);
-            if (stop) {
-              int first = __ffs((int)stop) - 1;
-              mlast = LZ_LANE_CAP + 8u * (uint32_t)first + __shfl_sync(ZB_FULL, nm, first);
-            } else {
-              mlast = LZ_LANE_CAP + 256u;
-            }
-            mlast = min(mlast, min((uint32_t)ZB_MAX_MATCH, b1 - pos));
-            if (lane == lastm) m = mlast;
-          }
-          const uint32_t cov = (ism & lbit) ? (low_mask((uint32_t)lane + m) & ~low_mask((uint32_t)lane)) : 0u;
-          const uint32_t covered = __reduce_or_sync(ZB_FULL, cov);
-          sel = ism | (~covered & ~low_mask(cur) & low_mask(nvalid));
-          endw = (uint32_t)lastm + mlast;
-          if (ism & lbit) {
-            uint32_t rank = (uint32_t)__popc(ism & (lbit - 1u));
-            ring[slot * ZB_MATCH_SLOTS + rank] = (m - 3u) | ((p - c - 1u) << 9);
-          }
-        } else {
-          sel = low_mask(nvalid) & ~low_mask(cur);
-        }
+        uint32_t endw;
+        lz_select(data, mis, wb, b1, cur, nvalid, m, p - c, ring + slot * ZB_MATCH_SLOTS, sel, ism, endw);
         entry = wb + max(endw, nvalid);
       }
       if ((uint32_t)lane == slot) {
@@ -243,27 +282,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
       if (slot == 31u || wb + 32 >= b1) {
         __syncwarp();
         const uint32_t bwin = win - slot + (uint32_t)lane;  // this lane's window
-        const bool active = (uint32_t)lane <= slot;
-        if (active) gmask[bwin] = make_uint2(ksel, kism);
-        const uint32_t im = active ? kism : 0u;
-        uint32_t s = active ? (ksel & ~kism) : 0u;  // literal tokens
-        const uint8_t *wdata = data + mis + (bwin << 5);
-        while (s) {
-          const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
-          s &= s - 1;
-          const uint32_t sy = wdata[bit];
-          atomicAdd(&whist[sy >> 1], 1u << ((sy & 1u) * 16u));
-        }
-        const uint32_t nmatch = (uint32_t)__popc(im);
-        for (uint32_t k = 0; k < nmatch; k++) {
-          const uint32_t raw = ring[(uint32_t)lane * ZB_MATCH_SLOTS + k];
-          int lc, dc;
-          const uint32_t fin = lz_final_rec((raw & 511u) + 3u, (raw >> 9) + 1u, lc, dc);
-          grecs[bwin * ZB_MATCH_SLOTS + k] = fin;
-          const uint32_t s1 = 257u + (uint32_t)lc, s2 = (uint32_t)ZB_NUM_LITLEN + (uint32_t)dc;
-          atomicAdd(&whist[s1 >> 1], 1u << ((s1 & 1u) * 16u));
-          atomicAdd(&whist[s2 >> 1], 1u << ((s2 & 1u) * 16u));
-        }
+        lz_batch_pass(data + mis + (bwin << 5), (uint32_t)lane <= slot, ksel, kism, ring + (uint32_t)lane * ZB_MATCH_SLOTS,
+                      whist, gmask + bwin, grecs + bwin * ZB_MATCH_SLOTS);
         ksel = kism = 0;
         __syncwarp();
       }
@@ -287,6 +307,255 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     cc.crc_raw = raw;
     cc.adler = zb_adler_from_sums(a % ZB_ADLER_MOD, b % ZB_ADLER_MOD, len);
     chk[chunk] = cc;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// k_lz2: the matcher for the LZ levels (-1, 2..9; replaces encodeLz77, lz77.nim:10-130, whose
+// head/chain arrays -- 256 KiB + 64 KiB per block -- do not fit next to the data).
+// Same CTA = chunk / warp = 8 KiB sub-chunk mapping as k_lz, with three differences:
+//  * the chunk is staged together with up to 32 KiB of the member's preceding bytes, so a
+//    match can reach back the full DEFLATE window across chunk boundaries;
+//  * each warp's dictionary is a private 4096-bucket x 8-way table of the most recent
+//    positions per hash (one 16-byte bucket = one 128-bit access), kept in global memory
+//    (L2-resident, 64 KiB per warp, one slot per resident CTA: the grid is persistent) and
+//    pre-seeded with the 32 KiB before the sub-chunk; every candidate in the bucket -- plus
+//    the nearest same-hash position inside the current window -- is verified and extended
+//    against shared memory and the longest wins (the reference walks up to 128 chain links);
+//  * one-step lazy evaluation: a match shorter than 16 is dropped when the next position
+//    has a longer one (the reference is greedy; this recovers what the shallower search loses).
+#define LZ2_HIST 32768
+#define LZ2_BUCKETS 4096
+#define LZ2_RING_WINDOWS 16
+#define LZ2_LAZY_MAX 16
+#define LZ2_SM_DATA_BYTES (ZB_CHUNK_BYTES + LZ2_HIST + 64)
+#define LZ2_SM_HIST (LZ2_SM_DATA_BYTES)
+#define LZ2_SM_RING (LZ2_SM_HIST + LZ_SM_HIST_BYTES)
+#define LZ2_SM_RING_BYTES (ZB_WARPS_PER_CHUNK * LZ2_RING_WINDOWS * ZB_MATCH_SLOTS * 4)
+#define LZ2_SM_CRC (LZ2_SM_RING + LZ2_SM_RING_BYTES)
+#define LZ2_SM_LMUL (LZ2_SM_CRC + 4096)
+#define LZ2_SM_PART (LZ2_SM_LMUL + LZ_SM_LMUL_BYTES)
+#define LZ2_SM_BAR (LZ2_SM_PART + LZ_SM_PART_BYTES)
+#define LZ2_SM_TOTAL (LZ2_SM_BAR + 16)
+static_assert(2 * (LZ2_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
+
+__device__ __forceinline__ uint32_t lz2_hash(uint32_t v) { return (v * 0x9E3779B1u) >> 20; }  // 12 bits
+
+// shift `e` into way 0 of a bucket of eight u16 entries (most recent first)
+__device__ __forceinline__ uint4 lz2_push(uint4 b, uint32_t e) {
+  uint4 r;
+  r.w = __funnelshift_l(b.z, b.w, 16);
+  r.z = __funnelshift_l(b.y, b.z, 16);
+  r.y = __funnelshift_l(b.x, b.y, 16);
+  r.x = (b.x << 16) | (e & 0xffffu);
+  return r;
+}
+
+// Insert the window's positions into the warp's table; returns each lane's bucket as it was
+// before this window (the lookup) and the mask of lanes sharing the lane's hash.
+__device__ __forceinline__ uint4 lz2_probe_insert(uint4 *tab, uint32_t v, bool can, uint32_t qwin, uint32_t &grp) {
+  const int lane = zb_lane();
+  const uint32_t h = lz2_hash(v);
+  grp = __match_any_sync(ZB_FULL, can ? h : (0x80000000u | (uint32_t)lane));
+  uint4 old = make_uint4(~0u, ~0u, ~0u, ~0u);
+  if (can) old = __ldcg(&tab[h]);
+  __syncwarp();
+  if (can && lane == 31 - __clz((int)grp)) {  // one writer per bucket: pushes every position of the group, in order
+    uint4 nb = old;
+    for (uint32_t g = grp; g; g &= g - 1) nb = lz2_push(nb, qwin + (uint32_t)(__ffs((int)g) - 1));
+    __stcg(&tab[h], nb);
+  }
+  __syncwarp();
+  return old;
+}
+
+__global__ void __launch_bounds__(LZ_THREADS, 2)
+    k_lz2(const uint8_t *__restrict__ src, const ZbChunkDesc *__restrict__ desc, uint2 *__restrict__ masks,
+          uint32_t *__restrict__ recs, uint16_t *__restrict__ hist, ZbChunkCheck *__restrict__ chk,
+          const ZbCrcTables *__restrict__ tabs, uint4 *__restrict__ tables, uint32_t n_chunks) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t *data = smem;
+  uint32_t *hist_all = reinterpret_cast<uint32_t *>(smem + LZ2_SM_HIST);
+  uint32_t *ring_all = reinterpret_cast<uint32_t *>(smem + LZ2_SM_RING);
+  uint32_t *crc_tab = reinterpret_cast<uint32_t *>(smem + LZ2_SM_CRC);
+  uint32_t *lane_mul = reinterpret_cast<uint32_t *>(smem + LZ2_SM_LMUL);
+  uint64_t *part = reinterpret_cast<uint64_t *>(smem + LZ2_SM_PART);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + LZ2_SM_BAR);
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *whist = hist_all + warp * ZB_HIST_WORDS;
+  uint32_t *ring = ring_all + warp * LZ2_RING_WINDOWS * ZB_MATCH_SLOTS;
+  uint4 *tab = tables + ((size_t)blockIdx.x * ZB_WARPS_PER_CHUNK + (size_t)warp) * LZ2_BUCKETS;
+
+  if (tid == 0) {
+    zb_mbar_init(bar, 1);
+    zb_fence_mbar_init();
+  }
+  for (int i = tid; i < 1024; i += LZ_THREADS) crc_tab[i] = (&tabs->mul1024[0][0])[i];
+  if (tid < 33) lane_mul[tid] = tabs->lane_mul[tid];
+  if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = tabs->sub_mul[tid - 64];
+  __syncthreads();
+
+  uint32_t phase = 0;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const ZbChunkDesc d = desc[chunk];
+    const uint32_t len = d.len, hb = d.pad;  // pad = bytes of history staged in front of the chunk
+    const uint8_t *rsrc = src + d.src_off - hb;
+    const uint32_t mis = (uint32_t)((uintptr_t)rsrc & 15u);
+    const uint32_t off0 = mis + hb;           // chunk position x lives at data[off0 + x]
+    if (tid == 0 && hb + len) zb_stage_chunk(data, rsrc, hb + len, bar);
+    for (int i = tid; i < ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS; i += LZ_THREADS) hist_all[i] = 0;
+    {  // empty this warp's dictionary
+      uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u);
+      for (int i = lane; i < LZ2_BUCKETS; i += 32) __stcg(&tab[i], ff);
+    }
+    __syncthreads();
+    if (hb + len) {
+      zb_mbar_wait(bar, phase);
+      phase ^= 1u;
+    }
+
+    const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES;
+    const uint32_t b1 = min(b0 + ZB_SUB_BYTES, len);
+    {
+      ZbCheck c;
+      c.crc_raw = 0;
+      c.a_sum = c.b_sum = 0;
+      uint32_t n = b0 < len ? b1 - b0 : 0;
+      if (n) {
+        c = zb_warp_checksums(data, off0 + b0, n, crc_tab, lane_mul);
+        const uint32_t after = len - b1;
+        if (after) {
+          const uint32_t shift = ((after & (ZB_SUB_BYTES - 1)) == 0) ? lane_mul[33 + after / ZB_SUB_BYTES] : zb_xpow8(after);
+          c.crc_raw = zb_gf2_mul(c.crc_raw, shift);
+          c.b_sum += (uint64_t)after * c.a_sum;
+        }
+      }
+      if (lane == 0) {
+        part[warp * 3 + 0] = c.crc_raw;
+        part[warp * 3 + 1] = c.a_sum;
+        part[warp * 3 + 2] = c.b_sum;
+      }
+      __syncwarp();
+    }
+
+    if (b0 < len) {
+      const uint32_t rlen = hb + len;  // staged bytes; region position q = hb + chunk position
+      {
+        // pre-seed with (up to) the 32 KiB before this sub-chunk
+        const uint32_t q0 = hb + b0;
+        uint32_t grp;
+        for (uint32_t s = q0 > LZ2_HIST ? q0 - LZ2_HIST : 0u; s < q0; s += 32) {
+          const uint32_t q = s + (uint32_t)lane;
+          const bool can = q < q0 && q + 4 <= rlen;
+          const uint32_t v = zb_ld32_unaligned(data, mis + q);
+          (void)lz2_probe_insert(tab, v, can, s, grp);
+        }
+      }
+      uint32_t entry = b0;
+      uint32_t ksel = 0, kism = 0;
+      uint2 *gmask = masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
+      uint32_t *grecs = recs + (size_t)chunk * ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS;
+      for (uint32_t wb = b0; wb < b1; wb += 32) {
+        const uint32_t win = wb >> 5, slot = win & (LZ2_RING_WINDOWS - 1u);
+        const uint32_t p = wb + (uint32_t)lane;
+        const uint32_t q = hb + p;               // region position of this lane
+        const uint32_t v = zb_ld32_unaligned(data, off0 + p);
+        const bool can = (p + 4 <= len);
+        uint32_t grp;
+        const uint4 bucket = lz2_probe_insert(tab, v, can, hb + wb, grp);
+        uint32_t sel = 0, ism = 0;
+        if (entry < wb + 32) {
+          const uint32_t nvalid = min(32u, b1 - wb);
+          const uint32_t cur = entry - wb;
+          const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
+          uint32_t m = 0, dist = 1;
+          if (can && p >= entry && limit >= ZB_MIN_MATCH) {
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(data) + ((off0 + p) >> 2);
+            const uint32_t sp = ((off0 + p) & 3u) * 8u;
+            const uint32_t lower = grp & ((1u << lane) - 1u);
+            // candidate 0: the nearest same-hash position inside this window; 1..8: the bucket
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) {
+              uint32_t dcand;
+              if (k == 0) {
+                if (!lower) continue;
+                dcand = (uint32_t)lane - (uint32_t)(31 - __clz((int)lower));
+              } else {
+                const uint32_t wsel = (k - 1) >> 1;
+                const uint32_t word = wsel == 0 ? bucket.x : wsel == 1 ? bucket.y : wsel == 2 ? bucket.z : bucket.w;
+                const uint32_t e = ((k - 1) & 1) ? (word >> 16) : (word & 0xffffu);
+                if (e == 0xffffu) break;               // ways fill from the front
+                dcand = (q - e) & 0xffffu;
+                if (dcand == 0 || dcand > ZB_MAX_DIST || dcand > q) continue;
+              }
+              const uint32_t co = off0 + p - dcand;
+              if (m >= 4 && data[co + m] != data[off0 + p + m]) continue;  // cannot beat the best so far
+              const uint32_t *wc = reinterpret_cast<const uint32_t *>(data) + (co >> 2);
+              const uint32_t sc = (co & 3u) * 8u;
+              uint32_t hp = wp[1], hc = wc[1];
+              if (__funnelshift_r(wc[0], hc, sc) != v) continue;
+              uint32_t mc = 4;
+#pragma unroll 1
+              for (int j = 2; j <= LZ_LANE_CAP / 4; j++) {
+                const uint32_t np = wp[j], nq = wc[j];
+                const uint32_t x = __funnelshift_r(hp, np, sp) ^ __funnelshift_r(hc, nq, sc);
+                if (x) {
+                  mc += (uint32_t)(__ffs((int)x) - 1) >> 3;
+                  break;
+                }
+                mc += 4;
+                hp = np;
+                hc = nq;
+              }
+              if (mc < LZ_LANE_CAP) mc = min(mc, limit);
+              if (mc > m) {
+                m = mc;
+                dist = dcand;
+                if (m >= LZ_LANE_CAP || m >= limit) break;
+              }
+            }
+          }
+          // one-step lazy evaluation (zlib's max_lazy idea)
+          const uint32_t mnext = __shfl_down_sync(ZB_FULL, m, 1);
+          if (lane < 31 && m != 0 && m < LZ2_LAZY_MAX && mnext > m) m = 0;
+          uint32_t endw;
+          lz_select(data, off0, wb, b1, cur, nvalid, m, dist, ring + slot * ZB_MATCH_SLOTS, sel, ism, endw);
+          entry = wb + max(endw, nvalid);
+        }
+        if ((uint32_t)lane == slot) {
+          ksel = sel;
+          kism = ism;
+        }
+        if (slot == LZ2_RING_WINDOWS - 1u || wb + 32 >= b1) {
+          __syncwarp();
+          const uint32_t bwin = win - slot + (uint32_t)lane;
+          lz_batch_pass(data + off0 + (bwin << 5), (uint32_t)lane <= slot, ksel, kism,
+                        ring + ((uint32_t)lane & (LZ2_RING_WINDOWS - 1u)) * ZB_MATCH_SLOTS, whist, gmask + bwin,
+                        grecs + bwin * ZB_MATCH_SLOTS);
+          ksel = kism = 0;
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+    {
+      uint32_t *gh = reinterpret_cast<uint32_t *>(hist + (size_t)chunk * ZB_WARPS_PER_CHUNK * ZB_HIST_SYMS);
+      for (int i = tid; i < ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS; i += LZ_THREADS) gh[i] = hist_all[i];
+    }
+    if (tid == 0) {
+      uint32_t raw = 0;
+      uint64_t a = 0, b = 0;
+      for (int w = 0; w < ZB_WARPS_PER_CHUNK; w++) {
+        raw ^= (uint32_t)part[w * 3 + 0];
+        a += part[w * 3 + 1];
+        b += part[w * 3 + 2];
+      }
+      ZbChunkCheck cc;
+      cc.crc_raw = raw;
+      cc.adler = zb_adler_from_sums(a % ZB_ADLER_MOD, b % ZB_ADLER_MOD, len);
+      chk[chunk] = cc;
+    }
+    __syncthreads();  // shared memory is reused by the next chunk
   }
 }
 
@@ -565,18 +834,35 @@ __global__ void __launch_bounds__(LZ_THREADS)
 }
 
 // ------------------------------------------------------------------------------------
+static bool zb_is_lz_level(int level) { return level == -1 || level >= 2; }
+size_t zb_lz2_table_bytes(int *grid_out) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = 2 * sms;
+  if (grid_out) *grid_out = grid;
+  return (size_t)grid * ZB_WARPS_PER_CHUNK * LZ2_BUCKETS * sizeof(uint4);
+}
 cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_lz<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
     cudaFuncSetAttribute(k_lz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
+    cudaFuncSetAttribute(k_lz2, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ2_SM_TOTAL);
     attr_set = true;
   }
   if (w.n_chunks == 0) return cudaSuccess;
-  if (w.level == -2 || w.level == 0)
+  if (zb_is_lz_level(w.level)) {
+    int grid = 0;
+    (void)zb_lz2_table_bytes(&grid);
+    if ((uint32_t)grid > w.n_chunks) grid = (int)w.n_chunks;
+    k_lz2<<<grid, LZ_THREADS, LZ2_SM_TOTAL, s>>>(w.src, w.desc, w.masks, w.recs, w.hist, w.chk, w.tabs, w.lz2_tables,
+                                                 w.n_chunks);
+  } else if (w.level == -2 || w.level == 0) {
     k_lz<0><<<w.n_chunks, LZ_THREADS, LZ_SM_TOTAL, s>>>(w.src, w.desc, w.masks, w.recs, w.hist, w.chk, w.tabs);
-  else
+  } else {
     k_lz<1><<<w.n_chunks, LZ_THREADS, LZ_SM_TOTAL, s>>>(w.src, w.desc, w.masks, w.recs, w.hist, w.chk, w.tabs);
+  }
   return cudaGetLastError();
 }
 cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s) {

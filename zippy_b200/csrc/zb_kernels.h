@@ -13,7 +13,7 @@ struct ZbChunkDesc {
   uint32_t len;       // 0..65536
   uint32_t member;    // index of the input this chunk belongs to
   uint32_t flags;     // bit0: first chunk of its member, bit1: last chunk
-  uint32_t pad;
+  uint32_t pad;       // k_lz2: bytes of the member's preceding data staged as history (<= 32768)
 };
 #define ZB_CHUNK_FIRST 1u
 #define ZB_CHUNK_LAST 2u
@@ -43,10 +43,12 @@ struct ZbCompressWork {
   const uint64_t *out_base_ptr;// ... or, when non-null, a device word holding it (the previous group's end),
                                // so consecutive groups can be enqueued without a host round trip
   const ZbCrcTables *tabs;     // device
+  uint4 *lz2_tables;           // k_lz2 dictionaries: [grid][8 warps][4096 buckets] (LZ levels only)
   uint32_t n_chunks, n_members;
   int level, data_format;
 };
 
+size_t zb_lz2_table_bytes(int *grid_out);
 cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_scan(const ZbCompressWork &w, cudaStream_t s);
