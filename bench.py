@@ -48,6 +48,14 @@ def text_corpus():
     return util.text_corpus(util.load_corpus())
 
 
+def bench_config(n, level, world):
+    return {"workload": "C2: batch %d x 64 KiB synthetic text-entropy blocks per GPU, compress level=%d "
+                        "dfGzip, one gzip member per block" % (n, level),
+            "blocks_per_gpu": n, "block_bytes": BLOCK, "level": level, "data_format": "dfGzip",
+            "l2": "inputs (4 GiB/GPU) larger than L2; no flush needed",
+            "parallelism": "independent members sharded over %d GPU(s); NCCL all_gather of sizes" % world}
+
+
 def block_offsets(T_len, first, count):
     return np.array([sm64(0xC2 + i) % (T_len - BLOCK) for i in range(first, first + count)], dtype=np.int64)
 
@@ -107,7 +115,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(T, n_blocks_hint, seconds=12.0, threads=None):
+def cpu_baseline(T, n_blocks_hint, seconds=12.0, threads=None, level=1):
     """Oracle (port of the reference's level-1 path) over independent blocks on all host cores."""
     from oracle import oracle as o
     cores = threads or os.cpu_count() or 1
@@ -124,16 +132,16 @@ def cpu_baseline(T, n_blocks_hint, seconds=12.0, threads=None):
     pilot_n = max(cores * 4, 16)
     buf, bo = make(pilot_n)
     t0 = time.perf_counter()
-    o.compress_batch(buf, bo, 1, o.dfGzip, threads=cores)
+    o.compress_batch(buf, bo, level, o.dfGzip, threads=cores)
     dt = max(time.perf_counter() - t0, 1e-3)
     nb = int(min(max(pilot_n, pilot_n * seconds / dt), 65536))
     buf, bo = make(nb)
     t0 = time.perf_counter()
-    total, lens, st = o.compress_batch(buf, bo, 1, o.dfGzip, threads=cores)
+    total, lens, st = o.compress_batch(buf, bo, level, o.dfGzip, threads=cores)
     dt = time.perf_counter() - t0
     assert not st.any()
     return {"value": nb * BLOCK / GIB / dt, "unit": "GiB/s", "cores": cores, "kind": "port",
-            "sample": "%d x 64 KiB C2 text blocks, oracle level 1 gzip, %d threads, %.1f s" % (nb, cores, dt),
+            "sample": "%d x 64 KiB C2 text blocks, oracle level %d gzip, %d threads, %.1f s" % (nb, level, cores, dt),
             "ratio": float(total) / (nb * BLOCK)}, nb, dt
 
 
@@ -146,7 +154,7 @@ def run_reference(args, rank, world):
     per_step = max(6.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     times, nbs = [], []
     for s in range(args.warmup + args.steps):
-        cb, nb, dt = cpu_baseline(T, 0, seconds=per_step, threads=cores)
+        cb, nb, dt = cpu_baseline(T, 0, seconds=per_step, threads=cores, level=args.level)
         if s >= args.warmup:
             times.append(dt)
             nbs.append(nb)
@@ -155,11 +163,11 @@ def run_reference(args, rank, world):
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "C2: 64 KiB text-corpus blocks, level 1 (BestSpeed), dfGzip; bounded CPU sample",
-                      "blocks_per_step": int(np.mean(nbs)), "block_bytes": BLOCK},
+           "config": bench_config(BLOCKS_PER_GPU, args.level, args.gpus),
            "cpu_baseline": {"value": val, "unit": "GiB/s", "cores": cores, "kind": "port",
-                            "sample": "%d blocks/step, oracle port of zippy level 1 (Nim unavailable: reference "
-                                      "cannot be compiled here), all host threads" % int(np.mean(nbs))},
+                            "sample": "%d x 64 KiB C2 blocks per step (bounded sample of the config), oracle port of "
+                                      "zippy level 1 (Nim unavailable: the reference cannot be compiled here), "
+                                      "all %d host threads" % (int(np.mean(nbs)), cores)},
            "e2e": {"value": val, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -350,16 +358,12 @@ def main():
 
     cpu = None
     if not args.no_cpu:
-        cpu, _, _ = cpu_baseline(T, n)
+        cpu, _, _ = cpu_baseline(T, n, level=args.level)
 
     out = {"metric": "compress_level1_gzip_input_throughput", "value": value, "unit": "GiB/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "C2: batch %d x 64 KiB synthetic text-entropy blocks per GPU, compress level=%d "
-                                  "dfGzip, one gzip member per block" % (n, args.level),
-                      "blocks_per_gpu": n, "block_bytes": BLOCK, "level": args.level, "data_format": "dfGzip",
-                      "l2": "inputs (4 GiB/GPU) larger than L2; no flush needed",
-                      "parallelism": "independent members sharded over %d GPU(s); NCCL all_gather of sizes" % world},
+           "config": bench_config(n, args.level, world),
            "ratio": comp_bytes / float(n * BLOCK), "clocks": clk, "gpu_launches": int(launches),
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
            "uncompress": {"out_gibs": n * BLOCK / GIB / (inflate_ms / 1e3), "in_gibs": comp_bytes / GIB / (inflate_ms / 1e3),

@@ -1,0 +1,101 @@
+#!/usr/bin/env python3
+"""Secondary measurements for BASELINE.json configs 3 and 4 (not the driver's bench line):
+  c3: batch uncompress of 65536 gzip members = the 23 reference fixtures tiled,
+      byte-exact against the fixtures' manifest; GiB/s of compressed input and of output.
+  c4: compress level=Default of urls.10K tiled to ~4 GiB, total size vs the oracle's level -1.
+Device-resident buffers, CUDA events on the ctx stream, 1 GPU."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GIB = float(1 << 30)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="c3,c4")
+    ap.add_argument("--members", type=int, default=65536)
+    ap.add_argument("--tiles", type=int, default=6118)
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import zippy_b200 as z
+    from oracle import oracle as o
+    from tests import util
+    dev = torch.device("cuda", 0)
+    ctx = z.Context(0)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    if "c3" in args.what:
+        golden = util.load_golden()
+        names = sorted(n for n in golden if n.endswith(".gz"))
+        assert len(names) == 23
+        cyc = [golden[n][0] for n in names]
+        cyc_bytes = np.frombuffer(b"".join(cyc), dtype=np.uint8)
+        n = args.members
+        reps = (n + 22) // 23
+        d_src = torch.from_numpy(cyc_bytes.copy()).to(dev).repeat(reps)
+        lens = np.array([len(c) for c in cyc] * reps, dtype=np.uint64)[:n]
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        sizes, st = ctx.uncompressed_sizes_device(d_src.data_ptr(), offs, z.dfDetect)
+        assert not st.any()
+        doffs = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(sizes, out=doffs[1:])
+        d_dst = torch.empty(int(doffs[n]) + 64, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            out_lens, st = ctx.uncompress_batch_device(d_src.data_ptr(), offs, z.dfDetect, d_dst.data_ptr(), doffs)
+        assert not st.any() and (out_lens == sizes).all()
+        host = d_dst[:int(doffs[23])].cpu().numpy()
+        for i, nme in enumerate(names):  # byte-exact against the reference's fixtures
+            assert util.sha(host[int(doffs[i]):int(doffs[i + 1])].tobytes()) == golden[nme][1]["sha256"], nme
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            ctx.uncompress_batch_device(d_src.data_ptr(), offs, z.dfDetect, d_dst.data_ptr(), doffs)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        t = ctx.timing()
+        print(json.dumps({"workload": "C3: %d gzip members (23 reference fixtures tiled), batch uncompress" % n,
+                          "in_bytes": int(offs[n]), "out_bytes": int(doffs[n]), "ms": ms,
+                          "in_gibs": int(offs[n]) / GIB / (ms / 1e3), "out_gibs": int(doffs[n]) / GIB / (ms / 1e3),
+                          "inflate_ms": t["inflate_ms"], "verify_ms": t["verify_ms"],
+                          "parity": "first cycle sha256 == manifest; all members CRC+ISIZE verified on device"}))
+        del d_src, d_dst
+
+    if "c4" in args.what:
+        raw = util.load_corpus()["urls.10K"]
+        n = args.tiles
+        d_src = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev).repeat(n)
+        offs = np.arange(n + 1, dtype=np.uint64) * len(raw)
+        cap = n * (len(raw) + 256)
+        d_dst = torch.empty(cap, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            oo = ctx.compress_batch_device(d_src.data_ptr(), offs, z.DefaultCompression, z.dfGzip, d_dst.data_ptr(), cap)
+        first = d_dst[:int(oo[1])].cpu().numpy().tobytes()
+        assert o.uncompress(first) == raw
+        ref = len(o.compress(raw, o.DefaultCompression, o.dfGzip))
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            ctx.compress_batch_device(d_src.data_ptr(), offs, z.DefaultCompression, z.dfGzip, d_dst.data_ptr(), cap)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        print(json.dumps({"workload": "C4: urls.10K x %d tiles, compress level=Default dfGzip" % n,
+                          "in_bytes": int(offs[n]), "out_bytes": int(oo[n]), "ms": ms,
+                          "in_gibs": int(offs[n]) / GIB / (ms / 1e3), "ratio": int(oo[n]) / float(offs[n]),
+                          "oracle_level6_ratio": ref / float(len(raw)),
+                          "size_vs_reference": int(oo[n]) / float(ref * n), "timing": ctx.timing()}))
+
+
+if __name__ == "__main__":
+    main()

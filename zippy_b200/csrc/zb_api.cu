@@ -263,7 +263,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
     w.member_check = (uint32_t *)ctx->member_check.p;
     w.member_isize = (uint32_t *)ctx->member_isize.p;
     w.tabs = ctx->d_tabs;
-    w.lz2_tables = (uint4 *)ctx->lz2_tables.p;
+    w.lz2_tables = (uint2 *)ctx->lz2_tables.p;
     w.n_chunks = (uint32_t)g.nc;
     w.n_members = (uint32_t)(g.m1 - g.m0);
     w.level = level;

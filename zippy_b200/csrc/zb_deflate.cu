@@ -316,16 +316,16 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 // Same CTA = chunk / warp = 8 KiB sub-chunk mapping as k_lz, with three differences:
 //  * the chunk is staged together with up to 32 KiB of the member's preceding bytes, so a
 //    match can reach back the full DEFLATE window across chunk boundaries;
-//  * each warp's dictionary is a private 4096-bucket x 8-way table of the most recent
-//    positions per hash (one 16-byte bucket = one 128-bit access), kept in global memory
-//    (L2-resident, 64 KiB per warp, one slot per resident CTA: the grid is persistent) and
+//  * each warp's dictionary is a private 8192-bucket x 4-way table of the most recent
+//    positions per hash (one 8-byte bucket = one 64-bit access), kept in global memory
+//    (64 KiB per warp, one slot per resident CTA: the grid is persistent) and
 //    pre-seeded with the 32 KiB before the sub-chunk; every candidate in the bucket -- plus
 //    the nearest same-hash position inside the current window -- is verified and extended
 //    against shared memory and the longest wins (the reference walks up to 128 chain links);
 //  * one-step lazy evaluation: a match shorter than 16 is dropped when the next position
 //    has a longer one (the reference is greedy; this recovers what the shallower search loses).
 #define LZ2_HIST 32768
-#define LZ2_BUCKETS 4096
+#define LZ2_BUCKETS 8192
 #define LZ2_RING_WINDOWS 16
 #define LZ2_LAZY_MAX 16
 #define LZ2_SM_DATA_BYTES (ZB_CHUNK_BYTES + LZ2_HIST + 64)
@@ -339,13 +339,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 #define LZ2_SM_TOTAL (LZ2_SM_BAR + 16)
 static_assert(2 * (LZ2_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
 
-__device__ __forceinline__ uint32_t lz2_hash(uint32_t v) { return (v * 0x9E3779B1u) >> 20; }  // 12 bits
+__device__ __forceinline__ uint32_t lz2_hash(uint32_t v) { return (v * 0x9E3779B1u) >> 19; }  // 13 bits
 
-// shift `e` into way 0 of a bucket of eight u16 entries (most recent first)
-__device__ __forceinline__ uint4 lz2_push(uint4 b, uint32_t e) {
-  uint4 r;
-  r.w = __funnelshift_l(b.z, b.w, 16);
-  r.z = __funnelshift_l(b.y, b.z, 16);
+// shift `e` into way 0 of a bucket of four u16 entries (most recent first)
+__device__ __forceinline__ uint2 lz2_push(uint2 b, uint32_t e) {
+  uint2 r;
   r.y = __funnelshift_l(b.x, b.y, 16);
   r.x = (b.x << 16) | (e & 0xffffu);
   return r;
@@ -353,15 +351,15 @@ __device__ __forceinline__ uint4 lz2_push(uint4 b, uint32_t e) {
 
 // Insert the window's positions into the warp's table; returns each lane's bucket as it was
 // before this window (the lookup) and the mask of lanes sharing the lane's hash.
-__device__ __forceinline__ uint4 lz2_probe_insert(uint4 *tab, uint32_t v, bool can, uint32_t qwin, uint32_t &grp) {
+__device__ __forceinline__ uint2 lz2_probe_insert(uint2 *tab, uint32_t v, bool can, uint32_t qwin, uint32_t &grp) {
   const int lane = zb_lane();
   const uint32_t h = lz2_hash(v);
   grp = __match_any_sync(ZB_FULL, can ? h : (0x80000000u | (uint32_t)lane));
-  uint4 old = make_uint4(~0u, ~0u, ~0u, ~0u);
+  uint2 old = make_uint2(~0u, ~0u);
   if (can) old = __ldcg(&tab[h]);
   __syncwarp();
   if (can && lane == 31 - __clz((int)grp)) {  // one writer per bucket: pushes every position of the group, in order
-    uint4 nb = old;
+    uint2 nb = old;
     for (uint32_t g = grp; g; g &= g - 1) nb = lz2_push(nb, qwin + (uint32_t)(__ffs((int)g) - 1));
     __stcg(&tab[h], nb);
   }
@@ -369,10 +367,42 @@ __device__ __forceinline__ uint4 lz2_probe_insert(uint4 *tab, uint32_t v, bool c
   return old;
 }
 
+// Verify and extend one candidate at distance dcand against the lane's position; keep it if
+// it beats the best match so far.  Position x of the chunk lives at data[off0 + x].
+__device__ __forceinline__ void lz2_eval(const uint8_t *data, uint32_t poff, uint32_t q, uint32_t v, uint32_t limit,
+                                         uint32_t dcand, uint32_t &m, uint32_t &dist) {
+  if (dcand == 0 || dcand > ZB_MAX_DIST || dcand > q) return;
+  const uint32_t co = poff - dcand;
+  if (m >= 4 && data[co + m] != data[poff + m]) return;  // cannot beat the best so far
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>(data) + (poff >> 2);
+  const uint32_t *wc = reinterpret_cast<const uint32_t *>(data) + (co >> 2);
+  const uint32_t sp = (poff & 3u) * 8u, sc = (co & 3u) * 8u;
+  uint32_t hp = wp[1], hc = wc[1];
+  if (__funnelshift_r(wc[0], hc, sc) != v) return;
+  uint32_t mc = 4;
+#pragma unroll 1
+  for (int j = 2; j <= LZ_LANE_CAP / 4; j++) {
+    const uint32_t np = wp[j], nq = wc[j];
+    const uint32_t x = __funnelshift_r(hp, np, sp) ^ __funnelshift_r(hc, nq, sc);
+    if (x) {
+      mc += (uint32_t)(__ffs((int)x) - 1) >> 3;
+      break;
+    }
+    mc += 4;
+    hp = np;
+    hc = nq;
+  }
+  if (mc < LZ_LANE_CAP) mc = min(mc, limit);
+  if (mc > m) {
+    m = mc;
+    dist = dcand;
+  }
+}
+
 __global__ void __launch_bounds__(LZ_THREADS, 2)
     k_lz2(const uint8_t *__restrict__ src, const ZbChunkDesc *__restrict__ desc, uint2 *__restrict__ masks,
           uint32_t *__restrict__ recs, uint16_t *__restrict__ hist, ZbChunkCheck *__restrict__ chk,
-          const ZbCrcTables *__restrict__ tabs, uint4 *__restrict__ tables, uint32_t n_chunks) {
+          const ZbCrcTables *__restrict__ tabs, uint2 *__restrict__ tables, uint32_t n_chunks) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *data = smem;
   uint32_t *hist_all = reinterpret_cast<uint32_t *>(smem + LZ2_SM_HIST);
@@ -384,7 +414,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *whist = hist_all + warp * ZB_HIST_WORDS;
   uint32_t *ring = ring_all + warp * LZ2_RING_WINDOWS * ZB_MATCH_SLOTS;
-  uint4 *tab = tables + ((size_t)blockIdx.x * ZB_WARPS_PER_CHUNK + (size_t)warp) * LZ2_BUCKETS;
+  uint2 *tab = tables + ((size_t)blockIdx.x * ZB_WARPS_PER_CHUNK + (size_t)warp) * LZ2_BUCKETS;
 
   if (tid == 0) {
     zb_mbar_init(bar, 1);
@@ -405,7 +435,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     if (tid == 0 && hb + len) zb_stage_chunk(data, rsrc, hb + len, bar);
     for (int i = tid; i < ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS; i += LZ_THREADS) hist_all[i] = 0;
     {  // empty this warp's dictionary
-      uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u);
+      uint2 ff = make_uint2(~0u, ~0u);
       for (int i = lane; i < LZ2_BUCKETS; i += 32) __stcg(&tab[i], ff);
     }
     __syncthreads();
@@ -462,7 +492,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
         const uint32_t v = zb_ld32_unaligned(data, off0 + p);
         const bool can = (p + 4 <= len);
         uint32_t grp;
-        const uint4 bucket = lz2_probe_insert(tab, v, can, hb + wb, grp);
+        const uint2 bucket = lz2_probe_insert(tab, v, can, hb + wb, grp);
         uint32_t sel = 0, ism = 0;
         if (entry < wb + 32) {
           const uint32_t nvalid = min(32u, b1 - wb);
@@ -470,50 +500,28 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
           uint32_t m = 0, dist = 1;
           if (can && p >= entry && limit >= ZB_MIN_MATCH) {
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(data) + ((off0 + p) >> 2);
-            const uint32_t sp = ((off0 + p) & 3u) * 8u;
+            // candidates, nearest first: the closest same-hash position inside this window, then
+            // the bucket's four ways (most recent first).  Once a match of 8+ is in hand only one
+            // more candidate is tried (the reference quarters its chain budget there, lz77.nim:104).
+            const uint32_t poff = off0 + p;
             const uint32_t lower = grp & ((1u << lane) - 1u);
-            // candidate 0: the nearest same-hash position inside this window; 1..8: the bucket
-#pragma unroll 1
-            for (int k = 0; k < 9; k++) {
-              uint32_t dcand;
-              if (k == 0) {
-                if (!lower) continue;
-                dcand = (uint32_t)lane - (uint32_t)(31 - __clz((int)lower));
-              } else {
-                const uint32_t wsel = (k - 1) >> 1;
-                const uint32_t word = wsel == 0 ? bucket.x : wsel == 1 ? bucket.y : wsel == 2 ? bucket.z : bucket.w;
-                const uint32_t e = ((k - 1) & 1) ? (word >> 16) : (word & 0xffffu);
-                if (e == 0xffffu) break;               // ways fill from the front
-                dcand = (q - e) & 0xffffu;
-                if (dcand == 0 || dcand > ZB_MAX_DIST || dcand > q) continue;
-              }
-              const uint32_t co = off0 + p - dcand;
-              if (m >= 4 && data[co + m] != data[off0 + p + m]) continue;  // cannot beat the best so far
-              const uint32_t *wc = reinterpret_cast<const uint32_t *>(data) + (co >> 2);
-              const uint32_t sc = (co & 3u) * 8u;
-              uint32_t hp = wp[1], hc = wc[1];
-              if (__funnelshift_r(wc[0], hc, sc) != v) continue;
-              uint32_t mc = 4;
-#pragma unroll 1
-              for (int j = 2; j <= LZ_LANE_CAP / 4; j++) {
-                const uint32_t np = wp[j], nq = wc[j];
-                const uint32_t x = __funnelshift_r(hp, np, sp) ^ __funnelshift_r(hc, nq, sc);
-                if (x) {
-                  mc += (uint32_t)(__ffs((int)x) - 1) >> 3;
-                  break;
-                }
-                mc += 4;
-                hp = np;
-                hc = nq;
-              }
-              if (mc < LZ_LANE_CAP) mc = min(mc, limit);
-              if (mc > m) {
-                m = mc;
-                dist = dcand;
-                if (m >= LZ_LANE_CAP || m >= limit) break;
-              }
+            if (lower) lz2_eval(data, poff, q, v, limit, (uint32_t)lane - (uint32_t)(31 - __clz((int)lower)), m, dist);
+            const uint32_t e0 = bucket.x & 0xffffu, e1 = bucket.x >> 16, e2 = bucket.y & 0xffffu, e3 = bucket.y >> 16;
+            const uint32_t stop = min(limit, (uint32_t)LZ_LANE_CAP);
+            int budget = 4;
+            if (e0 != 0xffffu && m < stop) {
+              lz2_eval(data, poff, q, v, limit, (q - e0) & 0xffffu, m, dist);
+              if (m >= 8) budget = 2;
             }
+            if (e1 != 0xffffu && m < stop && budget > 1) {
+              lz2_eval(data, poff, q, v, limit, (q - e1) & 0xffffu, m, dist);
+              if (m >= 8) budget = min(budget, 3);
+            }
+            if (e2 != 0xffffu && m < stop && budget > 2) {
+              lz2_eval(data, poff, q, v, limit, (q - e2) & 0xffffu, m, dist);
+              if (m >= 8) budget = min(budget, 3);
+            }
+            if (e3 != 0xffffu && m < stop && budget > 3) lz2_eval(data, poff, q, v, limit, (q - e3) & 0xffffu, m, dist);
           }
           // one-step lazy evaluation (zlib's max_lazy idea)
           const uint32_t mnext = __shfl_down_sync(ZB_FULL, m, 1);
@@ -841,7 +849,7 @@ size_t zb_lz2_table_bytes(int *grid_out) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = 2 * sms;
   if (grid_out) *grid_out = grid;
-  return (size_t)grid * ZB_WARPS_PER_CHUNK * LZ2_BUCKETS * sizeof(uint4);
+  return (size_t)grid * ZB_WARPS_PER_CHUNK * LZ2_BUCKETS * sizeof(uint2);
 }
 cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s) {
   static bool attr_set = false;

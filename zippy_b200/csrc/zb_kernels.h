@@ -43,7 +43,7 @@ struct ZbCompressWork {
   const uint64_t *out_base_ptr;// ... or, when non-null, a device word holding it (the previous group's end),
                                // so consecutive groups can be enqueued without a host round trip
   const ZbCrcTables *tabs;     // device
-  uint4 *lz2_tables;           // k_lz2 dictionaries: [grid][8 warps][4096 buckets] (LZ levels only)
+  uint2 *lz2_tables;           // k_lz2 dictionaries: [grid][8 warps][4096 buckets x 4 ways] (LZ levels only)
   uint32_t n_chunks, n_members;
   int level, data_format;
 };
