@@ -52,7 +52,7 @@ def bench_config(n, level, world):
     return {"workload": "C2: batch %d x 64 KiB synthetic text-entropy blocks per GPU, compress level=%d "
                         "dfGzip, one gzip member per block" % (n, level),
             "blocks_per_gpu": n, "block_bytes": BLOCK, "level": level, "data_format": "dfGzip",
-            "l2": "inputs (4 GiB/GPU) larger than L2; no flush needed",
+            "l2": "inputs (4 GiB/GPU) larger than L2; no flush needed", "launch_group_chunks": n,
             "parallelism": "independent members sharded over %d GPU(s); NCCL all_gather of sizes" % world}
 
 
@@ -219,6 +219,9 @@ def main():
     d_dst = torch.empty(cap, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
+    # one launch group per step: each kernel runs once per step, so the per-launch durations
+    # and algorithmic bytes below are per-step figures (default groups are 32768 chunks)
+    os.environ.setdefault("ZB200_DEV_GROUP_CHUNKS", str(max(n, 1)))
     ctx = z.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)

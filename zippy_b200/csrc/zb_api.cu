@@ -491,6 +491,10 @@ int zb200_init(int device, zb200_ctx **out) {
     long v = atol(e);
     if (v > 0) ctx->dev_group_chunks = ctx->host_group_chunks = (size_t)v;
   }
+  if (const char *e = getenv("ZB200_DEV_GROUP_CHUNKS")) {  // device-resident batches only (bench.py)
+    long v = atol(e);
+    if (v > 0) ctx->dev_group_chunks = (size_t)v;
+  }
   DeviceGuard g(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;

@@ -17,8 +17,25 @@
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 
+#define INF_G 32                      // lanes per member (16 = two members per warp: measured slower, the halves diverge)
 #define INF_WARPS 8
 #define INF_THREADS (INF_WARPS * 32)
+#define INF_GROUPS (INF_THREADS / INF_G)
+
+// A "group" is INF_G consecutive lanes that decode one member together; all collectives are
+// restricted to the group's own lanes.  INF_G = 32 is one member per warp.  INF_G = 16 (two
+// members per warp, hoping to halve the instructions per token) was measured 25-30 % SLOWER on
+// B200: the two halves sit on different code paths almost all the time, so nothing is shared.
+__device__ __forceinline__ int g_lane() { return (int)(threadIdx.x & (INF_G - 1)); }
+__device__ __forceinline__ uint32_t g_shift() { return threadIdx.x & 31u & ~(uint32_t)(INF_G - 1); }
+__device__ __forceinline__ uint32_t g_mask() { return (INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u)) << g_shift(); }
+__device__ __forceinline__ uint32_t g_shfl(uint32_t v, int idx) { return __shfl_sync(g_mask(), v, idx, INF_G); }
+__device__ __forceinline__ uint32_t g_shfl_up(uint32_t v, int d) { return __shfl_up_sync(g_mask(), v, d, INF_G); }
+__device__ __forceinline__ uint32_t g_ballot(bool p) {
+  return (__ballot_sync(g_mask(), p) >> g_shift()) & (INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u));
+}
+__device__ __forceinline__ uint32_t g_match_any(uint32_t v) { return __match_any_sync(g_mask(), v) >> g_shift(); }
+__device__ __forceinline__ void g_sync() { __syncwarp(g_mask()); }
 #define LL_BITS 10   // literal/length codes up to this long decode with one table lookup
 #define D_BITS 9     // same for distance codes
 
@@ -40,7 +57,7 @@ struct Tree {  // lane L holds the entries for code length L
 struct BitReader {
   const uint32_t *gbase;  // member start rounded down to 4 bytes
   uint32_t nwords;        // words that contain member bytes
-  uint32_t cur, nxt;      // lane-held words of lines `line` and `line + 1`
+  uint32_t cur, nxt;      // lane-held words of lines `line` and `line + 1` (a line = INF_G words)
   uint32_t widx;          // next word to feed into the bit buffer
   uint64_t buf;
   int cnt;                // valid bits in buf
@@ -49,7 +66,7 @@ struct BitReader {
 };
 
 __device__ __forceinline__ uint32_t br_load_line(const BitReader &b, uint32_t line) {
-  uint32_t idx = line * 32u + (uint32_t)zb_lane();
+  uint32_t idx = line * (uint32_t)INF_G + (uint32_t)g_lane();
   return idx < b.nwords ? __ldg(b.gbase + idx) : 0u;
 }
 __device__ __forceinline__ uint64_t br_consumed_abs(const BitReader &b) {
@@ -57,11 +74,11 @@ __device__ __forceinline__ uint64_t br_consumed_abs(const BitReader &b) {
 }
 __device__ __forceinline__ bool br_past_end(const BitReader &b) { return br_consumed_abs(b) > b.end_bit; }
 __device__ __forceinline__ uint32_t br_next_word(BitReader &b) {
-  uint32_t w = __shfl_sync(ZB_FULL, b.cur, (int)(b.widx & 31u));
+  uint32_t w = g_shfl(b.cur, (int)(b.widx & (uint32_t)(INF_G - 1)));
   b.widx++;
-  if ((b.widx & 31u) == 0) {
+  if ((b.widx & (uint32_t)(INF_G - 1)) == 0) {
     b.cur = b.nxt;
-    b.nxt = br_load_line(b, (b.widx >> 5) + 1u);
+    b.nxt = br_load_line(b, b.widx / (uint32_t)INF_G + 1u);
     // bits past the end read as zero; a reader that is a whole line past the end can only be
     // decoding garbage: flag it here so that no decode loop runs away (checked by the callers)
     if ((uint64_t)b.widx * 32ull > b.end_bit + 64ull) b.overrun = true;
@@ -73,7 +90,7 @@ __device__ __forceinline__ void br_seek(BitReader &b, uint32_t shift0, uint64_t 
   uint64_t abit = (shift0 + byte_off) * 8ull;
   b.widx = (uint32_t)(abit >> 5);
   uint32_t skip = (uint32_t)(abit & 31u);
-  uint32_t line = b.widx >> 5;
+  uint32_t line = b.widx / (uint32_t)INF_G;
   b.cur = br_load_line(b, line);
   b.nxt = br_load_line(b, line + 1);
   uint32_t w = br_next_word(b);
@@ -99,20 +116,20 @@ __device__ __forceinline__ uint32_t br_take(BitReader &b, int n) {  // n <= 32, 
 // (inflate.nim:32-34, 45-46).
 __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t *syms, uint16_t *lut, int lut_bits,
                                            WarpSmem *ws, Tree &t) {
-  const int lane = zb_lane();
+  const int lane = g_lane();
   if (lane < 16) ws->cnt[lane] = 0;
   {
     uint4 z = make_uint4(0u, 0u, 0u, 0u);
     uint4 *l4 = reinterpret_cast<uint4 *>(lut);
-    for (int i = lane; i < ((1 << lut_bits) * 2) / 16; i += 32) l4[i] = z;
+    for (int i = lane; i < ((1 << lut_bits) * 2) / 16; i += INF_G) l4[i] = z;
   }
-  __syncwarp();
-  for (int base = 0; base < n; base += 32) {
+  g_sync();
+  for (int base = 0; base < n; base += INF_G) {
     int s = base + lane;
     uint32_t l = s < n ? lens[s] : 0u;
-    uint32_t grp = __match_any_sync(ZB_FULL, l);
+    uint32_t grp = g_match_any(l);
     if (l && lane == __ffs((int)grp) - 1) ws->cnt[l] = (uint16_t)(ws->cnt[l] + __popc(grp));
-    __syncwarp();
+    g_sync();
   }
   // per-length first code / first slot (all lanes compute the same recurrence)
   bool ok = true;
@@ -129,18 +146,18 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
     code <<= 1;
     k += c;
   }
-  __syncwarp();
+  g_sync();
   if (lane < 16) {
     ws->offs[lane] = (uint16_t)my_offs;
     ws->first[lane] = (uint16_t)my_first;
     ws->cnt[lane] = 0;  // becomes the running rank per length
   }
-  __syncwarp();
+  g_sync();
   if (!ok) return false;
-  for (int base = 0; base < n; base += 32) {
+  for (int base = 0; base < n; base += INF_G) {
     int s = base + lane;
     uint32_t l = s < n ? lens[s] : 0u;
-    uint32_t grp = __match_any_sync(ZB_FULL, l);
+    uint32_t grp = g_match_any(l);
     if (l) {
       uint32_t rank = ws->cnt[l] + (uint32_t)__popc(grp & ((1u << lane) - 1u));
       syms[(uint32_t)ws->offs[l] + rank] = (uint16_t)s;
@@ -151,9 +168,9 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
         for (uint32_t idx = rev; idx < (1u << lut_bits); idx += (1u << l)) lut[idx] = e;
       }
     }
-    __syncwarp();
+    g_sync();
     if (l && lane == __ffs((int)grp) - 1) ws->cnt[l] = (uint16_t)(ws->cnt[l] + __popc(grp));
-    __syncwarp();
+    g_sync();
   }
   t.first = my_first;
   t.count = (lane >= 1 && lane <= 15) ? my_count : 0u;
@@ -164,14 +181,14 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
 // Lane-parallel canonical decode (codes longer than the lookup table, and the
 // "no code matches" case, which returns 0xffff: inflate.nim:77-82).
 __device__ __forceinline__ uint32_t decode_slow(BitReader &b, const Tree &t, const uint16_t *syms) {
-  const int lane = zb_lane();
+  const int lane = g_lane();
   uint32_t rev = __brev((uint32_t)b.buf);
   uint32_t code = lane ? (rev >> (32 - lane)) : 0u;
   uint32_t rel = code - t.first;
-  uint32_t hit = __ballot_sync(ZB_FULL, rel < t.count);
+  uint32_t hit = g_ballot(rel < t.count);
   if (!hit) return 0xffffu;
   int L = __ffs((int)hit) - 1;
-  uint32_t idx = __shfl_sync(ZB_FULL, t.offs + rel, L);
+  uint32_t idx = g_shfl(t.offs + rel, L);
   b.buf >>= L;
   b.cnt -= L;
   return syms[idx];
@@ -251,23 +268,23 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
   return ZB_ERR_INVALID_FORMAT;
 }
 
-// Materialise a batch of up to 32 decoded tokens (lane i holds token i):
+// Materialise a batch of up to INF_G decoded tokens (lane i of the group holds token i):
 //   literal: the byte;  match: 1 << 31 | (dist - 1) << 9 | len.
 // One lane per token: a warp prefix sum of the lengths places every token; literals and
 // matches whose source lies wholly before the batch are copied by their own lane, in
 // parallel; the few matches that read bytes produced inside the batch follow in stream
 // order, each copied by the whole warp (reads only touch finished output: i % dist).
 __device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, uint32_t tok, uint32_t ntok) {
-  const int lane = zb_lane();
-  __syncwarp();  // stores of earlier batches are visible to every lane from here on
+  const int lane = g_lane();
+  g_sync();  // stores of earlier batches are visible to every lane from here on
   const bool act = (uint32_t)lane < ntok;
   const bool is_m = act && (tok >> 31);
   const uint32_t len = act ? (is_m ? (tok & 511u) : 1u) : 0u;
   const uint32_t dist = ((tok >> 9) & 0x7fffu) + 1u;
   uint32_t incl = len;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(ZB_FULL, incl, o);
+  for (int o = 1; o < INF_G; o <<= 1) {
+    uint32_t t = g_shfl_up(incl, o);
     if (lane >= o) incl += t;
   }
   const uint32_t rel = incl - len;           // output offset inside the batch
@@ -279,19 +296,19 @@ __device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, ui
     const uint8_t *from = to - dist;
     for (uint32_t k = 0; k < len; k++) to[k] = from[k];
   }
-  uint32_t depmask = __ballot_sync(ZB_FULL, dep);
+  uint32_t depmask = g_ballot(dep);
   while (depmask) {
     const int j = __ffs((int)depmask) - 1;
     depmask &= depmask - 1;
-    const uint32_t rj = __shfl_sync(ZB_FULL, rel, j), lj = __shfl_sync(ZB_FULL, len, j);
-    const uint32_t dj = __shfl_sync(ZB_FULL, dist, j);
-    __syncwarp();
+    const uint32_t rj = g_shfl(rel, j), lj = g_shfl(len, j);
+    const uint32_t dj = g_shfl(dist, j);
+    g_sync();
     uint8_t *tj = out + batch_op + rj;
     const uint8_t *fj = tj - dj;
     if (dj >= lj) {
-      for (uint32_t i = (uint32_t)lane; i < lj; i += 32) tj[i] = fj[i];
+      for (uint32_t i = (uint32_t)lane; i < lj; i += INF_G) tj[i] = fj[i];
     } else {
-      for (uint32_t i = (uint32_t)lane; i < lj; i += 32) tj[i] = fj[i % dj];
+      for (uint32_t i = (uint32_t)lane; i < lj; i += INF_G) tj[i] = fj[i % dj];
     }
   }
 }
@@ -300,7 +317,7 @@ template <bool COUNT_ONLY>
 __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, uint64_t pos, uint8_t *out,
                                               uint64_t cap64, WarpSmem *ws, const uint32_t *len_tab,
                                               const uint32_t *dist_tab, uint64_t &out_len) {
-  const int lane = zb_lane();
+  const int lane = g_lane();
   const uint8_t clcl_order[19] = ZB_CLCL_ORDER;
   BitReader b;
   const uint32_t shift0 = (uint32_t)((uintptr_t)src & 3u);
@@ -334,7 +351,7 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
         if (byte_pos + l > len) return ZB_ERR_END_OF_BUFFER;
         if (!COUNT_ONLY) {
           if (l > cap - op) return ZB_ERR_DST_TOO_SMALL;
-          for (uint32_t i = (uint32_t)lane; i < l; i += 32) out[op + i] = src[byte_pos + i];
+          for (uint32_t i = (uint32_t)lane; i < l; i += INF_G) out[op + i] = src[byte_pos + i];
         } else if (l > cap - op) {
           return ZB_ERR_DST_TOO_SMALL;
         }
@@ -347,10 +364,10 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
     int hlit, hdist;
     if (btype == 1) {
       // ---- fixed codes (inflate.nim:111-113) ----
-      for (int i = lane; i < 320; i += 32) ws->lens[i] = (uint8_t)(i < 288 ? zb_fixed_ll_len(i) : 5);
+      for (int i = lane; i < 320; i += INF_G) ws->lens[i] = (uint8_t)(i < 288 ? zb_fixed_ll_len(i) : 5);
       hlit = 288;
       hdist = 30;
-      __syncwarp();
+      g_sync();
     } else {
       // ---- dynamic header (inflate.nim:115-171) ----
       br_refill(b);
@@ -359,17 +376,17 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
       int hclen = (int)br_take(b, 4) + 4;
       if (hlit > ZB_NUM_LITLEN) return ZB_ERR_UNCOMPRESS;
       if (hdist > ZB_NUM_DIST) return ZB_ERR_UNCOMPRESS;
-      if (lane < 19) ws->lens[lane] = 0;
-      __syncwarp();
+      for (int i = lane; i < 19; i += INF_G) ws->lens[i] = 0;
+      g_sync();
       for (int i = 0; i < hclen; i++) {
         br_refill(b);
         uint32_t v = br_take(b, 3);
         if (lane == 0) ws->lens[clcl_order[i]] = (uint8_t)v;
       }
-      __syncwarp();
+      g_sync();
       Tree tc;
       if (!build_tree(ws->lens, 19, ws->syms_d, ws->lut_d, 7, ws, tc)) return ZB_ERR_UNCOMPRESS;
-      __syncwarp();
+      g_sync();
       // the code-length code now lives in syms_d / lut_d; lens[] is rewritten with the
       // unpacked literal/length + distance code lengths.
       int i = 0;
@@ -396,7 +413,7 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
           prev = 0;
         } else if (sym == 18) {
           int rep = (int)br_take(b, 7) + 11;
-          for (int j = lane; j < rep && i + j < 320; j += 32) ws->lens[i + j] = 0;
+          for (int j = lane; j < rep && i + j < 320; j += INF_G) ws->lens[i + j] = 0;
           i += rep;
           prev = 0;
         } else {
@@ -406,11 +423,11 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
         if (i > total) return ZB_ERR_UNCOMPRESS;
       }
       if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-      __syncwarp();
+      g_sync();
     }
     if (!build_tree(ws->lens, hlit, ws->syms_ll, ws->lut_ll, LL_BITS, ws, tl)) return ZB_ERR_UNCOMPRESS;
     if (!build_tree(ws->lens + hlit, hdist, ws->syms_d, ws->lut_d, D_BITS, ws, td)) return ZB_ERR_UNCOMPRESS;
-    __syncwarp();
+    g_sync();
 
     // ---- symbol loop (inflate.nim:173-250): decode into a 32-token batch, then flush ----
     uint32_t tok = 0, ntok = 0, batch_op = op;
@@ -449,8 +466,8 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
       if ((uint32_t)lane == ntok) tok = t;
       ntok++;
       op += tlen;
-      if (ntok == 32) {
-        if (!COUNT_ONLY) flush_tokens(out, batch_op, tok, 32);
+      if (ntok == INF_G) {
+        if (!COUNT_ONLY) flush_tokens(out, batch_op, tok, INF_G);
         ntok = 0;
         batch_op = op;
       }
@@ -465,10 +482,10 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(INF_THREADS)
     k_inflate(ZbInflateWork w) {
-  __shared__ __align__(16) WarpSmem wsm[INF_WARPS];
+  __shared__ __align__(16) WarpSmem wsm[INF_GROUPS];
   __shared__ uint32_t len_tab[32], dist_tab[32];  // base | extra bits << 16 (RFC 1951 3.2.5)
-  const int lane = zb_lane(), warp = (int)(threadIdx.x >> 5);
-  WarpSmem *ws = &wsm[warp];
+  const int lane = g_lane();
+  WarpSmem *ws = &wsm[threadIdx.x / INF_G];
   if (threadIdx.x < 29) len_tab[threadIdx.x] = zb_len_base((int)threadIdx.x) | ((uint32_t)zb_len_extra_bits((int)threadIdx.x) << 16);
   if (threadIdx.x >= 32 && threadIdx.x < 62) {
     int c = (int)threadIdx.x - 32;
@@ -478,7 +495,7 @@ __global__ void __launch_bounds__(INF_THREADS)
   for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(w.counter, 1u);
-    i = __shfl_sync(ZB_FULL, i, 0);
+    i = g_shfl(i, 0);
     if (i >= w.n) break;
     const uint64_t s0 = w.src_off[i], s1 = w.src_off[i + 1];
     const uint8_t *src = w.src + s0;
@@ -492,7 +509,7 @@ __global__ void __launch_bounds__(INF_THREADS)
       if (COUNT_ONLY && kind == ZB_DF_GZIP) out_len = isize;  // gzip.nim:66 (trustSize's source)
       else st = inflate_member<COUNT_ONLY>(src, len, pos, out, cap, ws, len_tab, dist_tab, out_len);
     }
-    __syncwarp();
+    g_sync();
     if (lane == 0) {
       w.status[i] = st;
       w.out_len[i] = st == ZB_OK ? out_len : 0;
@@ -580,7 +597,7 @@ cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   uint32_t blocks = (uint32_t)sms * 6u;
-  uint32_t need = (w.n + INF_WARPS - 1) / INF_WARPS;
+  uint32_t need = (w.n + INF_GROUPS - 1) / INF_GROUPS;
   if (blocks > need) blocks = need;
   cudaError_t e = cudaMemsetAsync(w.counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
