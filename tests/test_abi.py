@@ -49,3 +49,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def _build_cpp_api_test():
+    import subprocess
+    src = os.path.join(ROOT, "tests", "native", "cpp_api_test.cpp")
+    exe = os.path.join(ROOT, "tests", "native", "cpp_api_test")
+    libdir = os.path.join(ROOT, "zippy_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, src, "-L" + libdir, "-l:libzippy_b200.so",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_mirror_compiles_and_links():
+    # include/zippy_b200.hpp is the compiled-language host side (Nim is unavailable here)
+    import __graft_entry__ as g
+    g.build()
+    assert os.path.exists(_build_cpp_api_test())

@@ -346,3 +346,11 @@ def test_default_level_ratio_vs_reference(z, o, corpus):
     assert sum(map(len, comp)) <= 1.03 * 6 * len(o.compress(raw, o.DefaultCompression, o.dfGzip))
     lvl1 = len(z.deflate(raw, 1))
     assert len(z.deflate(raw, 9)) < lvl1 and len(z.deflate(raw, 2)) < lvl1
+
+
+def test_cpp_host_mirror():
+    """include/zippy_b200.hpp (host framing in C++ as in zippy.nim, codec through the seam)."""
+    import subprocess
+    from tests.test_abi import _build_cpp_api_test
+    out = subprocess.run([_build_cpp_api_test()], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), (out.stdout, out.stderr)
