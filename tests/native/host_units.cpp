@@ -29,6 +29,21 @@ uint32_t t_crc32_lane_model(const uint8_t *data, uint64_t n) {
   static ZbCrcTables T;
   static int init = 0;
   if (!init) { zb_crc_build_tables(&T); init = 1; }
+  if (n == 8192) {  // the device's fast path: four chains of 16 rows joined by quarter shifts
+    uint32_t total = 0;
+    for (int lane = 0; lane < 32; lane++) {
+      uint32_t r[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 16; k++)
+        for (int c = 0; c < 4; c++) {
+          uint32_t w = ld32(data + 128 * (16 * c + k) + 4 * lane);
+          if (k) r[c] = T.mul1024[0][r[c] & 255] ^ T.mul1024[1][(r[c] >> 8) & 255] ^ T.mul1024[2][(r[c] >> 16) & 255] ^ T.mul1024[3][r[c] >> 24];
+          r[c] ^= w;
+        }
+      uint32_t rr = zb_gf2_mul(r[0], T.quart_mul[3]) ^ zb_gf2_mul(r[1], T.quart_mul[2]) ^ zb_gf2_mul(r[2], T.quart_mul[1]) ^ r[3];
+      total ^= zb_gf2_mul(rr, T.lane_mul[32 - lane]);
+    }
+    return zb_crc32_finalize(total, n);
+  }
   uint64_t K = n / 128, t = n - 128 * K;
   uint32_t r_main = 0;
   for (int lane = 0; lane < 32; lane++) {

@@ -71,6 +71,29 @@ def main():
                           "parity": "first cycle sha256 == manifest; all members CRC+ISIZE verified on device"}))
         del d_src, d_dst
 
+    if "crc" in args.what:
+        # standalone blocked checksums: 65536 x 64 KiB buffers, then the same 4 GiB as ONE buffer
+        import zlib
+        n = args.members
+        g = torch.Generator(device=dev)
+        g.manual_seed(1)
+        d_src = torch.randint(0, 256, (n * 65536,), dtype=torch.uint8, device=dev, generator=g)
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        for label, offs in (("%d x 64 KiB" % n, np.arange(n + 1, dtype=np.uint64) * 65536),
+                            ("1 x %d MiB" % (n // 16), np.array([0, n * 65536], dtype=np.uint64))):
+            for kind in ("crc32", "adler32"):
+                for _ in range(2):
+                    out = ctx.checksum_batch_device(d_src.data_ptr(), offs, kind)
+                ms = ctx.timing()["checksum_ms"]
+                h = d_src[:65536].cpu().numpy().tobytes() if len(offs) > 2 else None
+                if h is not None:
+                    assert int(out[0]) == (zlib.crc32(h) if kind == "crc32" else zlib.adler32(h))
+                gbs = n * 65536 / (ms / 1e3) / 1e9
+                print(json.dumps({"workload": "checksum %s, %s" % (kind, label), "ms": ms, "GB_s": gbs,
+                                  "hbm_peak_GB_s": peak, "frac_of_hbm_peak": gbs / peak, "value0": int(out[0])}))
+        del d_src
+
     if "c4" in args.what:
         raw = util.load_corpus()["urls.10K"]
         n = args.tiles

@@ -33,7 +33,7 @@ struct zb200_ctx {
   cudaStream_t own_stream = nullptr;
   ZbCrcTables *d_tabs = nullptr;
   DevBuf desc, member_first, fname, masks, recs, hist, chk, cb, chunk_off, member_off, member_check, member_isize;
-  DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out;
+  DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out, ck_pieces, ck_first, ck_piece_out;
   DevBuf in_stage, out_stage, lz2_tables;
   cudaEvent_t ev[10];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -361,6 +361,39 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   return ZB200_OK;
 }
 
+// 64 KiB pieces covering the capacity [offs[i], offs[i+1]) of every buffer (at least one per buffer)
+int upload_pieces(zb200_ctx *ctx, const uint64_t *offs, size_t n, ZbChecksumWork &w) {
+  std::vector<ZbPiece> pieces;
+  std::vector<uint32_t> first(n + 1);
+  for (size_t i = 0; i < n; i++) {
+    first[i] = (uint32_t)pieces.size();
+    uint64_t cap = offs[i + 1] - offs[i];
+    uint64_t rel = 0;
+    do {
+      ZbPiece p;
+      p.rel = rel;
+      p.buf = (uint32_t)i;
+      p.pad = 0;
+      pieces.push_back(p);
+      rel += ZB_CHUNK_BYTES;
+    } while (rel < cap);
+  }
+  first[n] = (uint32_t)pieces.size();
+  ENSURE(ctx->ck_pieces, pieces.size() * sizeof(ZbPiece));
+  ENSURE(ctx->ck_first, (n + 1) * sizeof(uint32_t));
+  ENSURE(ctx->ck_piece_out, pieces.size() * sizeof(ZbChunkCheck));
+  CK(cudaMemcpyAsync(ctx->ck_pieces.p, pieces.data(), pieces.size() * sizeof(ZbPiece), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->ck_first.p, first.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+  w.pieces = (const ZbPiece *)ctx->ck_pieces.p;
+  w.first = (const uint32_t *)ctx->ck_first.p;
+  w.piece_out = (ZbChunkCheck *)ctx->ck_piece_out.p;
+  w.n_pieces = (uint32_t)pieces.size();
+  w.tabs = ctx->d_tabs;
+  w.n = (uint32_t)n;
+  return ZB200_OK;
+}
+
 // ---- uncompress, device-resident ----
 int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                              int data_format, uint64_t raw_pos, uint8_t *d_dst, const uint64_t *dst_offsets,
@@ -394,10 +427,27 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
   w.data_format = data_format;
   w.pos = raw_pos;
   w.count_only = count_only ? 1 : 0;
+  ZbChecksumWork cw;
+  memset(&cw, 0, sizeof(cw));
+  if (!count_only) {  // piece table for the verification pass, uploaded before anything is launched
+    int rc = upload_pieces(ctx, dst_offsets, n, cw);
+    if (rc) return rc;
+  }
   CK(cudaEventRecord(ctx->ev[0], s));
   CK(zb_launch_inflate(w, s));
   CK(cudaEventRecord(ctx->ev[1], s));
-  CK(zb_launch_verify(w, s));
+  if (!count_only) {
+    // gzip.nim:80-88 / zippy.nim:154-162: checksum, then size, of every member that inflated
+    cw.src = d_dst;
+    cw.off = (const uint64_t *)ctx->dst_off.p;
+    cw.lens = (const uint64_t *)ctx->out_len.p;
+    cw.status = (int *)ctx->status.p;
+    cw.expect = (const uint32_t *)ctx->expect.p;
+    cw.kinds = (const uint32_t *)ctx->kind.p;
+    cw.isize_src = d_src;
+    cw.isize_off = (const uint64_t *)ctx->src_off.p;
+    CK(zb_launch_checksum(cw, s));
+  }
   CK(cudaEventRecord(ctx->ev[2], s));
   CK(cudaMemcpyAsync(dst_lens, ctx->out_len.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   std::vector<int> st_tmp;
@@ -410,7 +460,7 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
   CK(cudaStreamSynchronize(s));
   ctx->timing.inflate_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
   ctx->timing.verify_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
-  ctx->timing.kernel_launches += count_only ? 1 : 2;
+  ctx->timing.kernel_launches += count_only ? 1 : 3;
   for (size_t i = 0; i < n; i++)
     if (st[i] != ZB200_OK) dst_lens[i] = 0;
   return ZB200_OK;
@@ -420,16 +470,19 @@ int checksum_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
                            uint32_t *out) {
   if (kind != 0 && kind != 1) return ZB200_ERR_ARG;
   if (n == 0) return ZB200_OK;
+  for (size_t i = 0; i < n; i++)
+    if (src_offsets[i + 1] < src_offsets[i]) return ZB200_ERR_ARG;
   ENSURE(ctx->src_off, (n + 1) * sizeof(uint64_t));
   ENSURE(ctx->ck_out, n * sizeof(uint32_t));
   cudaStream_t s = ctx->stream;
   CK(cudaMemcpyAsync(ctx->src_off.p, src_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
   ZbChecksumWork w;
+  memset(&w, 0, sizeof(w));
+  int rc = upload_pieces(ctx, src_offsets, n, w);
+  if (rc) return rc;
   w.src = d_src;
   w.off = (const uint64_t *)ctx->src_off.p;
   w.out = (uint32_t *)ctx->ck_out.p;
-  w.tabs = ctx->d_tabs;
-  w.n = (uint32_t)n;
   w.kind = kind;
   CK(cudaEventRecord(ctx->ev[0], s));
   CK(zb_launch_checksum(w, s));
@@ -437,7 +490,7 @@ int checksum_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
   CK(cudaMemcpyAsync(out, ctx->ck_out.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   ctx->timing.checksum_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
-  ctx->timing.kernel_launches += 1;
+  ctx->timing.kernel_launches += 2;
   return ZB200_OK;
 }
 
@@ -523,7 +576,7 @@ void zb200_shutdown(zb200_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->desc, &ctx->member_first, &ctx->fname, &ctx->masks, &ctx->recs, &ctx->hist, &ctx->chk,
                     &ctx->cb, &ctx->chunk_off, &ctx->member_off, &ctx->member_check, &ctx->member_isize,
                     &ctx->src_off, &ctx->dst_off, &ctx->out_len, &ctx->status, &ctx->expect, &ctx->kind,
-                    &ctx->counter, &ctx->ck_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables};
+                    &ctx->counter, &ctx->ck_out, &ctx->ck_pieces, &ctx->ck_first, &ctx->ck_piece_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_tabs) cudaFree(ctx->d_tabs);

@@ -84,6 +84,7 @@ struct ZbCrcTables {
   uint32_t lane_mul[33];
   uint32_t sub_mul[8];  // [k] = x^(8 * 8192 * k) mod P, k = 1..7: shifts a sub-chunk's CRC to the chunk end;
                         // [0] = x^(8 * 65536) mod P: shifts by one whole chunk
+  uint32_t quart_mul[4];  // [k] = x^(8 * 2048 * k) mod P: shifts a quarter of a sub-chunk (16 rows of 128 B)
 };
 
 inline void zb_crc_build_tables(ZbCrcTables *t) {
@@ -93,4 +94,5 @@ inline void zb_crc_build_tables(ZbCrcTables *t) {
   for (int j = 0; j <= 32; j++) t->lane_mul[j] = zb_xpow8(4ull * (uint64_t)j);
   for (int k = 1; k < 8; k++) t->sub_mul[k] = zb_xpow8(8192ull * (uint64_t)k);
   t->sub_mul[0] = zb_xpow8(65536ull);
+  for (int k = 0; k < 4; k++) t->quart_mul[k] = zb_xpow8(2048ull * (uint64_t)k);
 }

@@ -34,7 +34,7 @@
 #define LZ_SM_RING (LZ_SM_HIST + LZ_SM_HIST_BYTES)
 #define LZ_SM_RING_BYTES (ZB_WARPS_PER_CHUNK * 32 * ZB_MATCH_SLOTS * 4)
 #define LZ_SM_LMUL (LZ_SM_RING + LZ_SM_RING_BYTES)
-#define LZ_SM_LMUL_BYTES (44 * 4)
+#define LZ_SM_LMUL_BYTES (48 * 4)
 #define LZ_SM_PART (LZ_SM_LMUL + LZ_SM_LMUL_BYTES)
 #define LZ_SM_PART_BYTES (ZB_WARPS_PER_CHUNK * 24)
 #define LZ_SM_BAR (LZ_SM_PART + LZ_SM_PART_BYTES)
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
   }
   if (tid < 33) lane_mul[tid] = tabs->lane_mul[tid];
   if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = tabs->sub_mul[tid - 64];
+  if (tid >= 96 && tid < 100) lane_mul[41 + tid - 96] = tabs->quart_mul[tid - 96];
   __syncthreads();
   if (len) zb_mbar_wait(bar, 0);
 
@@ -429,6 +430,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
   for (int i = tid; i < 1024; i += LZ_THREADS) crc_tab[i] = (&tabs->mul1024[0][0])[i];
   if (tid < 33) lane_mul[tid] = tabs->lane_mul[tid];
   if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = tabs->sub_mul[tid - 64];
+  if (tid >= 96 && tid < 100) lane_mul[41 + tid - 96] = tabs->quart_mul[tid - 96];
   __syncthreads();
 
   uint32_t phase = 0;

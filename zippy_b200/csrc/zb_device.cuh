@@ -108,6 +108,44 @@ struct ZbCheck {
 __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32_t off, uint32_t n,
                                                      const uint32_t *tab, const uint32_t *lane_mul) {
   const int lane = zb_lane();
+  if (n == 8192u) {
+    // Full 8 KiB piece (the common case): four independent Horner chains of 16 rows each, so the
+    // table-lookup latency of one chain hides behind the other three; they are joined with the
+    // quarter shifts lane_mul[41 + k] = x^(8 * 2048 * k).
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, a = 0;
+    uint64_t b = 0;
+    const uint32_t o = off + 4u * (uint32_t)lane, rel0 = 4u * (uint32_t)lane;
+#pragma unroll 2
+    for (uint32_t k = 0; k < 16; k++) {
+      const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (16u + k));
+      const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (32u + k)), w3 = zb_ld32_unaligned(base, o + 128u * (48u + k));
+      if (k) {
+        r0 = zb_mul1024(tab, r0);
+        r1 = zb_mul1024(tab, r1);
+        r2 = zb_mul1024(tab, r2);
+        r3 = zb_mul1024(tab, r3);
+      }
+      r0 ^= w0;
+      r1 ^= w1;
+      r2 ^= w2;
+      r3 ^= w3;
+      const uint32_t s0 = __dp4a(w0, 0x01010101u, 0u), s1 = __dp4a(w1, 0x01010101u, 0u);
+      const uint32_t s2 = __dp4a(w2, 0x01010101u, 0u), s3 = __dp4a(w3, 0x01010101u, 0u);
+      a += s0 + s1 + s2 + s3;
+      const uint32_t rel = rel0 + 128u * k;
+      b += (uint64_t)(8192u - rel) * s0 + (uint64_t)(8192u - 2048u - rel) * s1 + (uint64_t)(8192u - 4096u - rel) * s2 +
+           (uint64_t)(8192u - 6144u - rel) * s3;
+      b -= (uint64_t)(__dp4a(w0, 0x03020100u, 0u) + __dp4a(w1, 0x03020100u, 0u) + __dp4a(w2, 0x03020100u, 0u) +
+                      __dp4a(w3, 0x03020100u, 0u));
+    }
+    uint32_t r = zb_gf2_mul(r0, lane_mul[41 + 3]) ^ zb_gf2_mul(r1, lane_mul[41 + 2]) ^ zb_gf2_mul(r2, lane_mul[41 + 1]) ^ r3;
+    r = zb_gf2_mul(r, lane_mul[32 - lane]);
+    ZbCheck out;
+    out.crc_raw = zb_warp_xor(r);
+    out.a_sum = zb_warp_sum64((uint64_t)a);
+    out.b_sum = zb_warp_sum64(b);
+    return out;
+  }
   const uint32_t rows = n >> 7, tail = n & 127u;
   uint32_t r = 0;
   uint32_t a = 0;

@@ -520,72 +520,187 @@ __global__ void __launch_bounds__(INF_THREADS)
 }
 
 // ------------------------------------------------------------------------------------
-// Checksum kernels: one warp per buffer piece, staged through shared memory by TMA.
-// k_verify checks inflate outputs against their trailers (gzip.nim:80-88, zippy.nim:154-162).
-#define CK_PIECE 32768u
-#define CK_WARPS 4
-#define CK_THREADS (CK_WARPS * 32)
-#define CK_SM_PIECE_BYTES (CK_PIECE + 64)
-#define CK_SM_TOTAL (CK_WARPS * CK_SM_PIECE_BYTES + 4096 + 160 + CK_WARPS * 8 + 64)
+// Blocked combine-reduce checksums (replaces crc32 crc.nim:53 / crc32_simd.nim:39-144 and
+// adler32 adler32.nim:6 / adler32_simd.nim:45-120, and the trailer checks gzip.nim:80-88,
+// zippy.nim:154-162).  A buffer is cut into 64 KiB pieces; k_piece_checksum gives every piece
+// to one CTA (TMA-staged, 8 warps x 8 KiB, lane-strided CRC stepping + dp4a Adler sums, see
+// zb_device.cuh), k_buffer_combine folds a buffer's pieces with x^(8*len) multiplications /
+// the closed-form Adler merge, and in verify mode compares with the trailer.
+#define CK_PIECE ZB_CHUNK_BYTES
+#define CK_THREADS (ZB_WARPS_PER_CHUNK * 32)
+#define CK_STAGES 3
+#define CK_STAGE_BYTES (CK_PIECE + 128)
+#define CK_SM_CRC (CK_STAGES * CK_STAGE_BYTES)
+#define CK_SM_LMUL (CK_SM_CRC + 4096)
+#define CK_SM_PART (CK_SM_LMUL + 48 * 4)
+#define CK_SM_BAR (CK_SM_PART + ZB_WARPS_PER_CHUNK * 24)
+#define CK_SM_TOTAL (CK_SM_BAR + 8 * CK_STAGES + 8)
 
-// checksum of buf[0, n) by one warp; piece by piece through this warp's smem slot
-__device__ __forceinline__ uint32_t warp_buffer_checksum(const uint8_t *buf, uint64_t n, int kind, uint8_t *slot,
-                                                         uint64_t *bar, uint32_t &phase, const uint32_t *crc_tab,
-                                                         const uint32_t *lane_mul) {
-  const int lane = zb_lane();
-  uint32_t raw = 0, ad = 1;
-  for (uint64_t o = 0; o < n; o += CK_PIECE) {
-    uint32_t pl = (uint32_t)min((uint64_t)CK_PIECE, n - o);
-    uint32_t mis = (uint32_t)((uintptr_t)(buf + o) & 15u);
-    if (lane == 0) zb_stage_chunk(slot, buf + o, pl, bar);
-    zb_mbar_wait(bar, phase & 1u);
-    phase++;
-    ZbCheck c = zb_warp_checksums(slot, mis, pl, crc_tab, lane_mul);
-    __syncwarp();
-    if (kind == 0) raw = o ? (zb_gf2_mul(raw, zb_xpow8(pl)) ^ c.crc_raw) : c.crc_raw;
-    else ad = zb_adler32_combine(ad, zb_adler_from_sums(c.a_sum % ZB_ADLER_MOD, c.b_sum % ZB_ADLER_MOD, pl), pl);
-  }
-  return kind == 0 ? zb_crc32_finalize(raw, n) : ad;
+__device__ __forceinline__ uint32_t piece_len(uint64_t buflen, uint64_t rel) {
+  return rel < buflen ? (uint32_t)min((uint64_t)CK_PIECE, buflen - rel) : 0u;
+}
+__device__ __forceinline__ uint32_t ck_piece_info(const ZbChecksumWork &w, uint32_t pid, const uint8_t *&src) {
+  const ZbPiece pc = w.pieces[pid];
+  uint64_t buflen = w.lens ? w.lens[pc.buf] : w.off[pc.buf + 1] - w.off[pc.buf];
+  if (w.status && w.status[pc.buf] != ZB_OK) buflen = 0;
+  src = w.src + w.off[pc.buf] + pc.rel;
+  return piece_len(buflen, pc.rel);
 }
 
-__global__ void __launch_bounds__(CK_THREADS)
-    k_checksum(const uint8_t *base, const uint64_t *off, const uint64_t *lens_or_null, uint32_t *out, int *status,
-               const uint32_t *expect, const uint32_t *kinds, const ZbCrcTables *tabs, uint32_t n, int fixed_kind,
-               const uint8_t *src_for_isize, const uint64_t *src_off) {
+// Persistent CTAs (one per SM), a 3-stage ring of 64 KiB shared-memory buffers filled by TMA
+// bulk copies: while the 8 warps checksum stage k, the copies for k+1 and k+2 are in flight.
+// Piece descriptors (source pointer, length: two dependent global loads) are fetched 16..32
+// pieces ahead into a small shared ring so they never sit on the critical path.
+// This is the one kernel on the path that is genuinely memory-bound (0.12 instructions per byte).
+#define CK_INFO 32
+__global__ void __launch_bounds__(CK_THREADS, 1)
+    k_piece_checksum(ZbChecksumWork w) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint32_t *crc_tab = reinterpret_cast<uint32_t *>(smem + CK_WARPS * CK_SM_PIECE_BYTES);
-  uint32_t *lane_mul = crc_tab + 1024;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CK_WARPS * CK_SM_PIECE_BYTES + 4096 + 160);
+  uint32_t *crc_tab = reinterpret_cast<uint32_t *>(smem + CK_SM_CRC);
+  uint32_t *lane_mul = reinterpret_cast<uint32_t *>(smem + CK_SM_LMUL);
+  uint64_t *part = reinterpret_cast<uint64_t *>(smem + CK_SM_PART);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CK_SM_BAR);
+  __shared__ const uint8_t *info_src[CK_INFO];
+  __shared__ uint32_t info_len[CK_INFO];
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 1024; i += CK_THREADS) crc_tab[i] = (&tabs->mul1024[0][0])[i];
-  if (tid < 33) lane_mul[tid] = tabs->lane_mul[tid];
-  if (lane == 0) {
-    zb_mbar_init(&bars[warp], 1);
+  const uint32_t stride = gridDim.x;
+  if (tid == 0) {
+    for (int i = 0; i < CK_STAGES; i++) zb_mbar_init(&bars[i], 1);
     zb_fence_mbar_init();
   }
+  for (int i = tid; i < 1024; i += CK_THREADS) crc_tab[i] = (&w.tabs->mul1024[0][0])[i];
+  if (tid < 33) lane_mul[tid] = w.tabs->lane_mul[tid];
+  if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = w.tabs->sub_mul[tid - 64];
+  if (tid >= 96 && tid < 100) lane_mul[41 + tid - 96] = w.tabs->quart_mul[tid - 96];
+  if (tid >= 128 && tid < 128 + CK_INFO) {  // descriptors of this CTA's first 32 pieces
+    const uint32_t j = (uint32_t)tid - 128u, pid = blockIdx.x + j * stride;
+    const uint8_t *src = nullptr;
+    info_len[j] = pid < w.n_pieces ? ck_piece_info(w, pid, src) : 0u;
+    info_src[j] = src;
+  }
   __syncthreads();
-  uint8_t *slot = smem + warp * CK_SM_PIECE_BYTES;
-  uint32_t phase = 0;
-  for (uint32_t i = blockIdx.x * CK_WARPS + (uint32_t)warp; i < n; i += gridDim.x * CK_WARPS) {
-    if (status && status[i] != ZB_OK) continue;
-    int kind = fixed_kind;
-    if (kinds) {
-      uint32_t k = kinds[i];
-      if (k == ZB_DF_GZIP) kind = 0;
-      else if (k == ZB_DF_ZLIB) kind = 1;
-      else continue;  // raw deflate: nothing to verify
+  if (tid == 0) {  // prologue: fill the ring
+    for (uint32_t k = 0; k < CK_STAGES; k++) {
+      if (blockIdx.x + k * stride >= w.n_pieces) break;
+      if (info_len[k]) zb_stage_chunk(smem + k * CK_STAGE_BYTES, info_src[k], info_len[k], &bars[k]);
     }
-    uint64_t len = lens_or_null ? lens_or_null[i] : off[i + 1] - off[i];
-    uint32_t v = warp_buffer_checksum(base + off[i], len, kind, slot, &bars[warp], phase, crc_tab, lane_mul);
+  }
+  uint32_t k = 0, phases = 0;  // bit s of `phases` = parity of the next completion of stage s
+  for (uint32_t pid = blockIdx.x; pid < w.n_pieces; pid += stride, k++) {
+    const uint32_t stage = k % CK_STAGES;
+    const uint32_t len = info_len[k % CK_INFO];
+    const uint8_t *src = info_src[k % CK_INFO];
+    const uint8_t *data = smem + stage * CK_STAGE_BYTES;
+    const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
+    if (len) {  // empty pieces are never copied, so their stage's phase does not advance
+      zb_mbar_wait(&bars[stage], (phases >> stage) & 1u);
+      phases ^= 1u << stage;
+    }
+    const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES, b1 = min(b0 + ZB_SUB_BYTES, len);
+    ZbCheck c;
+    c.crc_raw = 0;
+    c.a_sum = c.b_sum = 0;
+    if (b0 < len) {
+      c = zb_warp_checksums(data, mis + b0, b1 - b0, crc_tab, lane_mul);
+      const uint32_t after = len - b1;
+      if (after) {
+        const uint32_t shift = ((after & (ZB_SUB_BYTES - 1)) == 0) ? lane_mul[33 + after / ZB_SUB_BYTES] : zb_xpow8(after);
+        c.crc_raw = zb_gf2_mul(c.crc_raw, shift);
+        c.b_sum += (uint64_t)after * c.a_sum;
+      }
+    }
     if (lane == 0) {
-      if (out) out[i] = v;
-      if (expect) {
-        if (v != expect[i]) status[i] = ZB_ERR_CHECKSUM;
-        else if (kind == 0 && src_for_isize) {
-          const uint8_t *t = src_for_isize + src_off[i + 1] - 4;
-          if (ld_le32(t) != (uint32_t)len) status[i] = ZB_ERR_SIZE;
+      part[warp * 3 + 0] = c.crc_raw;
+      part[warp * 3 + 1] = c.a_sum;
+      part[warp * 3 + 2] = c.b_sum;
+    }
+    __syncthreads();  // every warp is done with this stage (and with info slot k)
+    if (tid == 0) {
+      // refill this stage with the piece three iterations ahead
+      const uint32_t nk = k + CK_STAGES;
+      if (pid + CK_STAGES * stride < w.n_pieces && info_len[nk % CK_INFO])
+        zb_stage_chunk(smem + stage * CK_STAGE_BYTES, info_src[nk % CK_INFO], info_len[nk % CK_INFO], &bars[stage]);
+      uint32_t raw = 0;
+      uint64_t a = 0, b = 0;
+      for (int j = 0; j < ZB_WARPS_PER_CHUNK; j++) {
+        raw ^= (uint32_t)part[j * 3 + 0];
+        a += part[j * 3 + 1];
+        b += part[j * 3 + 2];
+      }
+      ZbChunkCheck cc;
+      cc.crc_raw = raw;
+      cc.adler = ((uint32_t)(b % ZB_ADLER_MOD) << 16) | (uint32_t)(a % ZB_ADLER_MOD);  // (B mod p, A mod p), not yet an Adler value
+      w.piece_out[pid] = cc;
+    } else if (warp == 1 && (k % 16u) == 15u && lane < 16) {
+      // descriptors for pieces k+17 .. k+32 go into the half of the ring that has just been used up
+      const uint32_t j = k + 17u + (uint32_t)lane, npid = blockIdx.x + j * stride;
+      const uint8_t *nsrc = nullptr;
+      info_len[j % CK_INFO] = npid < w.n_pieces ? ck_piece_info(w, npid, nsrc) : 0u;
+      info_src[j % CK_INFO] = nsrc;
+    }
+    __syncthreads();  // part[] and the descriptor ring are consistent for the next piece
+  }
+}
+
+// One warp per buffer: lane j folds pieces j, j+32, ... (Horner in x^(8 * 32 * 64 KiB)), the lane
+// results are shifted to the end of the buffer and XOR-reduced; Adler sums add up directly.
+__global__ void __launch_bounds__(128)
+    k_buffer_combine(ZbChecksumWork w) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = (int)(threadIdx.x & 31u);
+  if (i >= w.n) return;
+  if (w.status && w.status[i] != ZB_OK) return;
+  int kind = w.kind;
+  if (w.kinds) {
+    const uint32_t kd = w.kinds[i];
+    if (kd == ZB_DF_GZIP) kind = 0;
+    else if (kd == ZB_DF_ZLIB) kind = 1;
+    else return;  // raw deflate: nothing to verify
+  }
+  const uint64_t buflen = w.lens ? w.lens[i] : w.off[i + 1] - w.off[i];
+  const uint32_t p0 = w.first[i];
+  const uint32_t np = (uint32_t)((buflen + CK_PIECE - 1) / CK_PIECE);  // pieces that hold data
+  uint32_t r = 0;
+  uint64_t a = 0, b = 0, end = 0;  // end = bytes from the buffer start to the end of this lane's last piece
+  if (kind == 0) {
+    uint32_t step = 0;  // x^(8 * 32 * 64 KiB), computed only if a lane has more than one piece
+    for (uint32_t k = (uint32_t)lane; k < np; k += 32) {
+      const uint32_t l = piece_len(buflen, (uint64_t)k * CK_PIECE);
+      const uint32_t raw = w.piece_out[p0 + k].crc_raw;
+      if (k >= 32) {
+        if (l == CK_PIECE) {
+          if (!step) step = zb_xpow8(32ull * CK_PIECE);
+          r = zb_gf2_mul(r, step);
+        } else {
+          r = zb_gf2_mul(r, zb_xpow8(31ull * CK_PIECE + l));
         }
       }
+      r ^= raw;
+      end = (uint64_t)k * CK_PIECE + l;
+    }
+    if ((uint32_t)lane < np && end < buflen) r = zb_gf2_mul(r, zb_xpow8(buflen - end));
+    r = zb_warp_xor(r);
+  } else {
+    for (uint32_t k = (uint32_t)lane; k < np; k += 32) {
+      const uint32_t l = piece_len(buflen, (uint64_t)k * CK_PIECE);
+      const uint32_t ab = w.piece_out[p0 + k].adler;
+      const uint64_t ak = ab & 0xffffu, bk = ab >> 16;
+      const uint64_t after = (buflen - ((uint64_t)k * CK_PIECE + l)) % ZB_ADLER_MOD;
+      a += ak;
+      b = (b + bk + after * ak) % ZB_ADLER_MOD;
+    }
+    a = zb_warp_sum64(a % ZB_ADLER_MOD);
+    b = zb_warp_sum64(b);
+  }
+  if (lane != 0) return;
+  const uint32_t v = kind == 0 ? ~(zb_gf2_mul(buflen == CK_PIECE ? w.tabs->sub_mul[0] : zb_xpow8(buflen), 0xffffffffu) ^ r)
+                               : zb_adler_from_sums(a % ZB_ADLER_MOD, b % ZB_ADLER_MOD, buflen);
+  if (w.out) w.out[i] = v;
+  if (w.expect) {
+    if (v != w.expect[i]) w.status[i] = ZB_ERR_CHECKSUM;
+    else if (kind == 0 && w.isize_src) {
+      const uint8_t *t = w.isize_src + w.isize_off[i + 1] - 4;
+      if (ld_le32(t) != (uint32_t)buflen) w.status[i] = ZB_ERR_SIZE;
     }
   }
 }
@@ -606,34 +721,21 @@ cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-static cudaError_t ck_attr() {
+cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s) {
+  if (w.n == 0) return cudaSuccess;
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(k_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_piece_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL);
     if (e != cudaSuccess) return e;
     done = true;
   }
-  return cudaSuccess;
-}
-
-cudaError_t zb_launch_verify(const ZbInflateWork &w, cudaStream_t s) {
-  if (w.n == 0 || w.count_only) return cudaSuccess;
-  cudaError_t e = ck_attr();
-  if (e != cudaSuccess) return e;
-  uint32_t blocks = (w.n + CK_WARPS - 1) / CK_WARPS;
-  if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k_checksum<<<blocks, CK_THREADS, CK_SM_TOTAL, s>>>(w.dst, w.dst_off, w.out_len, nullptr, w.status, w.expect, w.kind,
-                                                     w.tabs, w.n, 0, w.src, w.src_off);
-  return cudaGetLastError();
-}
-
-cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s) {
-  if (w.n == 0) return cudaSuccess;
-  cudaError_t e = ck_attr();
-  if (e != cudaSuccess) return e;
-  uint32_t blocks = (w.n + CK_WARPS - 1) / CK_WARPS;
-  if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k_checksum<<<blocks, CK_THREADS, CK_SM_TOTAL, s>>>(w.src, w.off, nullptr, w.out, nullptr, nullptr, nullptr, w.tabs,
-                                                     w.n, w.kind, nullptr, nullptr);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (w.n_pieces) {
+    uint32_t grid = (uint32_t)sms < w.n_pieces ? (uint32_t)sms : w.n_pieces;
+    k_piece_checksum<<<grid, CK_THREADS, CK_SM_TOTAL, s>>>(w);
+  }
+  k_buffer_combine<<<(w.n + 3) / 4, 128, 0, s>>>(w);
   return cudaGetLastError();
 }

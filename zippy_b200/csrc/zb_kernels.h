@@ -72,16 +72,30 @@ struct ZbInflateWork {
   int count_only;
 };
 cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s);
-cudaError_t zb_launch_verify(const ZbInflateWork &w, cudaStream_t s);
 
-// ---- standalone checksums over a batch of buffers ----
-// kind: 0 crc32, 1 adler32.  piece arrays are scratch of size n_pieces.
+// ---- checksums over a batch of buffers (standalone crc32/adler32, and the trailer
+// verification after inflate) ----
+struct ZbPiece {
+  uint64_t rel;   // start of the piece relative to its buffer
+  uint32_t buf;   // buffer index
+  uint32_t pad;
+};
 struct ZbChecksumWork {
-  const uint8_t *src;
-  const uint64_t *off;         // device [n+1]
-  uint32_t *out;               // device [n]
+  const uint8_t *src;          // device: base of the buffers
+  const uint64_t *off;         // device [n+1]: buffer i starts at src + off[i]
+  const uint64_t *lens;        // device [n] actual lengths, or null (= off[i+1]-off[i])
+  const ZbPiece *pieces;       // device [n_pieces]: 64 KiB pieces covering every buffer's capacity
+  const uint32_t *first;       // device [n+1]: first piece of each buffer
+  ZbChunkCheck *piece_out;     // device [n_pieces] scratch
+  uint32_t *out;               // device [n] checksums, or null
+  int *status;                 // device [n] or null: buffers with a non-zero status are skipped;
+                               //   verify mode writes ZB_ERR_CHECKSUM / ZB_ERR_SIZE here
+  const uint32_t *expect;      // device [n] expected value (verify mode) or null
+  const uint32_t *kinds;       // device [n] resolved ZB_DF_* per buffer (gzip -> crc32, zlib -> adler32) or null
+  const uint8_t *isize_src;    // verify mode: compressed buffers (gzip ISIZE lives in their last 4 bytes)
+  const uint64_t *isize_off;   //   and their offsets [n+1]
   const ZbCrcTables *tabs;
-  uint32_t n;
-  int kind;
+  uint32_t n, n_pieces;
+  int kind;                    // 0 crc32, 1 adler32 when kinds == null
 };
 cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s);
