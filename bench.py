@@ -297,9 +297,10 @@ def main():
     # ---- e2e: host (pinned) buffers through the host-buffer C-ABI call ----
     e2e = None
     if not args.no_e2e:
+        hcap = comp_bytes + (64 << 20)
         h_src = torch.empty(n * BLOCK, dtype=torch.uint8).pin_memory()
         h_src.copy_(d_src)
-        h_dst = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        h_dst = torch.empty(hcap, dtype=torch.uint8).pin_memory()
         from zippy_b200 import _native
         L = _native.lib()
         out_offs = np.zeros(n + 1, dtype=np.uint64)
@@ -307,7 +308,7 @@ def main():
 
         def step_host():
             rc = L.zb200_compress_batch(ctx._h, h_src.data_ptr(), src_offsets.ctypes.data, n, args.level, z.dfGzip,
-                                        None, h_dst.data_ptr(), cap, out_offs.ctypes.data, stat.ctypes.data)
+                                        None, h_dst.data_ptr(), hcap, out_offs.ctypes.data, stat.ctypes.data)
             assert rc == 0, rc
             if world > 1:
                 mine = torch.from_numpy((out_offs[1:] - out_offs[:-1]).astype(np.int64)).to(dev)
