@@ -354,3 +354,38 @@ def test_cpp_host_mirror():
     from tests.test_abi import _build_cpp_api_test
     out = subprocess.run([_build_cpp_api_test()], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.startswith("OK"), (out.stdout, out.stderr)
+
+
+def test_mixed_entropy_corpus(z, o, corpus):
+    """BASELINE config 5 at reduced count (SURVEY 8d "C5"): 64 KiB blocks whose class is drawn per block --
+    text, urls, html, uniform random (stored path), run-length blobs -- compressed at level 1 and
+    inflated again on the GPU; every 16th member is also checked by the oracle and zlib."""
+    rng = random.Random(0xC5)
+    T = util.text_corpus(corpus)
+    srcs = {"urls": corpus["urls.10K"], "html": corpus["html"] * 2}
+    blocks = []
+    for i in range(768):
+        cls = util._sm64(0xC5 + i) % 8
+        if cls <= 3:
+            blocks.append(util.c2_block(T, i))
+        elif cls == 4:
+            s0 = rng.randrange(len(srcs["urls"]) - 65536)
+            blocks.append(srcs["urls"][s0:s0 + 65536])
+        elif cls == 5:
+            s0 = rng.randrange(len(srcs["html"]) - 65536)
+            blocks.append(srcs["html"][s0:s0 + 65536])
+        elif cls == 6:
+            blocks.append(rng.randbytes(65536))
+        else:
+            b = bytearray()
+            while len(b) < 65536:
+                b += bytes([rng.randrange(256)]) * rng.randrange(256)
+            blocks.append(bytes(b[:65536]))
+    comp = z.compress_batch(blocks, z.BestSpeed, z.dfGzip)
+    for i in range(0, len(blocks), 16):
+        assert o.uncompress(comp[i]) == blocks[i] and zlib.decompress(comp[i], 31) == blocks[i], i
+    back = z.uncompress_batch(comp)
+    assert all(r == b for r, b in zip(back, blocks))
+    # incompressible blocks must fall back to stored blocks: bounded expansion (deflate.nim:274-277)
+    for b, c in zip(blocks, comp):
+        assert len(c) <= len(b) + 10 + 36

@@ -327,7 +327,8 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
   b.overrun = false;
   br_seek(b, shift0, pos);
   // positions are 32-bit inside a member (a single member's output is limited to 4 GiB - 1)
-  const uint32_t cap = COUNT_ONLY ? 0xffffffffu : (uint32_t)min(cap64, (uint64_t)0xffffffffu);
+  // op + tlen is computed in 32 bits: keep 512 bytes of headroom below 2^32
+  const uint32_t cap = COUNT_ONLY ? 0xfffffdffu : (uint32_t)min(cap64, (uint64_t)0xfffffdffu);
   uint32_t op = 0;
   Tree tl, td;
   bool final_block = false;
@@ -430,39 +431,47 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
     g_sync();
 
     // ---- symbol loop (inflate.nim:173-250): decode into a 32-token batch, then flush ----
+    // One exit: errors are recorded in `err` and resolved after the loop, and a reader that ran a
+    // whole line past the end (b.overrun, set on the rare line-advance path) simply makes the
+    // capacity check fail -- so the hot path carries no per-token error plumbing.
     uint32_t tok = 0, ntok = 0, batch_op = op;
+    int err = 0;  // 0: end of block, 1: invalid stream, 2: out of room (or overrun)
     for (;;) {
       br_refill(b);
-      if (b.overrun) return ZB_ERR_END_OF_BUFFER;  // a whole line past the end: stop decoding zeros
-      uint32_t sym = decode_sym<LL_BITS>(b, ws->lut_ll, tl, ws->syms_ll);
-      uint32_t t, tlen;
-      if (sym < 256) {
-        t = sym;
-        tlen = 1;
-      } else {
+      const uint32_t e = ws->lut_ll[(uint32_t)b.buf & ((1u << LL_BITS) - 1u)];
+      uint32_t sym = e & 511u;
+      const uint32_t l = e >> 9;
+      if (l == 0) sym = decode_slow(b, tl, ws->syms_ll);  // long code (consumes its own bits) or none
+      b.buf >>= l;
+      b.cnt -= (int)l;
+      uint32_t t = sym, tlen = 1;
+      if (sym >= 256) {
         if (sym == 256) break;
-        uint32_t lidx = sym - 257u;
+        const uint32_t lidx = sym - 257u;
         if (lidx >= 29u) {  // includes the undecodable-code case
-          if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-          return ZB_ERR_UNCOMPRESS;
+          err = 1;
+          break;
         }
         const uint32_t lt = len_tab[lidx];
         tlen = (lt & 0xffffu) + br_take(b, (int)(lt >> 16));
         br_refill(b);
-        uint32_t didx = decode_sym<D_BITS>(b, ws->lut_d, td, ws->syms_d);
+        const uint32_t didx = decode_sym<D_BITS>(b, ws->lut_d, td, ws->syms_d);
         if (didx >= 30u) {
-          if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-          return ZB_ERR_UNCOMPRESS;
+          err = 1;
+          break;
         }
         const uint32_t dt = dist_tab[didx];
         const uint32_t dist = (dt & 0xffffu) + br_take(b, (int)(dt >> 16));
         if (dist > op) {
-          if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-          return ZB_ERR_UNCOMPRESS;
+          err = 1;
+          break;
         }
         t = (1u << 31) | ((dist - 1u) << 9) | tlen;
       }
-      if (tlen > cap - op) return (b.overrun || br_past_end(b)) ? ZB_ERR_END_OF_BUFFER : ZB_ERR_DST_TOO_SMALL;
+      if (op + tlen > (b.overrun ? 0u : cap)) {
+        err = 2;
+        break;
+      }
       if ((uint32_t)lane == ntok) tok = t;
       ntok++;
       op += tlen;
@@ -471,6 +480,10 @@ __device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, 
         ntok = 0;
         batch_op = op;
       }
+    }
+    if (err) {
+      if (b.overrun || br_past_end(b)) return ZB_ERR_END_OF_BUFFER;  // decoding ran off the input
+      return err == 1 ? ZB_ERR_UNCOMPRESS : ZB_ERR_DST_TOO_SMALL;
     }
     if (!COUNT_ONLY && ntok) flush_tokens(out, batch_op, tok, ntok);
     if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
