@@ -389,3 +389,37 @@ def test_mixed_entropy_corpus(z, o, corpus):
     # incompressible blocks must fall back to stored blocks: bounded expansion (deflate.nim:274-277)
     for b, c in zip(blocks, comp):
         assert len(c) <= len(b) + 10 + 36
+
+
+def test_device_pointers_of_any_alignment(z, o, corpus):
+    """Source buffers are staged by 16-byte TMA granules from wherever they start: give the device
+    variants a source pointer that is off by 1..15 bytes and members of odd sizes."""
+    torch = pytest.importorskip("torch")
+    ctx = z.Context()
+    items = [corpus["alice29.txt"][:70001], corpus["html"][:12345], b"", corpus["urls.10K"][:65537], b"q" * 31]
+    blob = b"".join(items)
+    offs = np.zeros(len(items) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(x) for x in items])
+    for shift in (1, 7, 15):
+        d_all = torch.zeros(len(blob) + 64, dtype=torch.uint8, device="cuda")
+        d_all[shift:shift + len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+        cap = len(blob) + 4096
+        d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        for level in (1, -1):
+            oo = ctx.compress_batch_device(d_all.data_ptr() + shift, offs, level, z.dfGzip, d_dst.data_ptr(), cap)
+            host = d_dst.cpu().numpy()
+            for i, x in enumerate(items):
+                assert o.uncompress(host[int(oo[i]):int(oo[i + 1])].tobytes()) == x, (shift, level, i)
+        crcs = ctx.checksum_batch_device(d_all.data_ptr() + shift, offs, "crc32")
+        assert [int(c) for c in crcs] == [zlib.crc32(x) for x in items]
+        # inflate from a misaligned compressed buffer into a misaligned output buffer
+        comp = b"".join(o.compress(x, 1, o.dfGzip) for x in items)
+        coffs = np.zeros(len(items) + 1, dtype=np.uint64)
+        coffs[1:] = np.cumsum([len(o.compress(x, 1, o.dfGzip)) for x in items])
+        d_c = torch.zeros(len(comp) + 64, dtype=torch.uint8, device="cuda")
+        d_c[shift:shift + len(comp)] = torch.frombuffer(bytearray(comp), dtype=torch.uint8).cuda()
+        d_o = torch.zeros(len(blob) + 64, dtype=torch.uint8, device="cuda")
+        lens, st = ctx.uncompress_batch_device(d_c.data_ptr() + shift, coffs, z.dfDetect, d_o.data_ptr() + shift, offs)
+        assert not st.any() and [int(l) for l in lens] == [len(x) for x in items]
+        assert d_o[shift:shift + len(blob)].cpu().numpy().tobytes() == blob
+    ctx.close()

@@ -154,6 +154,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
     for (size_t i = 0; i < n; i++)
       if (fname_lens[i] > 25) return ZB200_ERR_ARG;
   if (((uintptr_t)d_dst & 3u) != 0) return ZB200_ERR_ARG;
+  dst_cap &= ~(size_t)3;  // the packer writes whole 32-bit words: never touch a word that straddles the end
   for (size_t i = 0; i < n; i++) {
     if (src_offsets[i + 1] < src_offsets[i]) return ZB200_ERR_ARG;
     if (statuses) statuses[i] = ZB200_OK;
