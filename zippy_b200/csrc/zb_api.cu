@@ -170,7 +170,16 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   std::vector<ZbChunkDesc> desc;
   std::vector<uint32_t> first;
   size_t max_nc = 0, max_nm = 0;
+  size_t chunks_left = 0;
+  for (size_t i = 0; i < n; i++) {
+    uint64_t len = src_offsets[i + 1] - src_offsets[i];
+    chunks_left += len == 0 ? 1 : (size_t)((len + ZB_CHUNK_BYTES - 1) / ZB_CHUNK_BYTES);
+  }
+  const size_t group_cap = max_group_chunks;
   for (size_t m0 = 0; m0 < n;) {
+    // host pipeline: the work after the last H2D (kernels + D2H of the last group) is not overlapped
+    // with anything, so the groups shrink geometrically towards the end of the batch
+    if (h_src) max_group_chunks = std::min(group_cap, std::max<size_t>(512, chunks_left / 2));
     Group g;
     g.m0 = m0;
     g.c0 = desc.size();
@@ -196,6 +205,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
     }
     g.m1 = m1;
     g.nc = desc.size() - g.c0;
+    chunks_left -= std::min(chunks_left, g.nc);
     first.push_back((uint32_t)g.nc);
     g.in_lo = src_offsets[m0] - src_lo;
     g.in_hi = src_offsets[m1] - src_lo;
