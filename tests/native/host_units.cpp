@@ -29,13 +29,14 @@ uint32_t t_crc32_lane_model(const uint8_t *data, uint64_t n) {
   static ZbCrcTables T;
   static int init = 0;
   if (!init) { zb_crc_build_tables(&T); init = 1; }
-  if (n == 8192) {  // the device's fast path: four chains of 16 rows joined by quarter shifts
+  if (n == ZB_SUB_BYTES) {  // the device's fast path: four chains joined by quarter shifts
+    const int QR = ZB_SUB_BYTES / 512;
     uint32_t total = 0;
     for (int lane = 0; lane < 32; lane++) {
       uint32_t r[4] = {0, 0, 0, 0};
-      for (int k = 0; k < 16; k++)
+      for (int k = 0; k < QR; k++)
         for (int c = 0; c < 4; c++) {
-          uint32_t w = ld32(data + 128 * (16 * c + k) + 4 * lane);
+          uint32_t w = ld32(data + 128 * (QR * c + k) + 4 * lane);
           if (k) r[c] = T.mul1024[0][r[c] & 255] ^ T.mul1024[1][(r[c] >> 8) & 255] ^ T.mul1024[2][(r[c] >> 16) & 255] ^ T.mul1024[3][r[c] >> 24];
           r[c] ^= w;
         }

@@ -92,7 +92,7 @@ inline void zb_crc_build_tables(ZbCrcTables *t) {
   for (int k = 0; k < 4; k++)
     for (uint32_t b = 0; b < 256; b++) t->mul1024[k][b] = zb_gf2_mul(b << (8 * k), x1024);
   for (int j = 0; j <= 32; j++) t->lane_mul[j] = zb_xpow8(4ull * (uint64_t)j);
-  for (int k = 1; k < 8; k++) t->sub_mul[k] = zb_xpow8(8192ull * (uint64_t)k);
-  t->sub_mul[0] = zb_xpow8(65536ull);
-  for (int k = 0; k < 4; k++) t->quart_mul[k] = zb_xpow8(2048ull * (uint64_t)k);
+  for (int k = 1; k < 8; k++) t->sub_mul[k] = zb_xpow8((uint64_t)ZB_SUB_BYTES * (uint64_t)k);
+  t->sub_mul[0] = zb_xpow8((uint64_t)ZB_CHUNK_BYTES);
+  for (int k = 0; k < 4; k++) t->quart_mul[k] = zb_xpow8((uint64_t)(ZB_SUB_BYTES / 4) * (uint64_t)k);
 }

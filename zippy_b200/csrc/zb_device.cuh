@@ -108,7 +108,7 @@ struct ZbCheck {
 __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32_t off, uint32_t n,
                                                      const uint32_t *tab, const uint32_t *lane_mul) {
   const int lane = zb_lane();
-  if (n == 8192u) {
+  if (n == (uint32_t)ZB_SUB_BYTES) {
     // Full 8 KiB piece (the common case): four independent Horner chains of 16 rows each, so the
     // table-lookup latency of one chain hides behind the other three; they are joined with the
     // quarter shifts lane_mul[41 + k] = x^(8 * 2048 * k).
@@ -116,9 +116,11 @@ __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32
     uint64_t b = 0;
     const uint32_t o = off + 4u * (uint32_t)lane, rel0 = 4u * (uint32_t)lane;
 #pragma unroll 2
-    for (uint32_t k = 0; k < 16; k++) {
-      const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (16u + k));
-      const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (32u + k)), w3 = zb_ld32_unaligned(base, o + 128u * (48u + k));
+    constexpr uint32_t QR = ZB_SUB_BYTES / 512;  // rows of 128 B per quarter
+    constexpr uint32_t QB = ZB_SUB_BYTES / 4;    // bytes per quarter
+    for (uint32_t k = 0; k < QR; k++) {
+      const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (QR + k));
+      const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (2u * QR + k)), w3 = zb_ld32_unaligned(base, o + 128u * (3u * QR + k));
       if (k) {
         r0 = zb_mul1024(tab, r0);
         r1 = zb_mul1024(tab, r1);
@@ -133,8 +135,8 @@ __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32
       const uint32_t s2 = __dp4a(w2, 0x01010101u, 0u), s3 = __dp4a(w3, 0x01010101u, 0u);
       a += s0 + s1 + s2 + s3;
       const uint32_t rel = rel0 + 128u * k;
-      b += (uint64_t)(8192u - rel) * s0 + (uint64_t)(8192u - 2048u - rel) * s1 + (uint64_t)(8192u - 4096u - rel) * s2 +
-           (uint64_t)(8192u - 6144u - rel) * s3;
+      b += (uint64_t)(4u * QB - rel) * s0 + (uint64_t)(3u * QB - rel) * s1 + (uint64_t)(2u * QB - rel) * s2 +
+           (uint64_t)(QB - rel) * s3;
       b -= (uint64_t)(__dp4a(w0, 0x03020100u, 0u) + __dp4a(w1, 0x03020100u, 0u) + __dp4a(w2, 0x03020100u, 0u) +
                       __dp4a(w3, 0x03020100u, 0u));
     }
