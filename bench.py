@@ -61,58 +61,112 @@ def block_offsets(T_len, first, count):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+
+    Primary source is NVML in-process (a few microseconds per query, so even a 0.3 s region gets
+    dozens of samples); `nvidia-smi -lms` is the fallback when pynvml cannot open the device."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []  # (sm_mhz, sm_max_mhz, set(reasons))
         self.stop = threading.Event()
         self.proc = None
         self.gpu = gpu_index
+        self.nvml = None
+        self.source = None
+
+    def _open_nvml(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        h = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # probe
+        self.nvml, self.h = pynvml, h
+        self.masks = [(pynvml.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                      (pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                      (pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                      (pynvml.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.h
+        mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        while not self.stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((sm, mx, {nm for m, nm in self.masks if bits & m}))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            self._open_nvml()
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._sample_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
-        self.t = threading.Thread(target=self._read, daemon=True)
+        self.source = "nvidia-smi"
+        self.t = threading.Thread(target=self._read_smi, daemon=True)
         self.t.start()
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) >= 7:
+                try:
+                    self.rows.append((float(f[0]), float(f[1]),
+                                      {nm for nm, v in zip(self.NAMES, f[3:7]) if v.lower().startswith("active")}))
+                except ValueError:
+                    pass
             if self.stop.is_set():
                 break
 
+    def mark(self):
+        """Samples taken before this point (start-up, idle clocks) are dropped."""
+        self.first = len(self.rows)
+
     def finish(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock source (nvml, nvidia-smi)"]}
         self.stop.set()
-        try:
-            self.proc.terminate()
-        except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+        if self.proc:
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                self.proc.terminate()
+            except Exception:
+                pass
+        rows = self.rows[getattr(self, "first", 0):]
+        sm = [r[0] for r in rows]
+        reasons = set()
+        for r in rows:
+            reasons |= r[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[1] for r in rows) if rows else None,
+                "samples": len(sm), "source": self.source, "reasons": sorted(reasons)}
 
 
 def cpu_baseline(T, n_blocks_hint, seconds=12.0, threads=None, level=1):
@@ -225,6 +279,8 @@ def main():
     ctx = z.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    clocks = ClockSampler(local_rank)
+    clocks.start()   # samples before clocks.mark() (start-up, warm-up) are dropped
 
     sizes_all = None
 
@@ -269,10 +325,9 @@ def main():
     inflate_ms = t_inf["inflate_ms"] + t_inf["verify_ms"]
 
     # ---- timed region: device-resident ----
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     kern = {"lz_ms": 0.0, "huff_ms": 0.0, "scan_ms": 0.0, "pack_ms": 0.0}
     sync_all()
+    clocks.mark()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
