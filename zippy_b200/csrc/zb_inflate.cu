@@ -17,15 +17,20 @@
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 
-#define INF_G 32                      // lanes per member (16 = two members per warp: measured slower, the halves diverge)
-#define INF_WARPS 8
+#ifndef INF_G
+#define INF_G 8                       // lanes per member; 32 / INF_G members are decoded per warp
+#endif
+#define INF_WARPS 4
 #define INF_THREADS (INF_WARPS * 32)
 #define INF_GROUPS (INF_THREADS / INF_G)
+#define FULL_MASK 0xffffffffu
 
-// A "group" is INF_G consecutive lanes that decode one member together; all collectives are
-// restricted to the group's own lanes.  INF_G = 32 is one member per warp.  INF_G = 16 (two
-// members per warp, hoping to halve the instructions per token) was measured 25-30 % SLOWER on
-// B200: the two halves sit on different code paths almost all the time, so nothing is shared.
+// A "group" is INF_G consecutive lanes that decode one member together; every lane of a group
+// keeps the same decoder state, group collectives are restricted to the group's own lanes.  The
+// 32 / INF_G groups of a warp run the symbol loop in LOCKSTEP: one iteration decodes one token for
+// every group with the literal / match paths predicated instead of branched, so a warp instruction
+// advances 32 / INF_G members at once.  (A first attempt at two members per warp with a branching
+// token loop was 25-30 % slower than one member per warp: the halves never reconverged.)
 __device__ __forceinline__ int g_lane() { return (int)(threadIdx.x & (INF_G - 1)); }
 __device__ __forceinline__ uint32_t g_shift() { return threadIdx.x & 31u & ~(uint32_t)(INF_G - 1); }
 __device__ __forceinline__ uint32_t g_mask() { return (INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u)) << g_shift(); }
@@ -36,88 +41,127 @@ __device__ __forceinline__ uint32_t g_ballot(bool p) {
 }
 __device__ __forceinline__ uint32_t g_match_any(uint32_t v) { return __match_any_sync(g_mask(), v) >> g_shift(); }
 __device__ __forceinline__ void g_sync() { __syncwarp(g_mask()); }
+#ifndef LL_BITS
 #define LL_BITS 10   // literal/length codes up to this long decode with one table lookup
-#define D_BITS 9     // same for distance codes
+#endif
+#ifndef D_BITS
+#define D_BITS 9     // same for distance codes (>= 7: the table also serves the code-length code)
+#endif
 
-struct WarpSmem {
+struct GroupSmem {
   uint16_t lut_ll[1 << LL_BITS];  // symbol | code length << 9; 0 = longer code or no code: slow path
   uint16_t lut_d[1 << D_BITS];
   uint16_t syms_ll[288];          // symbols sorted by (length, symbol) for the canonical slow path
   uint16_t syms_d[32];
   uint8_t lens[320];              // code lengths of the current block (lit/len then distance)
   uint16_t cnt[16];               // per-length counts / running ranks while building
-  uint16_t offs[16];
-  uint16_t first[16];
+  uint16_t first[2][16];          // canonical ranges per code length: [0] literal/length, [1] distance
+  uint16_t count[2][16];          //   (and the code-length code while a dynamic header is read)
+  uint16_t offs[2][16];
 };
+static_assert(sizeof(GroupSmem) % 16 == 0, "group tables must keep 16-byte alignment");
 
-struct Tree {  // lane L holds the entries for code length L
-  uint32_t first, count, offs;
-};
-
+// Bit window of one member (identical in every lane of its group).  The compressed bytes are
+// viewed as 32-bit words from `gbase`; lane j of the group holds word j of two consecutive
+// "lines" (INF_G words each), refilled by one coalesced load per line; the three words at the
+// read position live in registers (w0, w1, w2) and the next two are fetched by shuffle while
+// the current token is being decoded, so consuming up to 48 bits per token never waits on memory.
 struct BitReader {
   const uint32_t *gbase;  // member start rounded down to 4 bytes
-  uint32_t nwords;        // words that contain member bytes
-  uint32_t cur, nxt;      // lane-held words of lines `line` and `line + 1` (a line = INF_G words)
-  uint32_t widx;          // next word to feed into the bit buffer
-  uint64_t buf;
-  int cnt;                // valid bits in buf
+  uint32_t nwords;        // words that contain member bytes (beyond: zeros)
+  uint32_t cur, nxt;      // lane-held words of the line that holds word wi + 3, and of the next line
+  uint32_t w0, w1, w2;    // words wi, wi + 1, wi + 2
+  uint32_t wi;
+  uint32_t bo;            // next unread bit inside w0 (0..31)
+  uint32_t over_word;     // a reader whose wi is beyond this is far past the end of the member
   uint64_t end_bit;       // absolute bit (from gbase) one past the member's last byte
-  bool overrun;           // set when the reader is found to have consumed bits past end_bit
+  bool overrun;           // the reader is far past the end: whatever is being decoded is garbage
 };
 
-__device__ __forceinline__ uint32_t br_load_line(const BitReader &b, uint32_t line) {
-  uint32_t idx = line * (uint32_t)INF_G + (uint32_t)g_lane();
+__device__ __forceinline__ uint32_t br_word(const BitReader &b, uint32_t idx) {
   return idx < b.nwords ? __ldg(b.gbase + idx) : 0u;
 }
-__device__ __forceinline__ uint64_t br_consumed_abs(const BitReader &b) {
-  return (uint64_t)b.widx * 32ull - (uint64_t)b.cnt;
+__device__ __forceinline__ uint32_t br_load_line(const BitReader &b, uint32_t line) {
+  return br_word(b, line * (uint32_t)INF_G + (uint32_t)g_lane());
 }
+__device__ __forceinline__ uint64_t br_consumed_abs(const BitReader &b) { return (uint64_t)b.wi * 32ull + b.bo; }
 __device__ __forceinline__ bool br_past_end(const BitReader &b) { return br_consumed_abs(b) > b.end_bit; }
-__device__ __forceinline__ uint32_t br_next_word(BitReader &b) {
-  uint32_t w = g_shfl(b.cur, (int)(b.widx & (uint32_t)(INF_G - 1)));
-  b.widx++;
-  if ((b.widx & (uint32_t)(INF_G - 1)) == 0) {
-    b.cur = b.nxt;
-    b.nxt = br_load_line(b, b.widx / (uint32_t)INF_G + 1u);
-    // bits past the end read as zero; a reader that is a whole line past the end can only be
-    // decoding garbage: flag it here so that no decode loop runs away (checked by the callers)
-    if ((uint64_t)b.widx * 32ull > b.end_bit + 64ull) b.overrun = true;
-  }
-  return w;
-}
 // position the reader at byte `byte_off` of the member (shift0 = member start & 3)
 __device__ __forceinline__ void br_seek(BitReader &b, uint32_t shift0, uint64_t byte_off) {
   uint64_t abit = (shift0 + byte_off) * 8ull;
-  b.widx = (uint32_t)(abit >> 5);
-  uint32_t skip = (uint32_t)(abit & 31u);
-  uint32_t line = b.widx / (uint32_t)INF_G;
+  b.wi = (uint32_t)(abit >> 5);
+  b.bo = (uint32_t)(abit & 31u);
+  b.w0 = br_word(b, b.wi);
+  b.w1 = br_word(b, b.wi + 1u);
+  b.w2 = br_word(b, b.wi + 2u);
+  const uint32_t line = (b.wi + 3u) / (uint32_t)INF_G;
   b.cur = br_load_line(b, line);
-  b.nxt = br_load_line(b, line + 1);
-  uint32_t w = br_next_word(b);
-  b.buf = (uint64_t)(w >> skip);
-  b.cnt = 32 - (int)skip;
+  b.nxt = br_load_line(b, line + 1u);
 }
-__device__ __forceinline__ void br_refill(BitReader &b) {  // afterwards cnt >= 32
-  if (b.cnt < 32) {
-    b.buf |= (uint64_t)br_next_word(b) << b.cnt;
-    b.cnt += 32;
+// word wi + 3 has just moved into a new line
+__device__ __forceinline__ void br_advance_line(BitReader &b) {
+  b.cur = b.nxt;
+  b.nxt = br_load_line(b, (b.wi + 3u) / (uint32_t)INF_G + 1u);
+  // bits past the end read as zero; a reader that is well past the end can only be decoding
+  // garbage: flag it here so that no decode loop runs away (checked by the callers)
+  if (b.wi > b.over_word) b.overrun = true;
+}
+// Consume n bits (n <= 48).  LOCKSTEP: every lane of the warp executes the call together (the
+// symbol loop), so the shuffle can name the full warp; groups with n == 0 keep their state.
+template <bool LOCKSTEP>
+__device__ __forceinline__ void br_skip(BitReader &b, uint32_t n) {
+  // shfl takes the source lane modulo the width: lane (wi + 3) % INF_G of the group holds word wi + 3
+  const uint32_t n0 = LOCKSTEP ? __shfl_sync(FULL_MASK, b.cur, (int)(b.wi + 3u), INF_G) : g_shfl(b.cur, (int)(b.wi + 3u));
+  const uint32_t pos = b.bo + n;
+  const uint32_t k = pos >> 5;  // whole words consumed: 0, 1 or (tokens longer than 32 bits) 2
+  b.bo = pos & 31u;
+  const bool k1 = k != 0u;
+  b.w0 = k1 ? b.w1 : b.w0;
+  b.w1 = k1 ? b.w2 : b.w1;
+  b.w2 = k1 ? n0 : b.w2;
+  b.wi += k1 ? 1u : 0u;
+  if (k1 && ((b.wi + 3u) & (uint32_t)(INF_G - 1)) == 0u) br_advance_line(b);
+  if (k >= 2u) {  // rare
+    const uint32_t n1 = g_shfl(b.cur, (int)(b.wi + 3u));
+    b.w0 = b.w1;
+    b.w1 = b.w2;
+    b.w2 = n1;
+    b.wi++;
+    if (((b.wi + 3u) & (uint32_t)(INF_G - 1)) == 0u) br_advance_line(b);
   }
 }
-__device__ __forceinline__ uint32_t br_take(BitReader &b, int n) {  // n <= 32, n <= cnt
-  uint32_t v = (uint32_t)b.buf & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
-  b.buf >>= n;
-  b.cnt -= n;
+__device__ __forceinline__ uint32_t br_peek(const BitReader &b) { return __funnelshift_r(b.w0, b.w1, b.bo); }
+__device__ __forceinline__ uint32_t br_take(BitReader &b, int n) {  // n <= 16
+  uint32_t v = br_peek(b) & ((1u << n) - 1u);
+  br_skip<false>(b, (uint32_t)n);
+  return v;
+}
+// shared-memory reads by 32-bit shared address (the decode tables in the symbol loop)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
 
 // Build the decode state from n code lengths (inflate.nim:24-65 initHuffman): the per-length
 // canonical ranges (for the lane-parallel slow path), the sorted symbols, and a direct lookup
-// table for codes of at most lut_bits.  Returns false for an over-subscribed set
-// (inflate.nim:32-34, 45-46).
+// table for codes of at most lut_bits.  Table entries (0 = no code this short: slow path):
+//   KIND 0 (code-length code): symbol | len << 9
+//   KIND 1 (literal/length)  : symbol | len << 9 | extra bits of a length symbol << 13
+//   KIND 2 (distance)        : symbol | len << 5 | extra bits << 9
+// so the number of bits a token occupies is known from the table entries alone and the base
+// values (len_tab / dist_tab) stay off the bit-position dependency chain.
+// Returns false for an over-subscribed set (inflate.nim:32-34, 45-46).
+template <int KIND>
 __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t *syms, uint16_t *lut, int lut_bits,
-                                           WarpSmem *ws, Tree &t) {
+                                           GroupSmem *gs, int which) {
   const int lane = g_lane();
-  if (lane < 16) ws->cnt[lane] = 0;
+  for (int i = lane; i < 16; i += INF_G) gs->cnt[i] = 0;
   {
     uint4 z = make_uint4(0u, 0u, 0u, 0u);
     uint4 *l4 = reinterpret_cast<uint4 *>(lut);
@@ -128,18 +172,18 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
     int s = base + lane;
     uint32_t l = s < n ? lens[s] : 0u;
     uint32_t grp = g_match_any(l);
-    if (l && lane == __ffs((int)grp) - 1) ws->cnt[l] = (uint16_t)(ws->cnt[l] + __popc(grp));
+    if (l && lane == __ffs((int)grp) - 1) gs->cnt[l] = (uint16_t)(gs->cnt[l] + __popc(grp));
     g_sync();
   }
   // per-length first code / first slot (all lanes compute the same recurrence)
   bool ok = true;
-  uint32_t code = 0, k = 0, my_first = 0, my_count = 0, my_offs = 0;
+  uint32_t code = 0, k = 0;
   for (int i = 1; i < 16; i++) {
-    uint32_t c = ws->cnt[i];
-    if (i == lane) {
-      my_first = code;
-      my_count = c;
-      my_offs = k;
+    uint32_t c = gs->cnt[i];
+    if (lane == 0) {
+      gs->first[which][i] = (uint16_t)code;
+      gs->count[which][i] = (uint16_t)c;
+      gs->offs[which][i] = (uint16_t)k;
     }
     code += c;
     if (c > 0 && code - 1 >= (1u << i)) ok = false;
@@ -147,11 +191,8 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
     k += c;
   }
   g_sync();
-  if (lane < 16) {
-    ws->offs[lane] = (uint16_t)my_offs;
-    ws->first[lane] = (uint16_t)my_first;
-    ws->cnt[lane] = 0;  // becomes the running rank per length
-  }
+  for (int i = lane; i < 16; i += INF_G) gs->cnt[i] = 0;  // becomes the running rank per length
+  if (lane == 0) gs->count[which][0] = 0;
   g_sync();
   if (!ok) return false;
   for (int base = 0; base < n; base += INF_G) {
@@ -159,52 +200,55 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
     uint32_t l = s < n ? lens[s] : 0u;
     uint32_t grp = g_match_any(l);
     if (l) {
-      uint32_t rank = ws->cnt[l] + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-      syms[(uint32_t)ws->offs[l] + rank] = (uint16_t)s;
+      uint32_t rank = gs->cnt[l] + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+      syms[(uint32_t)gs->offs[which][l] + rank] = (uint16_t)s;
       if ((int)l <= lut_bits) {
-        uint32_t c = (uint32_t)ws->first[l] + rank;          // canonical code, MSB first
+        uint32_t c = (uint32_t)gs->first[which][l] + rank;   // canonical code, MSB first
         uint32_t rev = __brev(c) >> (32 - l);                // as it appears in the LSB-first stream
-        uint16_t e = (uint16_t)((uint32_t)s | (l << 9));
-        for (uint32_t idx = rev; idx < (1u << lut_bits); idx += (1u << l)) lut[idx] = e;
+        uint32_t e = (uint32_t)s | (l << 9);
+        if (KIND == 1) e |= (s > 256 && s < 286) ? ((uint32_t)zb_len_extra_bits(s - 257) << 13) : 0u;
+        if (KIND == 2) e = (uint32_t)s | (l << 5) | (s < 30 ? ((uint32_t)zb_dist_extra_bits(s) << 9) : 0u);
+        for (uint32_t idx = rev; idx < (1u << lut_bits); idx += (1u << l)) lut[idx] = (uint16_t)e;
       }
     }
     g_sync();
-    if (l && lane == __ffs((int)grp) - 1) ws->cnt[l] = (uint16_t)(ws->cnt[l] + __popc(grp));
+    if (l && lane == __ffs((int)grp) - 1) gs->cnt[l] = (uint16_t)(gs->cnt[l] + __popc(grp));
     g_sync();
   }
-  t.first = my_first;
-  t.count = (lane >= 1 && lane <= 15) ? my_count : 0u;
-  t.offs = my_offs;
   return true;
 }
 
-// Lane-parallel canonical decode (codes longer than the lookup table, and the
-// "no code matches" case, which returns 0xffff: inflate.nim:77-82).
-__device__ __forceinline__ uint32_t decode_slow(BitReader &b, const Tree &t, const uint16_t *syms) {
+// Lane-parallel canonical decode of the code at the low end of x (codes longer than the lookup
+// table, and the "no code matches" case, which returns 0xffff with L = 0: inflate.nim:77-82).
+// Lane j tests the code lengths j, j + INF_G, ...; a ballot picks the shortest that matches.
+__device__ __forceinline__ uint32_t decode_slow(uint32_t x, const GroupSmem *gs, int which, const uint16_t *syms,
+                                                uint32_t &L_out) {
   const int lane = g_lane();
-  uint32_t rev = __brev((uint32_t)b.buf);
-  uint32_t code = lane ? (rev >> (32 - lane)) : 0u;
-  uint32_t rel = code - t.first;
-  uint32_t hit = g_ballot(rel < t.count);
-  if (!hit) return 0xffffu;
-  int L = __ffs((int)hit) - 1;
-  uint32_t idx = g_shfl(t.offs + rel, L);
-  b.buf >>= L;
-  b.cnt -= L;
-  return syms[idx];
-}
-// One symbol (needs >= 15 buffered bits; bits past the end of the member read as zero).
-template <int BITS>
-__device__ __forceinline__ uint32_t decode_sym(BitReader &b, const uint16_t *lut, const Tree &t,
-                                               const uint16_t *syms) {
-  uint32_t e = lut[(uint32_t)b.buf & ((1u << BITS) - 1u)];
-  uint32_t l = e >> 9;
-  if (l) {
-    b.buf >>= l;
-    b.cnt -= (int)l;
-    return e & 511u;
+  const uint32_t rev = __brev(x);
+  for (int base = 0; base < 16; base += INF_G) {
+    const int L = base + lane;
+    const uint32_t code = (L >= 1 && L < 16) ? (rev >> (32 - L)) : 0u;
+    const uint32_t rel = code - (uint32_t)gs->first[which][L & 15];
+    const bool h = L >= 1 && L < 16 && rel < (uint32_t)gs->count[which][L & 15];
+    const uint32_t hit = g_ballot(h);
+    if (hit) {
+      const int j = __ffs((int)hit) - 1;
+      const uint32_t idx = g_shfl((uint32_t)gs->offs[which][L & 15] + rel, j);
+      L_out = (uint32_t)(base + j);
+      return syms[idx];
+    }
   }
-  return decode_slow(b, t, syms);
+  L_out = 0;
+  return 0xffffu;
+}
+// One symbol of the code-length code (dynamic header).
+__device__ __forceinline__ uint32_t decode_clc(BitReader &b, const GroupSmem *gs) {
+  const uint32_t x = br_peek(b);
+  const uint32_t e = gs->lut_d[x & 127u];
+  uint32_t l = e >> 9, sym = e & 511u;
+  if (l == 0) sym = decode_slow(x, gs, 1, gs->syms_d, l);
+  br_skip<false>(b, l);
+  return sym;
 }
 
 __device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
@@ -268,266 +312,420 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
   return ZB_ERR_INVALID_FORMAT;
 }
 
-// Materialise a batch of up to INF_G decoded tokens (lane i of the group holds token i):
-//   literal: the byte;  match: 1 << 31 | (dist - 1) << 9 | len.
-// One lane per token: a warp prefix sum of the lengths places every token; literals and
-// matches whose source lies wholly before the batch are copied by their own lane, in
-// parallel; the few matches that read bytes produced inside the batch follow in stream
-// order, each copied by the whole warp (reads only touch finished output: i % dist).
-__device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, uint32_t tok, uint32_t ntok) {
+// Materialise a batch of up to 32 decoded tokens of one group.  Token k of the batch sits in
+// lane k % INF_G, slot k / INF_G:  literal: the byte;  match: 1 << 31 | (dist - 1) << 9 | len.
+// A group prefix sum of the lengths places every token; literals and short matches whose source
+// lies wholly before the batch are copied by their own lane, all in parallel (loads first, then
+// stores: the sources cannot alias anything written here); matches that read bytes produced
+// inside the batch, and long ones, follow in stream order, each copied by the whole group
+// (reads only touch finished output: i % dist).
+#define INF_ROUNDS (32 / INF_G)
+#define INF_LONG_MATCH 24u
+__device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, const uint32_t (&tok)[INF_ROUNDS],
+                                             uint32_t ntok) {
   const int lane = g_lane();
-  g_sync();  // stores of earlier batches are visible to every lane from here on
-  const bool act = (uint32_t)lane < ntok;
-  const bool is_m = act && (tok >> 31);
-  const uint32_t len = act ? (is_m ? (tok & 511u) : 1u) : 0u;
-  const uint32_t dist = ((tok >> 9) & 0x7fffu) + 1u;
-  uint32_t incl = len;
+  uint32_t len[INF_ROUNDS], rel[INF_ROUNDS];
+  bool is_m[INF_ROUNDS], dep[INF_ROUNDS];
+  uint32_t base = 0;
 #pragma unroll
-  for (int o = 1; o < INF_G; o <<= 1) {
-    uint32_t t = g_shfl_up(incl, o);
-    if (lane >= o) incl += t;
+  for (int r = 0; r < INF_ROUNDS; r++) {
+    const bool act = (uint32_t)(r * INF_G + lane) < ntok;
+    is_m[r] = act && (tok[r] >> 31);
+    len[r] = act ? (is_m[r] ? (tok[r] & 511u) : 1u) : 0u;
+    uint32_t incl = len[r];
+#pragma unroll
+    for (int o = 1; o < INF_G; o <<= 1) {  // the whole warp is here together: full-mask shuffles
+      uint32_t t = __shfl_up_sync(FULL_MASK, incl, o, INF_G);
+      if (lane >= o) incl += t;
+    }
+    rel[r] = base + incl - len[r];  // output offset inside the batch
+    base += __shfl_sync(FULL_MASK, incl, INF_G - 1, INF_G);
   }
-  const uint32_t rel = incl - len;           // output offset inside the batch
-  uint8_t *to = out + batch_op + rel;
-  const bool dep = is_m && dist < rel + len;  // source overlaps this batch's own output
-  if (act && !is_m) {
-    *to = (uint8_t)tok;
-  } else if (is_m && !dep) {
-    const uint8_t *from = to - dist;
-    for (uint32_t k = 0; k < len; k++) to[k] = from[k];
+  __syncwarp();  // stores of earlier batches are visible to every lane from here on
+  uint8_t *const bout = out + batch_op;
+  // parallel part, 4 bytes per token and pass
+  uint32_t more = 0;
+#pragma unroll
+  for (int r = 0; r < INF_ROUNDS; r++) {
+    const uint32_t dist = ((tok[r] >> 9) & 0x7fffu) + 1u;
+    dep[r] = is_m[r] && (dist < rel[r] + len[r] || len[r] > INF_LONG_MATCH);
+    if (len[r] == 1u && !is_m[r]) bout[rel[r]] = (uint8_t)tok[r];
+    if (is_m[r] && !dep[r] && len[r] > 4u) more |= 1u << r;
   }
-  uint32_t depmask = g_ballot(dep);
-  while (depmask) {
-    const int j = __ffs((int)depmask) - 1;
-    depmask &= depmask - 1;
-    const uint32_t rj = g_shfl(rel, j), lj = g_shfl(len, j);
-    const uint32_t dj = g_shfl(dist, j);
-    g_sync();
-    uint8_t *tj = out + batch_op + rj;
-    const uint8_t *fj = tj - dj;
-    if (dj >= lj) {
-      for (uint32_t i = (uint32_t)lane; i < lj; i += INF_G) tj[i] = fj[i];
-    } else {
-      for (uint32_t i = (uint32_t)lane; i < lj; i += INF_G) tj[i] = fj[i % dj];
+  {
+    uint8_t v[INF_ROUNDS][4];
+#pragma unroll
+    for (int r = 0; r < INF_ROUNDS; r++) {
+      const uint32_t dist = ((tok[r] >> 9) & 0x7fffu) + 1u;
+      const uint8_t *from = bout + rel[r] - dist;
+      const bool go = is_m[r] && !dep[r];
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[r][k] = (go && (uint32_t)k < len[r]) ? from[k] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int r = 0; r < INF_ROUNDS; r++) {
+      const bool go = is_m[r] && !dep[r];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (go && (uint32_t)k < len[r]) bout[rel[r] + k] = v[r][k];
+    }
+  }
+  if (more) {
+#pragma unroll
+    for (int r = 0; r < INF_ROUNDS; r++) {
+      if (more & (1u << r)) {
+        const uint32_t dist = ((tok[r] >> 9) & 0x7fffu) + 1u;
+        uint8_t *to = bout + rel[r];
+        const uint8_t *from = to - dist;
+        for (uint32_t k = 4; k < len[r]; k += 4) {
+          uint8_t c0 = from[k], c1 = k + 1 < len[r] ? from[k + 1] : (uint8_t)0, c2 = k + 2 < len[r] ? from[k + 2] : (uint8_t)0,
+                  c3 = k + 3 < len[r] ? from[k + 3] : (uint8_t)0;
+          to[k] = c0;
+          if (k + 1 < len[r]) to[k + 1] = c1;
+          if (k + 2 < len[r]) to[k + 2] = c2;
+          if (k + 3 < len[r]) to[k + 3] = c3;
+        }
+      }
+    }
+  }
+  // ordered part
+#pragma unroll
+  for (int r = 0; r < INF_ROUNDS; r++) {
+    uint32_t depmask = (__ballot_sync(FULL_MASK, dep[r]) >> g_shift()) & (INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u));
+    const uint32_t dist = ((tok[r] >> 9) & 0x7fffu) + 1u;
+    while (depmask) {
+      const int j = __ffs((int)depmask) - 1;
+      depmask &= depmask - 1;
+      const uint32_t rj = g_shfl(rel[r], j), lj = g_shfl(len[r], j);
+      const uint32_t dj = g_shfl(dist, j);
+      g_sync();
+      uint8_t *tj = bout + rj;
+      const uint8_t *fj = tj - dj;
+      if (dj >= lj) {
+        for (uint32_t i = (uint32_t)lane; i < lj; i += INF_G) tj[i] = fj[i];
+      } else {
+        for (uint32_t i = (uint32_t)lane; i < lj; i += INF_G) tj[i] = fj[i % dj];
+      }
     }
   }
 }
 
+// ---- per-group decoder state (identical in every lane of the group) ----
+enum { ST_FETCH = 0, ST_BLOCK = 1, ST_SYMS = 2, ST_EXIT = 3 };
+struct Grp {
+  BitReader b;
+  const uint8_t *src;   // member bytes
+  uint64_t len;
+  uint8_t *out;
+  uint32_t shift0, cap, op, idx, kind, expect;
+  int st;
+  bool final_block;
+};
+
+// Read one block header (inflate.nim:273-289, 104-171).  Stored blocks are copied here.
+// Returns BLK_SYMS when the decode tables are ready for the symbol loop, BLK_DONE when the block
+// is already complete (stored), or a (positive) ZB_ERR_*.
+enum { BLK_SYMS = -1, BLK_DONE = -2 };
 template <bool COUNT_ONLY>
-__device__ __forceinline__ int inflate_member(const uint8_t *src, uint64_t len, uint64_t pos, uint8_t *out,
-                                              uint64_t cap64, WarpSmem *ws, const uint32_t *len_tab,
-                                              const uint32_t *dist_tab, uint64_t &out_len) {
+__device__ __forceinline__ int begin_block(Grp &g, GroupSmem *gs) {
   const int lane = g_lane();
   const uint8_t clcl_order[19] = ZB_CLCL_ORDER;
-  BitReader b;
-  const uint32_t shift0 = (uint32_t)((uintptr_t)src & 3u);
-  b.gbase = reinterpret_cast<const uint32_t *>(src - shift0);
-  b.nwords = (uint32_t)((shift0 + len + 3u) >> 2);
-  b.end_bit = (shift0 + len) * 8ull;
-  b.overrun = false;
-  br_seek(b, shift0, pos);
-  // positions are 32-bit inside a member (a single member's output is limited to 4 GiB - 1)
-  // op + tlen is computed in 32 bits: keep 512 bytes of headroom below 2^32
-  const uint32_t cap = COUNT_ONLY ? 0xfffffdffu : (uint32_t)min(cap64, (uint64_t)0xfffffdffu);
-  uint32_t op = 0;
-  Tree tl, td;
-  bool final_block = false;
-  while (!final_block) {
-    br_refill(b);
-    uint32_t bfinal = br_take(b, 1);
-    uint32_t btype = br_take(b, 2);
+  BitReader &b = g.b;
+  uint32_t bfinal = br_take(b, 1);
+  uint32_t btype = br_take(b, 2);
+  if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+  if (bfinal) g.final_block = true;
+  if (btype == 0) {
+    // ---- stored (inflate.nim:252-266) ----
+    br_skip<false>(b, (8u - (b.bo & 7u)) & 7u);
+    uint32_t l = br_take(b, 16);
+    uint32_t nl = br_take(b, 16);
     if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-    if (bfinal) final_block = true;
-    if (btype == 0) {
-      // ---- stored (inflate.nim:252-266) ----
-      br_take(b, b.cnt & 7);
-      br_refill(b);
-      uint32_t l = br_take(b, 16);
-      br_refill(b);
-      uint32_t nl = br_take(b, 16);
-      if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-      if (l + nl != 65535u) return ZB_ERR_UNCOMPRESS;
-      if (l > 0) {
-        uint64_t byte_pos = (br_consumed_abs(b) >> 3) - shift0;
-        if (byte_pos + l > len) return ZB_ERR_END_OF_BUFFER;
-        if (!COUNT_ONLY) {
-          if (l > cap - op) return ZB_ERR_DST_TOO_SMALL;
-          for (uint32_t i = (uint32_t)lane; i < l; i += INF_G) out[op + i] = src[byte_pos + i];
-        } else if (l > cap - op) {
-          return ZB_ERR_DST_TOO_SMALL;
-        }
-        op += l;
-        br_seek(b, shift0, byte_pos + l);
-      }
-      continue;
+    if (l + nl != 65535u) return ZB_ERR_UNCOMPRESS;
+    if (l > 0) {
+      uint64_t byte_pos = (br_consumed_abs(b) >> 3) - g.shift0;
+      if (byte_pos + l > g.len) return ZB_ERR_END_OF_BUFFER;
+      if (l > g.cap - g.op) return ZB_ERR_DST_TOO_SMALL;
+      if (!COUNT_ONLY)
+        for (uint32_t i = (uint32_t)lane; i < l; i += INF_G) g.out[g.op + i] = g.src[byte_pos + i];
+      g.op += l;
+      br_seek(b, g.shift0, byte_pos + l);
     }
-    if (btype == 3) return ZB_ERR_BLOCK_HEADER;
-    int hlit, hdist;
-    if (btype == 1) {
-      // ---- fixed codes (inflate.nim:111-113) ----
-      for (int i = lane; i < 320; i += INF_G) ws->lens[i] = (uint8_t)(i < 288 ? zb_fixed_ll_len(i) : 5);
-      hlit = 288;
-      hdist = 30;
-      g_sync();
-    } else {
-      // ---- dynamic header (inflate.nim:115-171) ----
-      br_refill(b);
-      hlit = (int)br_take(b, 5) + 257;
-      hdist = (int)br_take(b, 5) + 1;
-      int hclen = (int)br_take(b, 4) + 4;
-      if (hlit > ZB_NUM_LITLEN) return ZB_ERR_UNCOMPRESS;
-      if (hdist > ZB_NUM_DIST) return ZB_ERR_UNCOMPRESS;
-      for (int i = lane; i < 19; i += INF_G) ws->lens[i] = 0;
-      g_sync();
-      for (int i = 0; i < hclen; i++) {
-        br_refill(b);
-        uint32_t v = br_take(b, 3);
-        if (lane == 0) ws->lens[clcl_order[i]] = (uint8_t)v;
-      }
-      g_sync();
-      Tree tc;
-      if (!build_tree(ws->lens, 19, ws->syms_d, ws->lut_d, 7, ws, tc)) return ZB_ERR_UNCOMPRESS;
-      g_sync();
-      // the code-length code now lives in syms_d / lut_d; lens[] is rewritten with the
-      // unpacked literal/length + distance code lengths.
-      int i = 0;
-      const int total = hlit + hdist;
-      uint32_t prev = 0;
-      while (i != total) {
-        br_refill(b);
-        uint32_t sym = decode_sym<7>(b, ws->lut_d, tc, ws->syms_d);
-        if (b.overrun) return ZB_ERR_END_OF_BUFFER;
-        if (sym <= 15) {
-          if (lane == 0) ws->lens[i] = (uint8_t)sym;
-          prev = sym;
-          i++;
-        } else if (sym == 16) {
-          if (i == 0) return ZB_ERR_UNCOMPRESS;
-          int rep = (int)br_take(b, 2) + 3;
-          if (i + rep > 320) return ZB_ERR_UNCOMPRESS;
-          if (lane < rep) ws->lens[i + lane] = (uint8_t)prev;
-          i += rep;
-        } else if (sym == 17) {
-          int rep = (int)br_take(b, 3) + 3;
-          if (i + rep <= 320 && lane < rep) ws->lens[i + lane] = 0;
-          i += rep;
-          prev = 0;
-        } else if (sym == 18) {
-          int rep = (int)br_take(b, 7) + 11;
-          for (int j = lane; j < rep && i + j < 320; j += INF_G) ws->lens[i + j] = 0;
-          i += rep;
-          prev = 0;
-        } else {
-          if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-          return ZB_ERR_INVALID_SYMBOL;  // also the undecodable-code case (0xffff)
-        }
-        if (i > total) return ZB_ERR_UNCOMPRESS;
-      }
-      if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
-      g_sync();
-    }
-    if (!build_tree(ws->lens, hlit, ws->syms_ll, ws->lut_ll, LL_BITS, ws, tl)) return ZB_ERR_UNCOMPRESS;
-    if (!build_tree(ws->lens + hlit, hdist, ws->syms_d, ws->lut_d, D_BITS, ws, td)) return ZB_ERR_UNCOMPRESS;
-    g_sync();
-
-    // ---- symbol loop (inflate.nim:173-250): decode into a 32-token batch, then flush ----
-    // One exit: errors are recorded in `err` and resolved after the loop, and a reader that ran a
-    // whole line past the end (b.overrun, set on the rare line-advance path) simply makes the
-    // capacity check fail -- so the hot path carries no per-token error plumbing.
-    uint32_t tok = 0, ntok = 0, batch_op = op;
-    int err = 0;  // 0: end of block, 1: invalid stream, 2: out of room (or overrun)
-    for (;;) {
-      br_refill(b);
-      const uint32_t e = ws->lut_ll[(uint32_t)b.buf & ((1u << LL_BITS) - 1u)];
-      uint32_t sym = e & 511u;
-      const uint32_t l = e >> 9;
-      if (l == 0) sym = decode_slow(b, tl, ws->syms_ll);  // long code (consumes its own bits) or none
-      b.buf >>= l;
-      b.cnt -= (int)l;
-      uint32_t t = sym, tlen = 1;
-      if (sym >= 256) {
-        if (sym == 256) break;
-        const uint32_t lidx = sym - 257u;
-        if (lidx >= 29u) {  // includes the undecodable-code case
-          err = 1;
-          break;
-        }
-        const uint32_t lt = len_tab[lidx];
-        tlen = (lt & 0xffffu) + br_take(b, (int)(lt >> 16));
-        br_refill(b);
-        const uint32_t didx = decode_sym<D_BITS>(b, ws->lut_d, td, ws->syms_d);
-        if (didx >= 30u) {
-          err = 1;
-          break;
-        }
-        const uint32_t dt = dist_tab[didx];
-        const uint32_t dist = (dt & 0xffffu) + br_take(b, (int)(dt >> 16));
-        if (dist > op) {
-          err = 1;
-          break;
-        }
-        t = (1u << 31) | ((dist - 1u) << 9) | tlen;
-      }
-      if (op + tlen > (b.overrun ? 0u : cap)) {
-        err = 2;
-        break;
-      }
-      if ((uint32_t)lane == ntok) tok = t;
-      ntok++;
-      op += tlen;
-      if (ntok == INF_G) {
-        if (!COUNT_ONLY) flush_tokens(out, batch_op, tok, INF_G);
-        ntok = 0;
-        batch_op = op;
-      }
-    }
-    if (err) {
-      if (b.overrun || br_past_end(b)) return ZB_ERR_END_OF_BUFFER;  // decoding ran off the input
-      return err == 1 ? ZB_ERR_UNCOMPRESS : ZB_ERR_DST_TOO_SMALL;
-    }
-    if (!COUNT_ONLY && ntok) flush_tokens(out, batch_op, tok, ntok);
-    if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+    return BLK_DONE;
   }
-  out_len = op;
-  return ZB_OK;
+  if (btype == 3) return ZB_ERR_BLOCK_HEADER;
+  int hlit, hdist;
+  if (btype == 1) {
+    // ---- fixed codes (inflate.nim:111-113) ----
+    for (int i = lane; i < 320; i += INF_G) gs->lens[i] = (uint8_t)(i < 288 ? zb_fixed_ll_len(i) : 5);
+    hlit = 288;
+    hdist = 30;
+    g_sync();
+  } else {
+    // ---- dynamic header (inflate.nim:115-171) ----
+    hlit = (int)br_take(b, 5) + 257;
+    hdist = (int)br_take(b, 5) + 1;
+    int hclen = (int)br_take(b, 4) + 4;
+    if (hlit > ZB_NUM_LITLEN) return ZB_ERR_UNCOMPRESS;
+    if (hdist > ZB_NUM_DIST) return ZB_ERR_UNCOMPRESS;
+    for (int i = lane; i < 19; i += INF_G) gs->lens[i] = 0;
+    g_sync();
+    for (int i = 0; i < hclen; i++) {
+      uint32_t v = br_take(b, 3);
+      if (lane == 0) gs->lens[clcl_order[i]] = (uint8_t)v;
+    }
+    g_sync();
+    if (!build_tree<0>(gs->lens, 19, gs->syms_d, gs->lut_d, 7, gs, 1)) return ZB_ERR_UNCOMPRESS;
+    g_sync();
+    // the code-length code now lives in syms_d / lut_d; lens[] is rewritten with the
+    // unpacked literal/length + distance code lengths.
+    int i = 0;
+    const int total = hlit + hdist;
+    uint32_t prev = 0;
+    while (i != total) {
+      uint32_t sym = decode_clc(b, gs);
+      if (b.overrun) return ZB_ERR_END_OF_BUFFER;
+      if (sym <= 15) {
+        if (lane == 0) gs->lens[i] = (uint8_t)sym;
+        prev = sym;
+        i++;
+      } else if (sym == 16) {
+        if (i == 0) return ZB_ERR_UNCOMPRESS;
+        int rep = (int)br_take(b, 2) + 3;
+        if (i + rep > 320) return ZB_ERR_UNCOMPRESS;
+        if (lane < rep) gs->lens[i + lane] = (uint8_t)prev;
+        i += rep;
+      } else if (sym == 17) {
+        int rep = (int)br_take(b, 3) + 3;
+        for (int j = lane; j < rep && i + j < 320; j += INF_G) gs->lens[i + j] = 0;
+        i += rep;
+        prev = 0;
+      } else if (sym == 18) {
+        int rep = (int)br_take(b, 7) + 11;
+        for (int j = lane; j < rep && i + j < 320; j += INF_G) gs->lens[i + j] = 0;
+        i += rep;
+        prev = 0;
+      } else {
+        if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+        return ZB_ERR_INVALID_SYMBOL;  // also the undecodable-code case (0xffff)
+      }
+      if (i > total) return ZB_ERR_UNCOMPRESS;
+    }
+    if (br_past_end(b)) return ZB_ERR_END_OF_BUFFER;
+    g_sync();
+  }
+  if (!build_tree<1>(gs->lens, hlit, gs->syms_ll, gs->lut_ll, LL_BITS, gs, 0)) return ZB_ERR_UNCOMPRESS;
+  if (!build_tree<2>(gs->lens + hlit, hdist, gs->syms_d, gs->lut_d, D_BITS, gs, 1)) return ZB_ERR_UNCOMPRESS;
+  g_sync();
+  return BLK_SYMS;
+}
+
+// The symbol loop (inflate.nim:173-250) for all groups of the warp at once.  Every iteration
+// decodes ONE token per decoding group; the match path is computed unconditionally and
+// selected, so the groups stay converged whatever mix of literals and matches they see.  The
+// bit position of the next token depends only on the two table entries (code length + extra
+// bit count are both in the entry), which keeps the loop-carried dependency short.  32 tokens
+// per group are collected (token k in lane k % INF_G, slot k / INF_G) and then flushed; a group
+// that reaches the end of its block or an error idles until the batch ends, the loop stops,
+// and the caller resolves the event.  ev: 0 none, 1 end of block, 2 invalid stream, 3 out of
+// room (or overrun).
+template <bool COUNT_ONLY>
+__device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t tab_addr) {
+  const int lane = g_lane();
+  bool act = g.st == ST_SYMS;
+  BitReader &b = g.b;
+  uint32_t op = g.op;
+  const uint32_t cap = g.cap;
+  // 32-bit shared addresses of this group's tables and of the base-value tables
+  const uint32_t ll_addr = (uint32_t)__cvta_generic_to_shared(gs->lut_ll);
+  const uint32_t d_addr = (uint32_t)__cvta_generic_to_shared(gs->lut_d);
+  uint32_t len_addr = tab_addr;
+  asm volatile("" : "+r"(len_addr));  // keep the address in a register (else it is recomputed from %cluster_ctaid per use)
+  const uint32_t dist_addr = len_addr + 128u;
+  int ev = 0;
+  for (;;) {
+    uint32_t tok[INF_ROUNDS];
+    uint32_t ntok = 0;
+    const uint32_t batch_op = op;
+#pragma unroll
+    for (int r = 0; r < INF_ROUNDS; r++) {
+      tok[r] = 0;
+#pragma unroll 1
+      for (int j = 0; j < INF_G; j++) {
+        const uint32_t x1 = br_peek(b);
+        const uint32_t e = lds_u16(ll_addr + ((x1 & ((1u << LL_BITS) - 1u)) << 1));
+        uint32_t sym = e & 511u, l = (e >> 9) & 15u, ext = e >> 13;
+        uint32_t p2 = b.bo + l + ext;  // <= 31 + 20
+        uint32_t x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
+        const uint32_t e2 = lds_u16(d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
+        uint32_t dsym = e2 & 31u, l2 = (e2 >> 5) & 15u, dext = e2 >> 9;
+        uint32_t lidx = min(sym - 257u, 31u);  // 29..31 (and every non-length symbol): not a length
+        bool want_d = act && sym > 256u && lidx < 29u;
+        if (act && (l == 0u || (want_d && l2 == 0u))) {
+          // rare: a code longer than its lookup table (or no code at all)
+          if (l == 0u) {
+            sym = decode_slow(x1, gs, 0, gs->syms_ll, l);
+            lidx = min(sym - 257u, 31u);
+            ext = lidx < 29u ? (lds_u32(len_addr + lidx * 4u) >> 16) : 0u;
+            want_d = sym > 256u && lidx < 29u;
+            p2 = b.bo + l + ext;
+            x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
+            const uint32_t e3 = lds_u16(d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
+            dsym = e3 & 31u;
+            l2 = (e3 >> 5) & 15u;
+            dext = e3 >> 9;
+          }
+          if (want_d && l2 == 0u) {
+            dsym = decode_slow(x2, gs, 1, gs->syms_d, l2);
+            dext = dsym < 30u ? (lds_u32(dist_addr + dsym * 4u) >> 16) : 0u;
+          }
+        }
+        const bool is_len = sym > 256u;
+        const uint32_t lenx = (x1 >> l) & ~(0xffffffffu << ext);
+        const uint32_t distx = (x2 >> l2) & ~(0xffffffffu << dext);
+        const uint32_t adv = (p2 - b.bo) + (want_d ? l2 + dext : 0u);
+        br_skip<true>(b, act ? adv : 0u);
+        // everything below is off the bit-position chain
+        const uint32_t tlen = is_len ? (lds_u32(len_addr + lidx * 4u) & 0xffffu) + lenx : 1u;
+        const uint32_t dist = (lds_u32(dist_addr + min(dsym, 31u) * 4u) & 0xffffu) + distx;
+        const bool bad = is_len && (lidx >= 29u || dsym >= 30u || dist > op);
+        const uint32_t t = is_len ? ((1u << 31) | ((dist - 1u) << 9) | tlen) : sym;
+        const bool room = op + tlen <= (b.overrun ? 0u : cap);
+        uint32_t now = sym == 256u ? 1u : (bad ? 2u : (room ? 0u : 3u));
+        now = act ? now : 0u;
+        const bool emit = act && now == 0u;
+        if (emit && lane == j) tok[r] = t;
+        ntok += emit ? 1u : 0u;
+        op += emit ? tlen : 0u;
+        ev = now ? (int)now : ev;
+        act = act && now == 0u;
+      }
+    }
+    if (!COUNT_ONLY) flush_tokens(g.out, batch_op, tok, ntok);
+    if (__any_sync(FULL_MASK, ev != 0)) break;
+  }
+  g.op = op;
+  return ev;
 }
 
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(INF_THREADS)
     k_inflate(ZbInflateWork w) {
-  __shared__ __align__(16) WarpSmem wsm[INF_GROUPS];
-  __shared__ uint32_t len_tab[32], dist_tab[32];  // base | extra bits << 16 (RFC 1951 3.2.5)
+  extern __shared__ __align__(16) unsigned char inf_smem[];
+  // base | extra bits << 16 (RFC 1951 3.2.5), unused slots 0; placed after the groups' tables
+  uint32_t *len_tab = reinterpret_cast<uint32_t *>(inf_smem + INF_GROUPS * sizeof(GroupSmem));
+  uint32_t *dist_tab = len_tab + 32;
+  const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(len_tab);
   const int lane = g_lane();
-  WarpSmem *ws = &wsm[threadIdx.x / INF_G];
-  if (threadIdx.x < 29) len_tab[threadIdx.x] = zb_len_base((int)threadIdx.x) | ((uint32_t)zb_len_extra_bits((int)threadIdx.x) << 16);
-  if (threadIdx.x >= 32 && threadIdx.x < 62) {
+  GroupSmem *gs = reinterpret_cast<GroupSmem *>(inf_smem) + threadIdx.x / INF_G;
+  if (threadIdx.x < 32)
+    len_tab[threadIdx.x] = threadIdx.x < 29 ? (zb_len_base((int)threadIdx.x) | ((uint32_t)zb_len_extra_bits((int)threadIdx.x) << 16)) : 0u;
+  else if (threadIdx.x < 64) {
     int c = (int)threadIdx.x - 32;
-    dist_tab[c] = zb_dist_base(c) | ((uint32_t)zb_dist_extra_bits(c) << 16);
+    dist_tab[c] = c < 30 ? (zb_dist_base(c) | ((uint32_t)zb_dist_extra_bits(c) << 16)) : 0u;
   }
   __syncthreads();
+  Grp g;
+  g.st = ST_FETCH;
+  g.b.gbase = nullptr;
+  g.b.nwords = 0;
+  g.b.cur = g.b.nxt = g.b.over_word = 0;
+  g.b.w0 = g.b.w1 = g.b.w2 = g.b.wi = g.b.bo = 0;
+  g.b.end_bit = 0;
+  g.b.overrun = false;
+  g.op = g.cap = 0;
+  g.out = nullptr;
   for (;;) {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(w.counter, 1u);
-    i = g_shfl(i, 0);
-    if (i >= w.n) break;
-    const uint64_t s0 = w.src_off[i], s1 = w.src_off[i + 1];
-    const uint8_t *src = w.src + s0;
-    const uint64_t len = s1 - s0;
-    uint64_t pos = 0, out_len = 0;
-    uint32_t kind = 0, expect = 0, isize = 0;
-    int st = parse_wrapper(src, len, w.data_format, w.pos, pos, kind, expect, isize);
-    if (st == ZB_OK) {
-      uint8_t *out = COUNT_ONLY ? nullptr : w.dst + w.dst_off[i];
-      uint64_t cap = COUNT_ONLY ? 0 : w.dst_off[i + 1] - w.dst_off[i];
-      if (COUNT_ONLY && kind == ZB_DF_GZIP) out_len = isize;  // gzip.nim:66 (trustSize's source)
-      else st = inflate_member<COUNT_ONLY>(src, len, pos, out, cap, ws, len_tab, dist_tab, out_len);
+    int done = 1;  // status to report when `fin` is set
+    bool fin = false;
+    if (g.st == ST_FETCH) {
+      uint32_t i = 0;
+      if (lane == 0) i = atomicAdd(w.counter, 1u);
+      i = g_shfl(i, 0);
+      if (i >= w.n) {
+        g.st = ST_EXIT;
+      } else {
+        const uint64_t s0 = w.src_off[i], s1 = w.src_off[i + 1];
+        g.idx = i;
+        g.src = w.src + s0;
+        g.len = s1 - s0;
+        g.op = 0;
+        g.final_block = false;
+        uint64_t pos = 0;
+        uint32_t isize = 0;
+        g.kind = 0;
+        g.expect = 0;
+        int st = parse_wrapper(g.src, g.len, w.data_format, w.pos, pos, g.kind, g.expect, isize);
+        if (st == ZB_OK && COUNT_ONLY && g.kind == ZB_DF_GZIP) {
+          g.op = isize;  // gzip.nim:66 (trustSize's source)
+          fin = true;
+          done = ZB_OK;
+        } else if (st != ZB_OK) {
+          fin = true;
+          done = st;
+        } else {
+          g.out = COUNT_ONLY ? nullptr : w.dst + w.dst_off[i];
+          const uint64_t cap64 = COUNT_ONLY ? ~0ull : w.dst_off[i + 1] - w.dst_off[i];
+          // positions are 32-bit inside a member (a single member's output is limited to 4 GiB - 1);
+          // op + tlen is computed in 32 bits: keep 512 bytes of headroom below 2^32
+          g.cap = (uint32_t)min(cap64, (uint64_t)0xfffffdffu);
+          g.shift0 = (uint32_t)((uintptr_t)g.src & 3u);
+          g.b.gbase = reinterpret_cast<const uint32_t *>(g.src - g.shift0);
+          g.b.nwords = (uint32_t)((g.shift0 + g.len + 3u) >> 2);
+          g.b.end_bit = (g.shift0 + g.len) * 8ull;
+          g.b.over_word = (uint32_t)((g.b.end_bit + 64ull) >> 5);
+          g.b.overrun = false;
+          br_seek(g.b, g.shift0, pos);
+          g.st = ST_BLOCK;
+        }
+      }
+    } else if (g.st == ST_BLOCK) {
+      int r = begin_block<COUNT_ONLY>(g, gs);
+      if (r >= 0) {
+        fin = true;
+        done = r;
+      } else if (r == BLK_SYMS) {
+        g.st = ST_SYMS;
+      } else if (g.final_block) {
+        fin = true;
+        done = ZB_OK;
+      }
     }
-    g_sync();
-    if (lane == 0) {
-      w.status[i] = st;
-      w.out_len[i] = st == ZB_OK ? out_len : 0;
-      w.kind[i] = kind;
-      w.expect[i] = expect;
+    if (fin) {
+      if (lane == 0) {
+        w.status[g.idx] = done;
+        w.out_len[g.idx] = done == ZB_OK ? (uint64_t)g.op : 0ull;
+        w.kind[g.idx] = g.kind;
+        w.expect[g.idx] = g.expect;
+      }
+      g.st = ST_FETCH;
+    }
+    __syncwarp();
+    if (__all_sync(FULL_MASK, g.st == ST_EXIT)) break;
+    // run the lockstep symbol loop only when no group of the warp is waiting for a header or a
+    // new member: those are short, and would otherwise stall behind a whole block of symbols
+    if (__any_sync(FULL_MASK, g.st == ST_FETCH || g.st == ST_BLOCK)) continue;
+    const int ev = symbol_loop<COUNT_ONLY>(g, gs, tab_addr);
+    if (g.st == ST_SYMS && ev) {
+      int st = ZB_OK;
+      if (ev == 1) {
+        if (br_past_end(g.b)) st = ZB_ERR_END_OF_BUFFER;
+      } else if (g.b.overrun || br_past_end(g.b)) {
+        st = ZB_ERR_END_OF_BUFFER;  // decoding ran off the input
+      } else {
+        st = ev == 2 ? ZB_ERR_UNCOMPRESS : ZB_ERR_DST_TOO_SMALL;
+      }
+      if (st != ZB_OK || g.final_block) {
+        if (lane == 0) {
+          w.status[g.idx] = st;
+          w.out_len[g.idx] = st == ZB_OK ? (uint64_t)g.op : 0ull;
+          w.kind[g.idx] = g.kind;
+          w.expect[g.idx] = g.expect;
+        }
+        g.st = ST_FETCH;
+      } else {
+        g.st = ST_BLOCK;
+      }
     }
   }
 }
@@ -721,16 +919,26 @@ __global__ void __launch_bounds__(128)
 // ------------------------------------------------------------------------------------
 cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s) {
   if (w.n == 0) return cudaSuccess;
+  const int smem = (int)(INF_GROUPS * sizeof(GroupSmem)) + 256;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(k_inflate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    done = true;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  uint32_t blocks = (uint32_t)sms * 6u;
+  uint32_t per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  uint32_t blocks = (uint32_t)sms * per_sm;
   uint32_t need = (w.n + INF_GROUPS - 1) / INF_GROUPS;
   if (blocks > need) blocks = need;
   cudaError_t e = cudaMemsetAsync(w.counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  if (w.count_only) k_inflate<true><<<blocks, INF_THREADS, 0, s>>>(w);
-  else k_inflate<false><<<blocks, INF_THREADS, 0, s>>>(w);
+  if (w.count_only) k_inflate<true><<<blocks, INF_THREADS, smem, s>>>(w);
+  else k_inflate<false><<<blocks, INF_THREADS, smem, s>>>(w);
   return cudaGetLastError();
 }
 
