@@ -41,11 +41,15 @@ __device__ __forceinline__ uint32_t g_ballot(bool p) {
 }
 __device__ __forceinline__ uint32_t g_match_any(uint32_t v) { return __match_any_sync(g_mask(), v) >> g_shift(); }
 __device__ __forceinline__ void g_sync() { __syncwarp(g_mask()); }
+// Table sizes trade slow-path decodes against occupancy: the kernel is bound by the latency of
+// the per-token dependency chain, so warps per SM matter more than table hits.  Measured on B200
+// (4 GiB of 64 KiB text members / the C3 fixture batch): 10 + 9 bits, 12 warps per SM: 117 / 200
+// ms;  9 + 8 bits, 20 warps per SM: 92 / 171 ms.
 #ifndef LL_BITS
-#define LL_BITS 10   // literal/length codes up to this long decode with one table lookup
+#define LL_BITS 9    // literal/length codes up to this long decode with one table lookup
 #endif
 #ifndef D_BITS
-#define D_BITS 9     // same for distance codes (>= 7: the table also serves the code-length code)
+#define D_BITS 8     // same for distance codes (>= 7: the table also serves the code-length code)
 #endif
 
 struct GroupSmem {
@@ -312,26 +316,40 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
   return ZB_ERR_INVALID_FORMAT;
 }
 
-// Materialise a batch of up to 32 decoded tokens of one group.  Token k of the batch sits in
-// lane k % INF_G, slot k / INF_G:  literal: the byte;  match: 1 << 31 | (dist - 1) << 9 | len.
-// A group prefix sum of the lengths places every token; literals and short matches whose source
-// lies wholly before the batch are copied by their own lane, all in parallel (loads first, then
-// stores: the sources cannot alias anything written here); matches that read bytes produced
-// inside the batch, and long ones, follow in stream order, each copied by the whole group
-// (reads only touch finished output: i % dist).
+// Validate and materialise a batch of up to 32 decoded tokens of one group.  Token k of the batch
+// sits in lane k % INF_G, slot k / INF_G, still "raw" as the symbol loop decoded it:
+//   symbol (9 bits) | length extra value << 9 | distance symbol << 14 | distance extra value << 19
+// Everything that does not feed the bit position is done HERE, one lane per token instead of
+// redundantly by the whole group: base values (RFC 1951 3.2.5), the checks of inflate.nim:203,
+// 212, 224 (length symbol >= 29, distance symbol >= 30, distance > bytes produced) and the
+// capacity check.  A group prefix sum of the lengths places every token.  Literals and short
+// matches whose source lies wholly before the batch are copied by their own lane, all in parallel
+// (loads first, then stores: the sources cannot alias anything written here); matches that read
+// bytes produced inside the batch, and long ones, follow in stream order, each copied by the
+// whole group (reads only touch finished output: i % dist).
+// Returns 0, or 2 (invalid token) / 3 (out of room) for the first offending token in stream order,
+// whose index is stored to bad_k; only the tokens before it are written and counted in op.
 #define INF_ROUNDS (32 / INF_G)
 #define INF_LONG_MATCH 24u
-__device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, const uint32_t (&tok)[INF_ROUNDS],
-                                             uint32_t ntok) {
+template <bool COUNT_ONLY>
+__device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t cap, const uint32_t (&raw)[INF_ROUNDS],
+                                            uint32_t ntok, uint32_t len_addr, uint32_t dist_addr, uint32_t &bad_k) {
   const int lane = g_lane();
-  uint32_t len[INF_ROUNDS], rel[INF_ROUNDS];
+  const uint32_t gsel = INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u);
+  const uint32_t batch_op = op;
+  uint32_t len[INF_ROUNDS], rel[INF_ROUNDS], dist[INF_ROUNDS];
   bool is_m[INF_ROUNDS], dep[INF_ROUNDS];
-  uint32_t base = 0;
+  uint32_t base = 0, evm[INF_ROUNDS], badm[INF_ROUNDS];
+  bool any_ev = false;
 #pragma unroll
   for (int r = 0; r < INF_ROUNDS; r++) {
     const bool act = (uint32_t)(r * INF_G + lane) < ntok;
-    is_m[r] = act && (tok[r] >> 31);
-    len[r] = act ? (is_m[r] ? (tok[r] & 511u) : 1u) : 0u;
+    const uint32_t sym = raw[r] & 511u;
+    const uint32_t lidx = min(sym - 257u, 31u);
+    const uint32_t dsym = (raw[r] >> 14) & 31u;
+    is_m[r] = act && sym > 256u;
+    len[r] = act ? (is_m[r] ? (lds_u32(len_addr + lidx * 4u) & 0xffffu) + ((raw[r] >> 9) & 31u) : 1u) : 0u;
+    dist[r] = (lds_u32(dist_addr + dsym * 4u) & 0xffffu) + (raw[r] >> 19);
     uint32_t incl = len[r];
 #pragma unroll
     for (int o = 1; o < INF_G; o <<= 1) {  // the whole warp is here together: full-mask shuffles
@@ -340,24 +358,50 @@ __device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, co
     }
     rel[r] = base + incl - len[r];  // output offset inside the batch
     base += __shfl_sync(FULL_MASK, incl, INF_G - 1, INF_G);
+    const bool bad = is_m[r] && (lidx >= 29u || dsym >= 30u || dist[r] > batch_op + rel[r]);
+    const bool noroom = act && rel[r] + len[r] > cap - batch_op;
+    badm[r] = (__ballot_sync(FULL_MASK, bad) >> g_shift()) & gsel;
+    evm[r] = (__ballot_sync(FULL_MASK, bad || noroom) >> g_shift()) & gsel;
+    any_ev = any_ev || evm[r] != 0u;
   }
+  int ev = 0;
+  uint32_t n_ok = ntok, total = base;
+  if (any_ev) {  // rare: cut the batch at the first offending token
+#pragma unroll
+    for (int r = INF_ROUNDS - 1; r >= 0; r--) {
+      if (evm[r]) {
+        const int j = __ffs((int)evm[r]) - 1;
+        n_ok = (uint32_t)(r * INF_G + j);
+        ev = ((badm[r] >> j) & 1u) ? 2 : 3;
+        total = g_shfl(rel[r], j);
+      }
+    }
+    bad_k = n_ok;
+#pragma unroll
+    for (int r = 0; r < INF_ROUNDS; r++) {
+      if ((uint32_t)(r * INF_G + lane) >= n_ok) {
+        len[r] = 0;
+        is_m[r] = false;
+      }
+    }
+  }
+  op = batch_op + total;
+  if (COUNT_ONLY) return ev;
   __syncwarp();  // stores of earlier batches are visible to every lane from here on
   uint8_t *const bout = out + batch_op;
   // parallel part, 4 bytes per token and pass
   uint32_t more = 0;
 #pragma unroll
   for (int r = 0; r < INF_ROUNDS; r++) {
-    const uint32_t dist = ((tok[r] >> 9) & 0x7fffu) + 1u;
-    dep[r] = is_m[r] && (dist < rel[r] + len[r] || len[r] > INF_LONG_MATCH);
-    if (len[r] == 1u && !is_m[r]) bout[rel[r]] = (uint8_t)tok[r];
+    dep[r] = is_m[r] && (dist[r] < rel[r] + len[r] || len[r] > INF_LONG_MATCH);
+    if (len[r] == 1u && !is_m[r]) bout[rel[r]] = (uint8_t)raw[r];
     if (is_m[r] && !dep[r] && len[r] > 4u) more |= 1u << r;
   }
   {
     uint8_t v[INF_ROUNDS][4];
 #pragma unroll
     for (int r = 0; r < INF_ROUNDS; r++) {
-      const uint32_t dist = ((tok[r] >> 9) & 0x7fffu) + 1u;
-      const uint8_t *from = bout + rel[r] - dist;
+      const uint8_t *from = bout + rel[r] - dist[r];
       const bool go = is_m[r] && !dep[r];
 #pragma unroll
       for (int k = 0; k < 4; k++) v[r][k] = (go && (uint32_t)k < len[r]) ? from[k] : (uint8_t)0;
@@ -374,9 +418,8 @@ __device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, co
 #pragma unroll
     for (int r = 0; r < INF_ROUNDS; r++) {
       if (more & (1u << r)) {
-        const uint32_t dist = ((tok[r] >> 9) & 0x7fffu) + 1u;
         uint8_t *to = bout + rel[r];
-        const uint8_t *from = to - dist;
+        const uint8_t *from = to - dist[r];
         for (uint32_t k = 4; k < len[r]; k += 4) {
           uint8_t c0 = from[k], c1 = k + 1 < len[r] ? from[k + 1] : (uint8_t)0, c2 = k + 2 < len[r] ? from[k + 2] : (uint8_t)0,
                   c3 = k + 3 < len[r] ? from[k + 3] : (uint8_t)0;
@@ -391,13 +434,12 @@ __device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, co
   // ordered part
 #pragma unroll
   for (int r = 0; r < INF_ROUNDS; r++) {
-    uint32_t depmask = (__ballot_sync(FULL_MASK, dep[r]) >> g_shift()) & (INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u));
-    const uint32_t dist = ((tok[r] >> 9) & 0x7fffu) + 1u;
+    uint32_t depmask = (__ballot_sync(FULL_MASK, dep[r]) >> g_shift()) & gsel;
     while (depmask) {
       const int j = __ffs((int)depmask) - 1;
       depmask &= depmask - 1;
       const uint32_t rj = g_shfl(rel[r], j), lj = g_shfl(len[r], j);
-      const uint32_t dj = g_shfl(dist, j);
+      const uint32_t dj = g_shfl(dist[r], j);
       g_sync();
       uint8_t *tj = bout + rj;
       const uint8_t *fj = tj - dj;
@@ -408,6 +450,7 @@ __device__ __forceinline__ void flush_tokens(uint8_t *out, uint32_t batch_op, co
       }
     }
   }
+  return ev;
 }
 
 // ---- per-group decoder state (identical in every lane of the group) ----
@@ -524,32 +567,32 @@ __device__ __forceinline__ int begin_block(Grp &g, GroupSmem *gs) {
 // decodes ONE token per decoding group; the match path is computed unconditionally and
 // selected, so the groups stay converged whatever mix of literals and matches they see.  The
 // bit position of the next token depends only on the two table entries (code length + extra
-// bit count are both in the entry), which keeps the loop-carried dependency short.  32 tokens
-// per group are collected (token k in lane k % INF_G, slot k / INF_G) and then flushed; a group
-// that reaches the end of its block or an error idles until the batch ends, the loop stops,
-// and the caller resolves the event.  ev: 0 none, 1 end of block, 2 invalid stream, 3 out of
-// room (or overrun).
+// bit count are both in the entry), which keeps the loop-carried dependency short; the loop
+// itself only extracts the raw fields, flush_tokens turns them into bytes (and finds invalid
+// tokens) one lane per token.  32 tokens per group are collected (token k in lane k % INF_G,
+// slot k / INF_G) and then flushed; a group that reaches the end of its block idles until the
+// batch ends, the loop stops, and the caller resolves the event.
+// Returns 0 (another group stopped the loop), 1 (end of block) or 100 + ZB_ERR_*.
 template <bool COUNT_ONLY>
 __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t tab_addr) {
   const int lane = g_lane();
   bool act = g.st == ST_SYMS;
   BitReader &b = g.b;
   uint32_t op = g.op;
-  const uint32_t cap = g.cap;
   // 32-bit shared addresses of this group's tables and of the base-value tables
   const uint32_t ll_addr = (uint32_t)__cvta_generic_to_shared(gs->lut_ll);
   const uint32_t d_addr = (uint32_t)__cvta_generic_to_shared(gs->lut_d);
   uint32_t len_addr = tab_addr;
   asm volatile("" : "+r"(len_addr));  // keep the address in a register (else it is recomputed from %cluster_ctaid per use)
   const uint32_t dist_addr = len_addr + 128u;
-  int ev = 0;
+  int ev = 0;  // 1: end of block, 4: reader overrun
   for (;;) {
-    uint32_t tok[INF_ROUNDS];
+    uint32_t tok[INF_ROUNDS], pos[INF_ROUNDS];
     uint32_t ntok = 0;
-    const uint32_t batch_op = op;
 #pragma unroll
     for (int r = 0; r < INF_ROUNDS; r++) {
       tok[r] = 0;
+      pos[r] = 0;
 #pragma unroll 1
       for (int j = 0; j < INF_G; j++) {
         const uint32_t x1 = br_peek(b);
@@ -559,15 +602,15 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
         uint32_t x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
         const uint32_t e2 = lds_u16(d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
         uint32_t dsym = e2 & 31u, l2 = (e2 >> 5) & 15u, dext = e2 >> 9;
-        uint32_t lidx = min(sym - 257u, 31u);  // 29..31 (and every non-length symbol): not a length
-        bool want_d = act && sym > 256u && lidx < 29u;
+        bool want_d = act && (sym - 257u) < 29u;
         if (act && (l == 0u || (want_d && l2 == 0u))) {
           // rare: a code longer than its lookup table (or no code at all)
           if (l == 0u) {
             sym = decode_slow(x1, gs, 0, gs->syms_ll, l);
-            lidx = min(sym - 257u, 31u);
+            sym = l ? sym : 287u;  // no code: an invalid length symbol
+            const uint32_t lidx = sym - 257u;
             ext = lidx < 29u ? (lds_u32(len_addr + lidx * 4u) >> 16) : 0u;
-            want_d = sym > 256u && lidx < 29u;
+            want_d = lidx < 29u;
             p2 = b.bo + l + ext;
             x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
             const uint32_t e3 = lds_u16(d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
@@ -577,39 +620,53 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
           }
           if (want_d && l2 == 0u) {
             dsym = decode_slow(x2, gs, 1, gs->syms_d, l2);
+            dsym = l2 ? dsym : 31u;  // no code: an invalid distance symbol
             dext = dsym < 30u ? (lds_u32(dist_addr + dsym * 4u) >> 16) : 0u;
           }
         }
-        const bool is_len = sym > 256u;
         const uint32_t lenx = (x1 >> l) & ~(0xffffffffu << ext);
         const uint32_t distx = (x2 >> l2) & ~(0xffffffffu << dext);
         const uint32_t adv = (p2 - b.bo) + (want_d ? l2 + dext : 0u);
         br_skip<true>(b, act ? adv : 0u);
-        // everything below is off the bit-position chain
-        const uint32_t tlen = is_len ? (lds_u32(len_addr + lidx * 4u) & 0xffffu) + lenx : 1u;
-        const uint32_t dist = (lds_u32(dist_addr + min(dsym, 31u) * 4u) & 0xffffu) + distx;
-        const bool bad = is_len && (lidx >= 29u || dsym >= 30u || dist > op);
-        const uint32_t t = is_len ? ((1u << 31) | ((dist - 1u) << 9) | tlen) : sym;
-        const bool room = op + tlen <= (b.overrun ? 0u : cap);
-        uint32_t now = sym == 256u ? 1u : (bad ? 2u : (room ? 0u : 3u));
-        now = act ? now : 0u;
-        const bool emit = act && now == 0u;
-        if (emit && lane == j) tok[r] = t;
+        const uint32_t t = sym | (lenx << 9) | (dsym << 14) | (distx << 19);
+        const bool emit = act && sym != 256u;
+        if (emit && lane == j) {
+          tok[r] = t;
+          pos[r] = (b.wi << 5) | b.bo;  // low 32 bits of the reader position after this token
+        }
         ntok += emit ? 1u : 0u;
-        op += emit ? tlen : 0u;
-        ev = now ? (int)now : ev;
-        act = act && now == 0u;
+        const bool stop = act && (sym == 256u || b.overrun);
+        ev = stop ? (sym == 256u ? 1 : 4) : ev;
+        act = act && !stop;
       }
     }
-    if (!COUNT_ONLY) flush_tokens(g.out, batch_op, tok, ntok);
+    uint32_t bad_k = 0;
+    const int fev = flush_tokens<COUNT_ONLY>(g.out, op, g.cap, tok, ntok, len_addr, dist_addr, bad_k);
+    if (fev) {
+      // inflate.nim:190-191 order: a token that ran off the input reports the end of the buffer
+      uint32_t pk = 0;
+#pragma unroll
+      for (int r = 0; r < INF_ROUNDS; r++) {
+        const uint32_t v = g_shfl(pos[r], (int)(bad_k & (uint32_t)(INF_G - 1)));
+        if ((bad_k / (uint32_t)INF_G) == (uint32_t)r) pk = v;
+      }
+      const uint64_t now_abs = br_consumed_abs(b);  // the token lies < 2^11 bits before this
+      const bool past = now_abs - (uint64_t)((uint32_t)now_abs - pk) > b.end_bit;
+      ev = 100 + (past ? ZB_ERR_END_OF_BUFFER : (fev == 2 ? ZB_ERR_UNCOMPRESS : ZB_ERR_DST_TOO_SMALL));
+    } else if (ev == 4) {
+      ev = 100 + ZB_ERR_END_OF_BUFFER;
+    }
     if (__any_sync(FULL_MASK, ev != 0)) break;
   }
   g.op = op;
   return ev;
 }
 
+#ifndef INF_MIN_CTAS
+#define INF_MIN_CTAS 5   // register budget for 5 CTAs (20 warps) per SM, the shared-memory limit
+#endif
 template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(INF_THREADS)
+__global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
     k_inflate(ZbInflateWork w) {
   extern __shared__ __align__(16) unsigned char inf_smem[];
   // base | extra bits << 16 (RFC 1951 3.2.5), unused slots 0; placed after the groups' tables
@@ -710,10 +767,8 @@ __global__ void __launch_bounds__(INF_THREADS)
       int st = ZB_OK;
       if (ev == 1) {
         if (br_past_end(g.b)) st = ZB_ERR_END_OF_BUFFER;
-      } else if (g.b.overrun || br_past_end(g.b)) {
-        st = ZB_ERR_END_OF_BUFFER;  // decoding ran off the input
       } else {
-        st = ev == 2 ? ZB_ERR_UNCOMPRESS : ZB_ERR_DST_TOO_SMALL;
+        st = ev - 100;
       }
       if (st != ZB_OK || g.final_block) {
         if (lane == 0) {
