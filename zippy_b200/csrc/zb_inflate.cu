@@ -319,6 +319,7 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
 // Validate and materialise a batch of up to 32 decoded tokens of one group.  Token k of the batch
 // sits in lane k % INF_G, slot k / INF_G, still "raw" as the symbol loop decoded it:
 //   symbol (9 bits) | length extra value << 9 | distance symbol << 14 | distance extra value << 19
+// or, for two literals in a row:  first byte | second byte << 14 | 1 << 22
 // Everything that does not feed the bit position is done HERE, one lane per token instead of
 // redundantly by the whole group: base values (RFC 1951 3.2.5), the checks of inflate.nim:203,
 // 212, 224 (length symbol >= 29, distance symbol >= 30, distance > bytes produced) and the
@@ -348,7 +349,8 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
     const uint32_t lidx = min(sym - 257u, 31u);
     const uint32_t dsym = (raw[r] >> 14) & 31u;
     is_m[r] = act && sym > 256u;
-    len[r] = act ? (is_m[r] ? (lds_u32(len_addr + lidx * 4u) & 0xffffu) + ((raw[r] >> 9) & 31u) : 1u) : 0u;
+    len[r] = act ? (is_m[r] ? (lds_u32(len_addr + lidx * 4u) & 0xffffu) + ((raw[r] >> 9) & 31u) : 1u + ((raw[r] >> 22) & 1u))
+                 : 0u;
     dist[r] = (lds_u32(dist_addr + dsym * 4u) & 0xffffu) + (raw[r] >> 19);
     uint32_t incl = len[r];
 #pragma unroll
@@ -394,7 +396,10 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
 #pragma unroll
   for (int r = 0; r < INF_ROUNDS; r++) {
     dep[r] = is_m[r] && (dist[r] < rel[r] + len[r] || len[r] > INF_LONG_MATCH);
-    if (len[r] == 1u && !is_m[r]) bout[rel[r]] = (uint8_t)raw[r];
+    if (len[r] != 0u && !is_m[r]) {
+      bout[rel[r]] = (uint8_t)raw[r];
+      if (len[r] == 2u) bout[rel[r] + 1u] = (uint8_t)(raw[r] >> 14);
+    }
     if (is_m[r] && !dep[r] && len[r] > 4u) more |= 1u << r;
   }
   {
@@ -600,8 +605,14 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
         uint32_t sym = e & 511u, l = (e >> 9) & 15u, ext = e >> 13;
         uint32_t p2 = b.bo + l + ext;  // <= 31 + 20
         uint32_t x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
-        const uint32_t e2 = lds_u16(d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
-        uint32_t dsym = e2 & 31u, l2 = (e2 >> 5) & 15u, dext = e2 >> 9;
+        // second lookup: the distance table after a length symbol; after a literal, the
+        // literal/length table again -- two literals in a row leave as ONE token slot
+        const bool lit1 = sym < 256u;
+        const uint32_t e2 = lds_u16(lit1 ? ll_addr + ((x2 & ((1u << LL_BITS) - 1u)) << 1)
+                                         : d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
+        uint32_t dsym = e2 & 31u, l2 = (e2 >> 5) & 15u, dext = e2 >> 9;  // read as a distance entry
+        const uint32_t sym2 = e2 & 511u, l2b = (e2 >> 9) & 15u;          // read as a literal/length entry
+        const bool pair = act && lit1 && l != 0u && l2b != 0u && sym2 < 256u;
         bool want_d = act && (sym - 257u) < 29u;
         if (act && (l == 0u || (want_d && l2 == 0u))) {
           // rare: a code longer than its lookup table (or no code at all)
@@ -626,9 +637,10 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
         }
         const uint32_t lenx = (x1 >> l) & ~(0xffffffffu << ext);
         const uint32_t distx = (x2 >> l2) & ~(0xffffffffu << dext);
-        const uint32_t adv = (p2 - b.bo) + (want_d ? l2 + dext : 0u);
+        const uint32_t adv = (p2 - b.bo) + (want_d ? l2 + dext : (pair ? l2b : 0u));
         br_skip<true>(b, act ? adv : 0u);
-        const uint32_t t = sym | (lenx << 9) | (dsym << 14) | (distx << 19);
+        const uint32_t hi = want_d ? ((dsym << 14) | (distx << 19)) : (pair ? ((sym2 << 14) | (1u << 22)) : 0u);
+        const uint32_t t = sym | (lenx << 9) | hi;
         const bool emit = act && sym != 256u;
         if (emit && lane == j) {
           tok[r] = t;
