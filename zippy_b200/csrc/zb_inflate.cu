@@ -24,6 +24,9 @@
 #define INF_THREADS (INF_WARPS * 32)
 #define INF_GROUPS (INF_THREADS / INF_G)
 #define FULL_MASK 0xffffffffu
+#ifndef INF_SPLIT_LONG
+#define INF_SPLIT_LONG 0   // 1: of more than 32 bits are consumed in two steps by the rare path (measured 4 % slower: the test sits on the bit-position chain)
+#endif
 
 // A "group" is INF_G consecutive lanes that decode one member together; every lane of a group
 // keeps the same decoder state, group collectives are restricted to the group's own lanes.  The
@@ -110,8 +113,9 @@ __device__ __forceinline__ void br_advance_line(BitReader &b) {
   // garbage: flag it here so that no decode loop runs away (checked by the callers)
   if (b.wi > b.over_word) b.overrun = true;
 }
-// Consume n bits (n <= 48).  LOCKSTEP: every lane of the warp executes the call together (the
-// symbol loop), so the shuffle can name the full warp; groups with n == 0 keep their state.
+// Consume n bits.  LOCKSTEP: every lane of the warp executes the call together (the symbol
+// loop), so the shuffle can name the full warp; groups with n == 0 keep their state; n <= 32
+// there (longer tokens are split by the caller).  Otherwise n <= 48.
 template <bool LOCKSTEP>
 __device__ __forceinline__ void br_skip(BitReader &b, uint32_t n) {
   // shfl takes the source lane modulo the width: lane (wi + 3) % INF_G of the group holds word wi + 3
@@ -125,7 +129,7 @@ __device__ __forceinline__ void br_skip(BitReader &b, uint32_t n) {
   b.w2 = k1 ? n0 : b.w2;
   b.wi += k1 ? 1u : 0u;
   if (k1 && ((b.wi + 3u) & (uint32_t)(INF_G - 1)) == 0u) br_advance_line(b);
-  if (k >= 2u) {  // rare
+  if ((!LOCKSTEP || !INF_SPLIT_LONG) && k >= 2u) {  // rare
     const uint32_t n1 = g_shfl(b.cur, (int)(b.wi + 3u));
     b.w0 = b.w1;
     b.w1 = b.w2;
@@ -318,8 +322,11 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
 
 // Validate and materialise a batch of up to 32 decoded tokens of one group.  Token k of the batch
 // sits in lane k % INF_G, slot k / INF_G, still "raw" as the symbol loop decoded it:
-//   symbol (9 bits) | length extra value << 9 | distance symbol << 14 | distance extra value << 19
-// or, for two literals in a row:  first byte | second byte << 14 | 1 << 22
+//   ta = symbol (9 bits) | length extra value << 9 | second table entry << 14
+//   tb = distance extra value (13 bits) | reader position after the token << 13
+// The second table entry is the distance entry (symbol | code length << 5 | extra bits << 9)
+// after a length symbol; after a literal it is the literal/length entry of the NEXT symbol, and
+// when that is a literal too (symbol < 256, code length != 0) the slot holds both bytes.
 // Everything that does not feed the bit position is done HERE, one lane per token instead of
 // redundantly by the whole group: base values (RFC 1951 3.2.5), the checks of inflate.nim:203,
 // 212, 224 (length symbol >= 29, distance symbol >= 30, distance > bytes produced) and the
@@ -333,8 +340,9 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
 #define INF_ROUNDS (32 / INF_G)
 #define INF_LONG_MATCH 24u
 template <bool COUNT_ONLY>
-__device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t cap, const uint32_t (&raw)[INF_ROUNDS],
-                                            uint32_t ntok, uint32_t len_addr, uint32_t dist_addr, uint32_t &bad_k) {
+__device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t cap, const uint32_t (&ta)[INF_ROUNDS],
+                                            const uint32_t (&tb)[INF_ROUNDS], uint32_t ntok, uint32_t len_addr,
+                                            uint32_t dist_addr, uint32_t &bad_k) {
   const int lane = g_lane();
   const uint32_t gsel = INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u);
   const uint32_t batch_op = op;
@@ -345,13 +353,14 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
 #pragma unroll
   for (int r = 0; r < INF_ROUNDS; r++) {
     const bool act = (uint32_t)(r * INF_G + lane) < ntok;
-    const uint32_t sym = raw[r] & 511u;
+    const uint32_t sym = ta[r] & 511u;
     const uint32_t lidx = min(sym - 257u, 31u);
-    const uint32_t dsym = (raw[r] >> 14) & 31u;
+    const uint32_t e2 = ta[r] >> 14;
+    const uint32_t dsym = e2 & 31u;
+    const bool two = (e2 & 511u) < 256u && ((e2 >> 9) & 15u) != 0u;  // (only looked at for a literal)
     is_m[r] = act && sym > 256u;
-    len[r] = act ? (is_m[r] ? (lds_u32(len_addr + lidx * 4u) & 0xffffu) + ((raw[r] >> 9) & 31u) : 1u + ((raw[r] >> 22) & 1u))
-                 : 0u;
-    dist[r] = (lds_u32(dist_addr + dsym * 4u) & 0xffffu) + (raw[r] >> 19);
+    len[r] = act ? (is_m[r] ? (lds_u32(len_addr + lidx * 4u) & 0xffffu) + ((ta[r] >> 9) & 31u) : (two ? 2u : 1u)) : 0u;
+    dist[r] = (lds_u32(dist_addr + dsym * 4u) & 0xffffu) + (tb[r] & 0x1fffu);
     uint32_t incl = len[r];
 #pragma unroll
     for (int o = 1; o < INF_G; o <<= 1) {  // the whole warp is here together: full-mask shuffles
@@ -397,8 +406,8 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
   for (int r = 0; r < INF_ROUNDS; r++) {
     dep[r] = is_m[r] && (dist[r] < rel[r] + len[r] || len[r] > INF_LONG_MATCH);
     if (len[r] != 0u && !is_m[r]) {
-      bout[rel[r]] = (uint8_t)raw[r];
-      if (len[r] == 2u) bout[rel[r] + 1u] = (uint8_t)(raw[r] >> 14);
+      bout[rel[r]] = (uint8_t)ta[r];
+      if (len[r] == 2u) bout[rel[r] + 1u] = (uint8_t)(ta[r] >> 14);
     }
     if (is_m[r] && !dep[r] && len[r] > 4u) more |= 1u << r;
   }
@@ -590,83 +599,88 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
   uint32_t len_addr = tab_addr;
   asm volatile("" : "+r"(len_addr));  // keep the address in a register (else it is recomputed from %cluster_ctaid per use)
   const uint32_t dist_addr = len_addr + 128u;
-  int ev = 0;  // 1: end of block, 4: reader overrun
+  const bool act0 = act;
+  int ev = 0;
   for (;;) {
-    uint32_t tok[INF_ROUNDS], pos[INF_ROUNDS];
+    // token k of the batch: lane k % INF_G, slot k / INF_G, two registers (see flush_tokens)
+    uint32_t ta[INF_ROUNDS], tb[INF_ROUNDS];
     uint32_t ntok = 0;
 #pragma unroll
     for (int r = 0; r < INF_ROUNDS; r++) {
-      tok[r] = 0;
-      pos[r] = 0;
+      ta[r] = 0;
+      tb[r] = 0;
 #pragma unroll 1
       for (int j = 0; j < INF_G; j++) {
+        const uint32_t bo0 = b.bo;
         const uint32_t x1 = br_peek(b);
         const uint32_t e = lds_u16(ll_addr + ((x1 & ((1u << LL_BITS) - 1u)) << 1));
         uint32_t sym = e & 511u, l = (e >> 9) & 15u, ext = e >> 13;
-        uint32_t p2 = b.bo + l + ext;  // <= 31 + 20
+        uint32_t p2 = bo0 + l + ext;  // <= 31 + 20
         uint32_t x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
         // second lookup: the distance table after a length symbol; after a literal, the
         // literal/length table again -- two literals in a row leave as ONE token slot
         const bool lit1 = sym < 256u;
-        const uint32_t e2 = lds_u16(lit1 ? ll_addr + ((x2 & ((1u << LL_BITS) - 1u)) << 1)
-                                         : d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
-        uint32_t dsym = e2 & 31u, l2 = (e2 >> 5) & 15u, dext = e2 >> 9;  // read as a distance entry
-        const uint32_t sym2 = e2 & 511u, l2b = (e2 >> 9) & 15u;          // read as a literal/length entry
+        uint32_t e2 = lds_u16(lit1 ? ll_addr + ((x2 & ((1u << LL_BITS) - 1u)) << 1)
+                                   : d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
+        uint32_t l2 = (e2 >> 5) & 15u, dext = e2 >> 9;  // read as a distance entry
+        const uint32_t sym2 = e2 & 511u, l2b = dext & 15u;  // read as a literal/length entry
         const bool pair = act && lit1 && l != 0u && l2b != 0u && sym2 < 256u;
         bool want_d = act && (sym - 257u) < 29u;
-        if (act && (l == 0u || (want_d && l2 == 0u))) {
-          // rare: a code longer than its lookup table (or no code at all)
+        uint32_t pre = 0;  // bits already consumed by the rare path below
+        if (act && (l == 0u || (want_d && (l2 == 0u || (INF_SPLIT_LONG && (p2 - bo0) + l2 + dext > 32u))))) {
+          // rare: a code longer than its lookup table (or no code at all), or a token of more
+          // than 32 bits (consumed in two steps)
           if (l == 0u) {
             sym = decode_slow(x1, gs, 0, gs->syms_ll, l);
             sym = l ? sym : 287u;  // no code: an invalid length symbol
             const uint32_t lidx = sym - 257u;
             ext = lidx < 29u ? (lds_u32(len_addr + lidx * 4u) >> 16) : 0u;
             want_d = lidx < 29u;
-            p2 = b.bo + l + ext;
+            p2 = bo0 + l + ext;
             x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
-            const uint32_t e3 = lds_u16(d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
-            dsym = e3 & 31u;
-            l2 = (e3 >> 5) & 15u;
-            dext = e3 >> 9;
+            e2 = want_d ? lds_u16(d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1)) : 0u;  // 0: never a literal pair
+            l2 = (e2 >> 5) & 15u;
+            dext = e2 >> 9;
           }
           if (want_d && l2 == 0u) {
-            dsym = decode_slow(x2, gs, 1, gs->syms_d, l2);
+            uint32_t dsym = decode_slow(x2, gs, 1, gs->syms_d, l2);
             dsym = l2 ? dsym : 31u;  // no code: an invalid distance symbol
             dext = dsym < 30u ? (lds_u32(dist_addr + dsym * 4u) >> 16) : 0u;
+            e2 = dsym | (l2 << 5) | (dext << 9);
+          }
+          if (INF_SPLIT_LONG && want_d && (p2 - bo0) + l2 + dext > 32u) {
+            pre = p2 - bo0;
+            br_skip<false>(b, pre);
           }
         }
         const uint32_t lenx = (x1 >> l) & ~(0xffffffffu << ext);
         const uint32_t distx = (x2 >> l2) & ~(0xffffffffu << dext);
-        const uint32_t adv = (p2 - b.bo) + (want_d ? l2 + dext : (pair ? l2b : 0u));
+        const uint32_t adv = (p2 - bo0) - pre + (want_d ? l2 + dext : (pair ? l2b : 0u));
         br_skip<true>(b, act ? adv : 0u);
-        const uint32_t hi = want_d ? ((dsym << 14) | (distx << 19)) : (pair ? ((sym2 << 14) | (1u << 22)) : 0u);
-        const uint32_t t = sym | (lenx << 9) | hi;
         const bool emit = act && sym != 256u;
         if (emit && lane == j) {
-          tok[r] = t;
-          pos[r] = (b.wi << 5) | b.bo;  // low 32 bits of the reader position after this token
+          ta[r] = sym | (lenx << 9) | (e2 << 14);
+          tb[r] = distx | (((b.wi << 5) | b.bo) << 13);  // + low bits of the reader position after the token
         }
         ntok += emit ? 1u : 0u;
-        const bool stop = act && (sym == 256u || b.overrun);
-        ev = stop ? (sym == 256u ? 1 : 4) : ev;
-        act = act && !stop;
+        act = emit && !b.overrun;
       }
     }
     uint32_t bad_k = 0;
-    const int fev = flush_tokens<COUNT_ONLY>(g.out, op, g.cap, tok, ntok, len_addr, dist_addr, bad_k);
+    const int fev = flush_tokens<COUNT_ONLY>(g.out, op, g.cap, ta, tb, ntok, len_addr, dist_addr, bad_k);
+    // a group that stopped: end of block (symbol 256), or a reader far past the end of its input
+    ev = (act0 && !act) ? (b.overrun ? 100 + ZB_ERR_END_OF_BUFFER : 1) : 0;
     if (fev) {
       // inflate.nim:190-191 order: a token that ran off the input reports the end of the buffer
       uint32_t pk = 0;
 #pragma unroll
       for (int r = 0; r < INF_ROUNDS; r++) {
-        const uint32_t v = g_shfl(pos[r], (int)(bad_k & (uint32_t)(INF_G - 1)));
-        if ((bad_k / (uint32_t)INF_G) == (uint32_t)r) pk = v;
+        const uint32_t v = g_shfl(tb[r], (int)(bad_k & (uint32_t)(INF_G - 1)));
+        if ((bad_k / (uint32_t)INF_G) == (uint32_t)r) pk = v >> 13;
       }
       const uint64_t now_abs = br_consumed_abs(b);  // the token lies < 2^11 bits before this
-      const bool past = now_abs - (uint64_t)((uint32_t)now_abs - pk) > b.end_bit;
+      const bool past = now_abs - (uint64_t)(((uint32_t)now_abs - pk) & 0x7ffffu) > b.end_bit;
       ev = 100 + (past ? ZB_ERR_END_OF_BUFFER : (fev == 2 ? ZB_ERR_UNCOMPRESS : ZB_ERR_DST_TOO_SMALL));
-    } else if (ev == 4) {
-      ev = 100 + ZB_ERR_END_OF_BUFFER;
     }
     if (__any_sync(FULL_MASK, ev != 0)) break;
   }
