@@ -117,11 +117,14 @@ __device__ __forceinline__ void br_advance_line(BitReader &b) {
 // loop), so the shuffle can name the full warp; groups with n == 0 keep their state; n <= 32
 // there (longer tokens are split by the caller).  Otherwise n <= 48.
 template <bool LOCKSTEP>
-__device__ __forceinline__ void br_skip(BitReader &b, uint32_t n) {
+__device__ __forceinline__ uint32_t br_skip(BitReader &b, uint32_t n) {
   // shfl takes the source lane modulo the width: lane (wi + 3) % INF_G of the group holds word wi + 3
   const uint32_t n0 = LOCKSTEP ? __shfl_sync(FULL_MASK, b.cur, (int)(b.wi + 3u), INF_G) : g_shfl(b.cur, (int)(b.wi + 3u));
   const uint32_t pos = b.bo + n;
   const uint32_t k = pos >> 5;  // whole words consumed: 0, 1 or (tokens longer than 32 bits) 2
+  // the 32 bits at the new position, from the window as it is (valid for pos < 64): lets the
+  // next token start without waiting for the window registers to move
+  const uint32_t peek = (pos & 32u) ? __funnelshift_r(b.w1, b.w2, pos) : __funnelshift_r(b.w0, b.w1, pos);
   b.bo = pos & 31u;
   const bool k1 = k != 0u;
   b.w0 = k1 ? b.w1 : b.w0;
@@ -136,13 +139,21 @@ __device__ __forceinline__ void br_skip(BitReader &b, uint32_t n) {
     b.w2 = n1;
     b.wi++;
     if (((b.wi + 3u) & (uint32_t)(INF_G - 1)) == 0u) br_advance_line(b);
+    return __funnelshift_r(b.w0, b.w1, b.bo);
   }
+  return peek;
 }
 __device__ __forceinline__ uint32_t br_peek(const BitReader &b) { return __funnelshift_r(b.w0, b.w1, b.bo); }
 __device__ __forceinline__ uint32_t br_take(BitReader &b, int n) {  // n <= 16
   uint32_t v = br_peek(b) & ((1u << n) - 1u);
   br_skip<false>(b, (uint32_t)n);
   return v;
+}
+// base + 2 * idx in one instruction (the address of a 16-bit table entry)
+__device__ __forceinline__ uint32_t lut_addr(uint32_t base, uint32_t idx) {
+  uint32_t a;
+  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a) : "r"(idx), "r"(base));
+  return a;
 }
 // shared-memory reads by 32-bit shared address (the decode tables in the symbol loop)
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
@@ -160,10 +171,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 // canonical ranges (for the lane-parallel slow path), the sorted symbols, and a direct lookup
 // table for codes of at most lut_bits.  Table entries (0 = no code this short: slow path):
 //   KIND 0 (code-length code): symbol | len << 9
-//   KIND 1 (literal/length)  : symbol | len << 9 | extra bits of a length symbol << 13
-//   KIND 2 (distance)        : symbol | len << 5 | extra bits << 9
-// so the number of bits a token occupies is known from the table entries alone and the base
-// values (len_tab / dist_tab) stay off the bit-position dependency chain.
+//   KIND 1 (literal/length)  : symbol | (len + extra bits of a length symbol) << 11
+//   KIND 2 (distance)        : symbol | (len + extra bits) << 11
+// so the number of bits a token occupies is one shift away from the table entries and nothing
+// else (base values, the split of code and extra bits) sits on the bit-position dependency chain.
 // Returns false for an over-subscribed set (inflate.nim:32-34, 45-46).
 template <int KIND>
 __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t *syms, uint16_t *lut, int lut_bits,
@@ -214,8 +225,8 @@ __device__ __forceinline__ bool build_tree(const uint8_t *lens, int n, uint16_t 
         uint32_t c = (uint32_t)gs->first[which][l] + rank;   // canonical code, MSB first
         uint32_t rev = __brev(c) >> (32 - l);                // as it appears in the LSB-first stream
         uint32_t e = (uint32_t)s | (l << 9);
-        if (KIND == 1) e |= (s > 256 && s < 286) ? ((uint32_t)zb_len_extra_bits(s - 257) << 13) : 0u;
-        if (KIND == 2) e = (uint32_t)s | (l << 5) | (s < 30 ? ((uint32_t)zb_dist_extra_bits(s) << 9) : 0u);
+        if (KIND == 1) e = (uint32_t)s | ((l + ((s > 256 && s < 286) ? (uint32_t)zb_len_extra_bits(s - 257) : 0u)) << 11);
+        if (KIND == 2) e = (uint32_t)s | ((l + (s < 30 ? (uint32_t)zb_dist_extra_bits(s) : 0u)) << 11);
         for (uint32_t idx = rev; idx < (1u << lut_bits); idx += (1u << l)) lut[idx] = (uint16_t)e;
       }
     }
@@ -324,8 +335,8 @@ __device__ __forceinline__ int parse_wrapper(const uint8_t *src, uint64_t len, i
 // sits in lane k % INF_G, slot k / INF_G, still "raw" as the symbol loop decoded it:
 //   ta = symbol (9 bits) | length extra value << 9 | second table entry << 14
 //   tb = distance extra value (13 bits) | reader position after the token << 13
-// The second table entry is the distance entry (symbol | code length << 5 | extra bits << 9)
-// after a length symbol; after a literal it is the literal/length entry of the NEXT symbol, and
+// The second table entry is the distance entry (symbol | (code + extra bits) << 11) after a
+// length symbol; after a literal it is the literal/length entry of the NEXT symbol, and
 // when that is a literal too (symbol < 256, code length != 0) the slot holds both bytes.
 // Everything that does not feed the bit position is done HERE, one lane per token instead of
 // redundantly by the whole group: base values (RFC 1951 3.2.5), the checks of inflate.nim:203,
@@ -357,7 +368,7 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
     const uint32_t lidx = min(sym - 257u, 31u);
     const uint32_t e2 = ta[r] >> 14;
     const uint32_t dsym = e2 & 31u;
-    const bool two = (e2 & 511u) < 256u && ((e2 >> 9) & 15u) != 0u;  // (only looked at for a literal)
+    const bool two = (e2 & 511u) < 256u && (e2 >> 11) != 0u;  // (only looked at for a literal)
     is_m[r] = act && sym > 256u;
     len[r] = act ? (is_m[r] ? (lds_u32(len_addr + lidx * 4u) & 0xffffu) + ((ta[r] >> 9) & 31u) : (two ? 2u : 1u)) : 0u;
     dist[r] = (lds_u32(dist_addr + dsym * 4u) & 0xffffu) + (tb[r] & 0x1fffu);
@@ -605,6 +616,7 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
     // token k of the batch: lane k % INF_G, slot k / INF_G, two registers (see flush_tokens)
     uint32_t ta[INF_ROUNDS], tb[INF_ROUNDS];
     uint32_t ntok = 0;
+    uint32_t x1 = br_peek(b);  // the 32 bits at the read position, carried from token to token
 #pragma unroll
     for (int r = 0; r < INF_ROUNDS; r++) {
       ta[r] = 0;
@@ -612,51 +624,47 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
 #pragma unroll 1
       for (int j = 0; j < INF_G; j++) {
         const uint32_t bo0 = b.bo;
-        const uint32_t x1 = br_peek(b);
-        const uint32_t e = lds_u16(ll_addr + ((x1 & ((1u << LL_BITS) - 1u)) << 1));
-        uint32_t sym = e & 511u, l = (e >> 9) & 15u, ext = e >> 13;
-        uint32_t p2 = bo0 + l + ext;  // <= 31 + 20
+        const uint32_t e = lds_u16(lut_addr(ll_addr, x1 & ((1u << LL_BITS) - 1u)));
+        uint32_t sym = e & 511u, s1 = e >> 11;  // s1: code + extra bits of this symbol
+        uint32_t p2 = bo0 + s1;                 // <= 31 + 20
         uint32_t x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
         // second lookup: the distance table after a length symbol; after a literal, the
         // literal/length table again -- two literals in a row leave as ONE token slot
         const bool lit1 = sym < 256u;
-        uint32_t e2 = lds_u16(lit1 ? ll_addr + ((x2 & ((1u << LL_BITS) - 1u)) << 1)
-                                   : d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1));
-        uint32_t l2 = (e2 >> 5) & 15u, dext = e2 >> 9;  // read as a distance entry
-        const uint32_t sym2 = e2 & 511u, l2b = dext & 15u;  // read as a literal/length entry
-        const bool pair = act && lit1 && l != 0u && l2b != 0u && sym2 < 256u;
+        uint32_t e2 = lds_u16(lut_addr(lit1 ? ll_addr : d_addr, x2 & (lit1 ? ((1u << LL_BITS) - 1u) : ((1u << D_BITS) - 1u))));
+        uint32_t s2 = e2 >> 11;  // bits of the distance (code + extra), or of the second literal
+        const bool pair = act && lit1 && s1 != 0u && s2 != 0u && (e2 & 511u) < 256u;
         bool want_d = act && (sym - 257u) < 29u;
-        uint32_t pre = 0;  // bits already consumed by the rare path below
-        if (act && (l == 0u || (want_d && (l2 == 0u || (INF_SPLIT_LONG && (p2 - bo0) + l2 + dext > 32u))))) {
-          // rare: a code longer than its lookup table (or no code at all), or a token of more
-          // than 32 bits (consumed in two steps)
-          if (l == 0u) {
+        if (act && (s1 == 0u || (want_d && s2 == 0u))) {
+          // rare: a code longer than its lookup table (or no code at all)
+          if (s1 == 0u) {
+            uint32_t l;
             sym = decode_slow(x1, gs, 0, gs->syms_ll, l);
             sym = l ? sym : 287u;  // no code: an invalid length symbol
             const uint32_t lidx = sym - 257u;
-            ext = lidx < 29u ? (lds_u32(len_addr + lidx * 4u) >> 16) : 0u;
+            s1 = l + (lidx < 29u ? (lds_u32(len_addr + lidx * 4u) >> 16) : 0u);
             want_d = lidx < 29u;
-            p2 = bo0 + l + ext;
+            p2 = bo0 + s1;
             x2 = (p2 & 32u) ? __funnelshift_r(b.w1, b.w2, p2) : __funnelshift_r(b.w0, b.w1, p2);
-            e2 = want_d ? lds_u16(d_addr + ((x2 & ((1u << D_BITS) - 1u)) << 1)) : 0u;  // 0: never a literal pair
-            l2 = (e2 >> 5) & 15u;
-            dext = e2 >> 9;
+            e2 = want_d ? lds_u16(lut_addr(d_addr, x2 & ((1u << D_BITS) - 1u))) : 0u;  // 0: never a literal pair
+            s2 = e2 >> 11;
           }
-          if (want_d && l2 == 0u) {
+          if (want_d && s2 == 0u) {
+            uint32_t l2;
             uint32_t dsym = decode_slow(x2, gs, 1, gs->syms_d, l2);
             dsym = l2 ? dsym : 31u;  // no code: an invalid distance symbol
-            dext = dsym < 30u ? (lds_u32(dist_addr + dsym * 4u) >> 16) : 0u;
-            e2 = dsym | (l2 << 5) | (dext << 9);
-          }
-          if (INF_SPLIT_LONG && want_d && (p2 - bo0) + l2 + dext > 32u) {
-            pre = p2 - bo0;
-            br_skip<false>(b, pre);
+            s2 = l2 + (dsym < 30u ? (lds_u32(dist_addr + dsym * 4u) >> 16) : 0u);
+            e2 = dsym | (s2 << 11);
           }
         }
-        const uint32_t lenx = (x1 >> l) & ~(0xffffffffu << ext);
-        const uint32_t distx = (x2 >> l2) & ~(0xffffffffu << dext);
-        const uint32_t adv = (p2 - bo0) - pre + (want_d ? l2 + dext : (pair ? l2b : 0u));
-        br_skip<true>(b, act ? adv : 0u);
+        const uint32_t adv = s1 + ((want_d || pair) ? s2 : 0u);
+        const uint32_t x1n = br_skip<true>(b, act ? adv : 0u);
+        // off the bit-position chain: the extra-bit values
+        const uint32_t ext = want_d ? (lds_u32(len_addr + (sym - 257u) * 4u) >> 16) : 0u;
+        const uint32_t dext = lds_u32(dist_addr + (e2 & 31u) * 4u) >> 16;
+        const uint32_t lenx = (x1 >> (s1 - ext)) & ~(0xffffffffu << ext);
+        const uint32_t distx = (x2 >> (s2 - dext)) & ~(0xffffffffu << dext);
+        x1 = x1n;
         const bool emit = act && sym != 256u;
         if (emit && lane == j) {
           ta[r] = sym | (lenx << 9) | (e2 << 14);
