@@ -351,6 +351,7 @@ def main():
 
     # ---- e2e: host (pinned) buffers through the host-buffer C-ABI call ----
     e2e = None
+    unc_e2e = None
     if not args.no_e2e:
         hcap = comp_bytes + (64 << 20)
         h_src = torch.empty(n * BLOCK, dtype=torch.uint8).pin_memory()
@@ -387,6 +388,33 @@ def main():
                "h2d_bytes_per_step": int(n * BLOCK), "d2h_bytes_per_step": int(out_offs[n]),
                "h2d_ms": th["h2d_ms"], "d2h_ms": th["d2h_ms"]}
         assert int(out_offs[n]) == comp_bytes
+        # the reverse direction through the host-buffer call (rank 0, 1 GPU runs only): compressed
+        # members in pinned host memory -> original bytes in pinned host memory
+        unc_e2e = None
+        if world == 1:
+            lens_b = np.zeros(n, dtype=np.uint64)
+            h_src.zero_()
+
+            def step_back():
+                rc = L.zb200_uncompress_batch(ctx._h, h_dst.data_ptr(), out_offs.ctypes.data, n, z.dfDetect,
+                                              h_src.data_ptr(), src_offsets.ctypes.data, lens_b.ctypes.data,
+                                              stat.ctypes.data)
+                assert rc == 0, rc
+
+            step_back()
+            sync_all()
+            assert not stat.any() and bool((lens_b == BLOCK).all())
+            assert torch.equal(h_src[:64 << 20], d_src[:64 << 20].cpu()), "host round trip mismatch"
+            e0.record(stream)
+            for _ in range(args.steps):
+                step_back()
+            e1.record(stream)
+            sync_all()
+            ms3 = e0.elapsed_time(e1) / args.steps
+            tb = ctx.timing()
+            unc_e2e = {"out_gibs": n * BLOCK / GIB / (ms3 / 1e3), "in_gibs": comp_bytes / GIB / (ms3 / 1e3), "ms": ms3,
+                       "h2d_bytes": comp_bytes, "d2h_bytes": int(n * BLOCK), "h2d_ms": tb["h2d_ms"], "d2h_ms": tb["d2h_ms"],
+                       "inflate_ms": tb["inflate_ms"] + tb["verify_ms"]}
         del h_src, h_dst
 
     if rank != 0:
@@ -426,7 +454,8 @@ def main():
            "ratio": comp_bytes / float(n * BLOCK), "clocks": clk, "gpu_launches": int(launches),
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
            "uncompress": {"out_gibs": n * BLOCK / GIB / (inflate_ms / 1e3), "in_gibs": comp_bytes / GIB / (inflate_ms / 1e3),
-                          "ms": inflate_ms, "note": "GPU inflate + CRC verify of this batch's own members (device-resident)"}}
+                          "ms": inflate_ms, "note": "GPU inflate + CRC verify of this batch's own members (device-resident)",
+                          "e2e": unc_e2e}}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

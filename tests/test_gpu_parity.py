@@ -329,6 +329,30 @@ def test_launch_groups_and_tight_capacity(z, o, corpus, monkeypatch):
     ctx.close()
 
 
+def test_host_uncompress_member_groups(z, o, corpus, monkeypatch):
+    """The host-buffer uncompress runs member groups through a copy-in / inflate / copy-out
+    pipeline; force tiny groups (many groups, groups of one oversized member, empty members)."""
+    monkeypatch.setenv("ZB200_UNC_GROUP_BYTES", "150000")
+    ctx = z.Context()
+    monkeypatch.delenv("ZB200_UNC_GROUP_BYTES")
+    rng = random.Random(5)
+    raws = [corpus["alice29.txt"], b"", corpus["html"], corpus["urls.10K"], b"q" * 300000, corpus["geo.protodata"],
+            bytes(rng.randrange(256) for _ in range(100000)), b"abc", corpus["lcet10.txt"], b""]
+    items = [o.compress(r, [1, -1, 6, 0][i % 4], [o.dfGzip, o.dfZlib][i % 2]) for i, r in enumerate(raws)]
+    items[3] = items[3][:-5] + bytes([items[3][-5] ^ 0x40]) + items[3][-4:]   # break one trailer
+    base = np.frombuffer(b"".join(items), dtype=np.uint8)
+    offs = np.zeros(len(items) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(x) for x in items])
+    out, do, lens, st = ctx.uncompress_batch(base, offs, z.dfDetect)
+    for i, r in enumerate(raws):
+        if i == 3:
+            assert st[i] != 0
+            continue
+        assert st[i] == 0, (i, st[i])
+        assert out[int(do[i]):int(do[i]) + int(lens[i])].tobytes() == r, i
+    ctx.close()
+
+
 def test_default_level_ratio_vs_reference(z, o, corpus):
     """BASELINE config 4: at level=Default the total compressed size on the urls.10K corpus must
     stay within 3 % of the reference's (oracle port, hash-chain level 6, deflate.nim:262-272)."""

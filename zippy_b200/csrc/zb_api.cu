@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -42,6 +43,7 @@ struct zb200_ctx {
   size_t pin_cap = 0;
   DevBuf group_end;               // device u64 per group: end offset of the group's output
   size_t dev_group_chunks = kMaxChunksPerGroup, host_group_chunks = kHostGroupChunks;
+  uint64_t unc_group_out_bytes = 0;  // host uncompress: output bytes per pipelined member group (0: a quarter of the batch)
   zb200_timing timing;
   std::string last_err;
   std::mutex mu;
@@ -408,9 +410,9 @@ int upload_pieces(zb200_ctx *ctx, const uint64_t *offs, size_t n, ZbChecksumWork
 // ---- uncompress, device-resident ----
 int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                              int data_format, uint64_t raw_pos, uint8_t *d_dst, const uint64_t *dst_offsets,
-                             uint64_t *dst_lens, int *statuses, bool count_only) {
+                             uint64_t *dst_lens, int *statuses, bool count_only,
+                             const std::function<int()> *after_launch = nullptr) {
   if (data_format < ZB200_DF_DETECT || data_format > ZB200_DF_DEFLATE) return ZB200_ERR_INVALID_FORMAT;
-  ctx->timing.inflate_ms = ctx->timing.verify_ms = 0.f;
   if (n == 0) return ZB200_OK;
   ENSURE(ctx->src_off, (n + 1) * sizeof(uint64_t));
   ENSURE(ctx->dst_off, (n + 1) * sizeof(uint64_t));
@@ -460,6 +462,10 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
     CK(zb_launch_checksum(cw, s));
   }
   CK(cudaEventRecord(ctx->ev[2], s));
+  if (after_launch) {  // work to queue behind the kernels (other streams) before this thread waits
+    int rc = (*after_launch)();
+    if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(dst_lens, ctx->out_len.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   std::vector<int> st_tmp;
   int *st = statuses;
@@ -469,8 +475,8 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
   }
   CK(cudaMemcpyAsync(st, ctx->status.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  ctx->timing.inflate_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
-  ctx->timing.verify_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+  ctx->timing.inflate_ms += ev_ms(ctx->ev[0], ctx->ev[1]);
+  ctx->timing.verify_ms += ev_ms(ctx->ev[1], ctx->ev[2]);
   ctx->timing.kernel_launches += count_only ? 1 : 3;
   for (size_t i = 0; i < n; i++)
     if (st[i] != ZB200_OK) dst_lens[i] = 0;
@@ -554,6 +560,10 @@ int zb200_init(int device, zb200_ctx **out) {
   if (const char *e = getenv("ZB200_GROUP_CHUNKS")) {  // test hook: force small launch groups
     long v = atol(e);
     if (v > 0) ctx->dev_group_chunks = ctx->host_group_chunks = (size_t)v;
+  }
+  if (const char *e = getenv("ZB200_UNC_GROUP_BYTES")) {  // test hook: small pipelined groups in the host uncompress
+    long long v = atoll(e);
+    if (v > 0) ctx->unc_group_out_bytes = (uint64_t)v;
   }
   if (const char *e = getenv("ZB200_DEV_GROUP_CHUNKS")) {  // device-resident batches only (bench.py)
     long v = atol(e);
@@ -698,6 +708,7 @@ int zb200_uncompress_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const ui
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   ctx->timing.kernel_launches = 0;
+  ctx->timing.inflate_ms = ctx->timing.verify_ms = 0.f;
   return uncompress_device_locked(ctx, d_src, src_offsets, n, data_format, 0, d_dst, dst_offsets, dst_lens, statuses,
                                   false);
 }
@@ -708,6 +719,7 @@ int zb200_uncompress_sizes_device(zb200_ctx *ctx, const uint8_t *d_src, const ui
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   ctx->timing.kernel_launches = 0;
+  ctx->timing.inflate_ms = ctx->timing.verify_ms = 0.f;
   return uncompress_device_locked(ctx, d_src, src_offsets, n, data_format, 0, nullptr, nullptr, sizes, statuses,
                                   true);
 }
@@ -732,25 +744,83 @@ int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   memset(&ctx->timing, 0, sizeof(ctx->timing));
-  std::vector<uint64_t> reb;
-  int rc = stage_in(ctx, src_base, src_offsets, n, reb);
-  if (rc) return rc;
+  if (n == 0) return ZB200_OK;
   for (size_t i = 0; i < n; i++)
-    if (dst_offsets[i + 1] < dst_offsets[i]) return ZB200_ERR_ARG;
-  uint64_t lo = n ? dst_offsets[0] : 0, hi = n ? dst_offsets[n] : 0;
-  std::vector<uint64_t> dreb(n + 1);
-  for (size_t i = 0; i <= n; i++) dreb[i] = dst_offsets[i] - lo;
+    if (src_offsets[i + 1] < src_offsets[i] || dst_offsets[i + 1] < dst_offsets[i]) return ZB200_ERR_ARG;
+  const uint64_t slo = src_offsets[0], shi = src_offsets[n], lo = dst_offsets[0], hi = dst_offsets[n];
+  std::vector<uint64_t> reb(n + 1), dreb(n + 1);
+  for (size_t i = 0; i <= n; i++) {
+    reb[i] = src_offsets[i] - slo;
+    dreb[i] = dst_offsets[i] - lo;
+  }
+  ENSURE(ctx->in_stage, (size_t)(shi - slo) + 64);
   ENSURE(ctx->out_stage, (size_t)(hi - lo) + 64);
-  rc = uncompress_device_locked(ctx, (const uint8_t *)ctx->in_stage.p, reb.data(), n, data_format, 0,
-                                (uint8_t *)ctx->out_stage.p, dreb.data(), dst_lens, statuses, false);
+  // Member groups: group g inflates while group g + 1 is copied in on the H2D stream and group
+  // g - 1 is copied out on the D2H stream.  A launch wants ~7000 members to fill the GPU, so the
+  // groups are big: a quarter of the batch, between 64 MiB and 1 GiB of output.  (The copies only
+  // run asynchronously for page-locked host buffers; with pageable memory the same code is
+  // correct but the copies block this thread.)
+  std::vector<size_t> gb(1, 0);
+  {
+    uint64_t out_cap = ctx->unc_group_out_bytes;
+    if (!out_cap) out_cap = std::min<uint64_t>(std::max<uint64_t>((hi - lo) / 4, 64ull << 20), 1ull << 30);
+    const uint64_t in_cap = out_cap;
+    size_t a = 0;
+    for (size_t i = 1; i <= n; i++)
+      if (i == n || dreb[i + 1] - dreb[a] > out_cap || reb[i + 1] - reb[a] > in_cap) {
+        gb.push_back(i);
+        a = i;
+      }
+  }
+  const size_t ng = gb.size() - 1;
+  int rc = ensure_group_events(ctx, 2 * ng + 2);
   if (rc) return rc;
-  CK(cudaEventRecord(ctx->ev[8], ctx->stream));
-  if (hi > lo && dst_base)
-    CK(cudaMemcpyAsync(dst_base + lo, ctx->out_stage.p, (size_t)(hi - lo), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[9], ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  cudaStream_t s = ctx->stream, sh = ctx->h2d_stream, sd = ctx->d2h_stream;
+  // the side streams start after whatever the caller's stream already holds
+  CK(cudaEventRecord(ctx->gev[2 * ng], s));
+  CK(cudaStreamWaitEvent(sh, ctx->gev[2 * ng], 0));
+  CK(cudaStreamWaitEvent(sd, ctx->gev[2 * ng], 0));
+  CK(cudaEventRecord(ctx->ev[6], sh));
+  CK(cudaEventRecord(ctx->ev[8], sd));
+  auto copy_in = [&](size_t gi) -> int {
+    const uint64_t b0 = reb[gb[gi]], b1 = reb[gb[gi + 1]];
+    if (b1 > b0)
+      CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + b0, src_base + slo + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sh));
+    CK(cudaEventRecord(ctx->gev[2 * gi], sh));
+    return ZB200_OK;
+  };
+  rc = copy_in(0);
+  if (rc) return rc;
+  for (size_t gi = 0; gi < ng; gi++) {
+    if (gi + 1 < ng) {
+      rc = copy_in(gi + 1);
+      if (rc) return rc;
+    }
+    CK(cudaStreamWaitEvent(s, ctx->gev[2 * gi], 0));
+    const size_t m0 = gb[gi], m1 = gb[gi + 1];
+    const std::function<int()> copy_out = [&]() -> int {
+      CK(cudaEventRecord(ctx->gev[2 * gi + 1], s));
+      CK(cudaStreamWaitEvent(sd, ctx->gev[2 * gi + 1], 0));
+      const uint64_t b0 = dreb[m0], b1 = dreb[m1];
+      if (b1 > b0 && dst_base)
+        CK(cudaMemcpyAsync(dst_base + lo + b0, (uint8_t *)ctx->out_stage.p + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, sd));
+      return ZB200_OK;
+    };
+    rc = uncompress_device_locked(ctx, (const uint8_t *)ctx->in_stage.p, reb.data() + m0, m1 - m0, data_format, 0,
+                                  (uint8_t *)ctx->out_stage.p, dreb.data() + m0, dst_lens + m0,
+                                  statuses ? statuses + m0 : nullptr, false, &copy_out);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(ctx->ev[7], sh));
+  CK(cudaEventRecord(ctx->ev[9], sd));
+  // the caller's stream ends after the last copy out
+  CK(cudaEventRecord(ctx->gev[2 * ng + 1], sd));
+  CK(cudaStreamWaitEvent(s, ctx->gev[2 * ng + 1], 0));
+  CK(cudaStreamSynchronize(sd));
+  CK(cudaStreamSynchronize(sh));
   ctx->timing.h2d_ms = ev_ms(ctx->ev[6], ctx->ev[7]);
   ctx->timing.d2h_ms = ev_ms(ctx->ev[8], ctx->ev[9]);
+  ctx->timing.h2d_bytes = shi - slo;
   ctx->timing.d2h_bytes = hi - lo;
   return ZB200_OK;
 }
