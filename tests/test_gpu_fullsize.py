@@ -1,0 +1,135 @@
+"""BASELINE.json's configurations at FULL size, checked through size-independent properties
+(SURVEY.md 8d).  Each test moves 4-12 GiB through the GPU and takes a few seconds on a B200.
+
+  C2: 65 536 x 64 KiB text blocks, level 1 gzip -- every member's trailer (CRC-32, ISIZE) equals a
+      checksum of the source computed independently by the checksum kernels ("checksum of
+      checksums"), the GPU inflater returns the source bit-exactly, a sample goes through the
+      oracle and zlib, and the total size stays within 2 % of the oracle's level 1.
+  C3: 65 536 gzip members (the reference's 23 fixtures tiled) -- the first cycle is byte-exact
+      against the fixtures' manifest, every later cycle equals the first (idempotence over the
+      tiling), all trailers verified on the device.
+  C4: urls.10K tiled to 4 GiB at the Default level -- round trip, and total size <= 1.03 x the
+      oracle's Default level (BASELINE config 4's criterion).
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+BLOCK = 65536
+
+
+@pytest.fixture(scope="module")
+def env():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import zippy_b200 as z
+    from oracle import oracle as o
+    free, _ = torch.cuda.mem_get_info()
+    if free < (40 << 30):
+        pytest.skip("needs 40 GiB of free device memory")
+    ctx = z.Context(0)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    yield torch, z, o, ctx
+    ctx.close()
+
+
+def _c2_batch(torch, n):
+    """block i = T[o : o + 64 KiB], o = splitmix64(0xC2 + i) mod (|T| - 64 KiB)."""
+    T = util.text_corpus(util.load_corpus())
+    T_d = torch.frombuffer(bytearray(T), dtype=torch.uint8).cuda()
+    offs = np.array([util._sm64(0xC2 + i) % (len(T) - BLOCK) for i in range(n)], dtype=np.int64)
+    offs_d = torch.from_numpy(offs).cuda()
+    windows = T_d.unfold(0, BLOCK, 1)
+    d_src = torch.empty(n * BLOCK, dtype=torch.uint8, device="cuda")
+    for s in range(0, n, 4096):
+        e = min(n, s + 4096)
+        d_src[s * BLOCK:e * BLOCK] = torch.index_select(windows, 0, offs_d[s:e]).reshape(-1)
+    return T, offs, d_src
+
+
+def test_c2_full_size_properties(env):
+    torch, z, o, ctx = env
+    n = 65536
+    T, offs, d_src = _c2_batch(torch, n)
+    src_offsets = np.arange(n + 1, dtype=np.uint64) * BLOCK
+    cap = n * (BLOCK + 64) + 4096
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    oo = ctx.compress_batch_device(d_src.data_ptr(), src_offsets, 1, z.dfGzip, d_dst.data_ptr(), cap)
+    assert (np.diff(oo.astype(np.int64)) > 18).all()
+    # checksum of checksums: trailers written by the compress kernels vs the checksum kernels
+    crc = ctx.checksum_batch_device(d_src.data_ptr(), src_offsets, "crc32")
+    ends = torch.from_numpy(oo[1:].astype(np.int64)).cuda()
+    tr = torch.stack([d_dst[ends - k].to(torch.int64) for k in range(8, 0, -1)], dim=1)   # last 8 bytes of each member
+    got_crc = (tr[:, 0] | (tr[:, 1] << 8) | (tr[:, 2] << 16) | (tr[:, 3] << 24)).cpu().numpy().astype(np.uint32)
+    got_isz = (tr[:, 4] | (tr[:, 5] << 8) | (tr[:, 6] << 16) | (tr[:, 7] << 24)).cpu().numpy()
+    assert (got_crc == crc).all() and (got_isz == BLOCK).all()
+    for i in (0, 1, 32767, 65535):   # the independent CPU checks on a sample
+        want = T[int(offs[i]):int(offs[i]) + BLOCK]
+        m = d_dst[int(oo[i]):int(oo[i + 1])].cpu().numpy().tobytes()
+        assert zlib.crc32(want) == int(crc[i])
+        assert o.uncompress(m) == want and zlib.decompress(m, 31) == want
+    # GPU inflate returns the source, bit-exactly, for all 65 536 members
+    d_back = torch.empty(n * BLOCK, dtype=torch.uint8, device="cuda")
+    lens, st = ctx.uncompress_batch_device(d_dst.data_ptr(), oo, z.dfDetect, d_back.data_ptr(), src_offsets)
+    assert not st.any() and (lens == BLOCK).all()
+    assert torch.equal(d_back, d_src)
+    # size: within 2 % of the oracle's level 1 on a 256-block sample of the same blocks
+    sample = [T[int(offs[i]):int(offs[i]) + BLOCK] for i in range(0, n, 256)]
+    ref = sum(len(o.compress(b, 1, o.dfGzip)) for b in sample)
+    mine = sum(int(oo[i + 1] - oo[i]) for i in range(0, n, 256))
+    assert mine <= 1.02 * ref, (mine, ref)
+
+
+def test_c3_full_size_properties(env):
+    torch, z, o, ctx = env
+    golden = util.load_golden()
+    names = sorted(k for k in golden if k.endswith(".gz"))
+    assert len(names) == 23
+    cyc = [golden[k][0] for k in names]
+    n = 65536
+    reps = (n + 22) // 23
+    d_src = torch.from_numpy(np.frombuffer(b"".join(cyc), dtype=np.uint8).copy()).cuda().repeat(reps)
+    lens = np.array([len(c) for c in cyc] * reps, dtype=np.uint64)[:n]
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    sizes, st = ctx.uncompressed_sizes_device(d_src.data_ptr(), offs, z.dfDetect)
+    assert not st.any()
+    doffs = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(sizes, out=doffs[1:])
+    d_dst = torch.empty(int(doffs[n]) + 64, dtype=torch.uint8, device="cuda")
+    out_lens, st = ctx.uncompress_batch_device(d_src.data_ptr(), offs, z.dfDetect, d_dst.data_ptr(), doffs)
+    assert not st.any() and (out_lens == sizes).all()    # CRC-32 + ISIZE of every member verified on the device
+    cyc_out = int(doffs[23])
+    host = d_dst[:cyc_out].cpu().numpy()
+    for i, k in enumerate(names):                         # byte-exact against the reference's fixtures
+        assert util.sha(host[int(doffs[i]):int(doffs[i + 1])].tobytes()) == golden[k][1]["sha256"], k
+    full = (n // 23) * 23
+    tiles = d_dst[:cyc_out * (full // 23)].view(full // 23, cyc_out)
+    assert bool((tiles == tiles[0]).all())                # every cycle equals the first
+
+
+def test_c4_full_size_properties(env):
+    torch, z, o, ctx = env
+    raw = util.load_corpus()["urls.10K"]
+    n = 6118
+    d_src = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda().repeat(n)
+    offs = np.arange(n + 1, dtype=np.uint64) * len(raw)
+    cap = n * (len(raw) + 256)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    oo = ctx.compress_batch_device(d_src.data_ptr(), offs, z.DefaultCompression, z.dfGzip, d_dst.data_ptr(), cap)
+    sizes = np.diff(oo.astype(np.int64))
+    assert (sizes == sizes[0]).all()                      # identical tiles give identical members (determinism)
+    first = d_dst[:int(oo[1])].cpu().numpy().tobytes()
+    assert o.uncompress(first) == raw and zlib.decompress(first, 31) == raw
+    ref = len(o.compress(raw, o.DefaultCompression, o.dfGzip))
+    assert int(oo[n]) <= 1.03 * ref * n, (int(oo[n]) / n, ref)
+    d_back = torch.empty(n * len(raw), dtype=torch.uint8, device="cuda")
+    lens, st = ctx.uncompress_batch_device(d_dst.data_ptr(), oo, z.dfDetect, d_back.data_ptr(), offs)
+    assert not st.any() and (lens == len(raw)).all()
+    assert torch.equal(d_back, d_src)
