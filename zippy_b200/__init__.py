@@ -119,13 +119,17 @@ class Context:
                                                   sizes.ctypes.data, st.ctypes.data))
         return sizes[:n], st[:n]
 
-    def uncompress_batch(self, base, offsets, dataFormat=dfDetect, max_total=None):
-        """-> (out uint8 array, out_offsets uint64[n+1], out_lens uint64[n], statuses int32[n])."""
+    def uncompress_batch(self, base, offsets, dataFormat=dfDetect, max_total=None, sizes=None):
+        """-> (out uint8 array, out_offsets uint64[n+1], out_lens uint64[n], statuses int32[n]).
+        `sizes`: uncompressed sizes known to the caller (a container's directory); skips the sizing pass."""
         L = _native.lib()
         base = _as_u8(base)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
-        sizes, st0 = self.uncompressed_sizes(base, offsets, dataFormat)
+        if sizes is None:
+            sizes, st0 = self.uncompressed_sizes(base, offsets, dataFormat)
+        else:
+            sizes, st0 = np.ascontiguousarray(sizes, dtype=np.uint64), np.zeros(n, dtype=np.int32)
         sizes = np.where(st0 == 0, sizes, 0).astype(np.uint64)
         # a gzip ISIZE is a claim, not a fact: DEFLATE cannot expand more than 1032:1, so a
         # larger claim can only end in a size/checksum failure -- never allocate for it.
