@@ -20,7 +20,9 @@
 #ifndef INF_G
 #define INF_G 8                       // lanes per member; 32 / INF_G members are decoded per warp
 #endif
+#ifndef INF_WARPS
 #define INF_WARPS 4
+#endif
 #define INF_THREADS (INF_WARPS * 32)
 #define INF_GROUPS (INF_THREADS / INF_G)
 #define FULL_MASK 0xffffffffu
@@ -561,7 +563,7 @@ __device__ __forceinline__ int begin_block(Grp &g, GroupSmem *gs) {
         if (i == 0) return ZB_ERR_UNCOMPRESS;
         int rep = (int)br_take(b, 2) + 3;
         if (i + rep > 320) return ZB_ERR_UNCOMPRESS;
-        if (lane < rep) gs->lens[i + lane] = (uint8_t)prev;
+        for (int j = lane; j < rep; j += INF_G) gs->lens[i + j] = (uint8_t)prev;
         i += rep;
       } else if (sym == 17) {
         int rep = (int)br_take(b, 3) + 3;
