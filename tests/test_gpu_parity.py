@@ -3,6 +3,7 @@
 and system zlib.  Mirrors tests/test.nim, test_levels.nim, test_known_bad.nim, fuzz.nim,
 stress.nim and stress2.nim of the reference.  Integer/byte work: every comparison is
 bit-exact."""
+import os
 import random
 import zlib
 
@@ -351,6 +352,70 @@ def test_host_uncompress_member_groups(z, o, corpus, monkeypatch):
         assert st[i] == 0, (i, st[i])
         assert out[int(do[i]):int(do[i]) + int(lens[i])].tobytes() == r, i
     ctx.close()
+
+
+def test_large_members_decode_as_parallel_segments(z, o, corpus, monkeypatch):
+    """a large member whose stream is a chain of independent byte-aligned pieces (this
+    library's multi-chunk members, zlib full-flush streams) is decoded as parallel segments; every
+    other large member falls back to the serial decode.  Same bytes and the same accept / reject
+    decision as the oracle in every case."""
+    monkeypatch.setenv("ZB200_BIG_MEMBER_BYTES", "20000")
+    ctx = z.Context()
+    monkeypatch.delenv("ZB200_BIG_MEMBER_BYTES")
+    T = util.text_corpus(corpus)
+    raw = T[:700000] + corpus["urls.10K"][:300000] + bytes(1000) + corpus["fireworks.jpg"]
+
+    def one(item, fmt=z.dfDetect):
+        base = np.frombuffer(item, dtype=np.uint8)
+        offs = np.array([0, len(item)], dtype=np.uint64)
+        out, do, lens, st = ctx.uncompress_batch(base, offs, fmt)
+        return (out[:int(lens[0])].tobytes() if st[0] == 0 else None), int(st[0]), ctx.timing()["kernel_launches"]
+
+    # launches per call: 3 for the ordinary path (inflate + 2 verify); the segment path adds 2 (marker
+    # search + optimistic pass) and, when the 64 KiB guess is wrong, 2 for the count pass and 1 for the
+    # placed pass.  (a) our own multi-chunk members, all three wrappers: one optimistic pass
+    for fmt in (z.dfGzip, z.dfZlib, z.dfDeflate):
+        comp = ctx.compress_batch(np.frombuffer(raw, dtype=np.uint8), np.array([0, len(raw)], dtype=np.uint64), 1, fmt)
+        blob = comp[0][:int(comp[1][1])].tobytes()
+        got, st, launches = one(blob, fmt if fmt == z.dfDeflate else z.dfDetect)
+        assert st == 0 and got == raw
+        assert launches == 5, launches
+    # (b) zlib full-flush stream (independent pieces) and (c) sync-flush stream (pieces depend on history)
+    for flush_mode, parallel in ((zlib.Z_FULL_FLUSH, True), (zlib.Z_SYNC_FLUSH, False)):
+        c = zlib.compressobj(6, zlib.DEFLATED, 31)
+        blob = b"".join(c.compress(raw[i:i + 90000]) + c.flush(flush_mode) for i in range(0, len(raw), 90000)) + c.flush()
+        got, st, launches = one(blob)
+        assert st == 0 and got == raw
+        assert launches == (8 if parallel else 7), (flush_mode, launches)   # count + placed pass, or fallback
+    # (d) a stored block whose data contains the marker bytes: a false boundary, serial fallback
+    tricky = b"\x00\x00\xff\xff" * 5000 + os.urandom(60000)
+    blob = o.compress(tricky, 0, o.dfGzip)
+    got, st, _ = one(blob)
+    assert st == 0 and got == tricky
+    # (e) corrupted large members: same decision as the oracle
+    comp = ctx.compress_batch(np.frombuffer(raw, dtype=np.uint8), np.array([0, len(raw)], dtype=np.uint64), 1, z.dfGzip)
+    good = comp[0][:int(comp[1][1])].tobytes()
+    rng = random.Random(3)
+    for _ in range(12):
+        bad = bytearray(good)
+        pos = rng.randrange(20, len(bad))
+        bad[pos] ^= 1 << rng.randrange(8)
+        got, st, _ = one(bytes(bad))
+        try:
+            want = o.uncompress(bytes(bad))
+        except o.ZippyError:
+            assert st != 0
+            continue
+        assert st == 0 and got == want
+    got, st, _ = one(good[:len(good) // 2])
+    assert st != 0
+    # (f) the single-stream seam: size query and inflate of a large raw stream
+    rawdef = ctx.deflate(raw, 1)
+    assert ctx.inflate(rawdef) == raw
+    ctx.close()
+    # (g) at the default threshold, through the module-level call
+    big = T * 8
+    assert z.uncompress(z.compress(big, 1, z.dfGzip)) == big
 
 
 def test_default_level_ratio_vs_reference(z, o, corpus):

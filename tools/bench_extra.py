@@ -94,6 +94,54 @@ def main():
                                   "hbm_peak_GB_s": peak, "frac_of_hbm_peak": gbs / peak, "value0": int(out[0])}))
         del d_src
 
+    if "big" in args.what:
+        # ONE large input -> one gzip member of 64 KiB chunks -> back, device-resident;
+        # the inflate runs as parallel segments (and, for comparison, serially on a 32 MiB slice)
+        T = util.text_corpus(util.load_corpus())
+        reps = (1 << 30) // len(T) + 1
+        d_src = torch.frombuffer(bytearray(T), dtype=torch.uint8).to(dev).repeat(reps)[:1 << 30].contiguous()
+        n_bytes = d_src.numel()
+        offs = np.array([0, n_bytes], dtype=np.uint64)
+        cap = n_bytes + n_bytes // 8 + (1 << 20)
+        d_dst = torch.empty(cap, dtype=torch.uint8, device=dev)
+        d_back = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            oo = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfGzip, d_dst.data_ptr(), cap)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        oo = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfGzip, d_dst.data_ptr(), cap)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        c_ms = e0.elapsed_time(e1)
+        for _ in range(2):
+            lens, st = ctx.uncompress_batch_device(d_dst.data_ptr(), oo, z.dfDetect, d_back.data_ptr(), offs)
+        assert not st.any() and int(lens[0]) == n_bytes and torch.equal(d_back, d_src)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        ctx.uncompress_batch_device(d_dst.data_ptr(), oo, z.dfDetect, d_back.data_ptr(), offs)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        u_ms = e0.elapsed_time(e1)
+        launches = ctx.timing()["kernel_launches"]
+        os.environ["ZB200_BIG_MEMBER_BYTES"] = str(1 << 62)
+        ctx2 = z.Context(0)
+        del os.environ["ZB200_BIG_MEMBER_BYTES"]
+        small = 32 << 20
+        o2 = ctx2.compress_batch_device(d_src.data_ptr(), np.array([0, small], dtype=np.uint64), 1, z.dfGzip, d_dst.data_ptr(), cap)
+        import time
+        t0 = time.time()
+        lens, st = ctx2.uncompress_batch_device(d_dst.data_ptr(), o2, z.dfDetect, d_back.data_ptr(), np.array([0, small], dtype=np.uint64))
+        torch.cuda.synchronize()
+        ser = time.time() - t0
+        assert not st.any() and torch.equal(d_back[:small], d_src[:small])
+        print(json.dumps({"workload": "one 1 GiB input as a single gzip member (level 1), device-resident",
+                          "compress_ms": c_ms, "compress_gibs": n_bytes / GIB / (c_ms / 1e3), "member_bytes": int(oo[1]),
+                          "uncompress_ms": u_ms, "uncompress_out_gibs": n_bytes / GIB / (u_ms / 1e3),
+                          "uncompress_kernel_launches": int(launches),
+                          "serial_decode_32MiB_s": ser, "serial_out_gibs": small / GIB / ser}))
+        ctx2.close()
+        del d_src, d_dst, d_back
+
     if "c4" in args.what:
         raw = util.load_corpus()["urls.10K"]
         n = args.tiles

@@ -36,6 +36,8 @@ struct zb200_ctx {
   DevBuf desc, member_first, fname, masks, recs, hist, chk, cb, chunk_off, member_off, member_check, member_isize;
   DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out, ck_pieces, ck_first, ck_piece_out;
   DevBuf in_stage, out_stage, lz2_tables;
+  DevBuf seg_src, seg_dst, seg_len, seg_status, seg_kind, seg_expect, seg_cand, skip_mask;  // large-member segments
+  uint64_t big_member_bytes = 512ull << 10;  // members at least this long are tried as parallel segments
   cudaEvent_t ev[10];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> gev;   // per-group events (H2D done, compute done, offsets ready)
@@ -407,6 +409,206 @@ int upload_pieces(zb200_ctx *ctx, const uint64_t *offs, size_t n, ZbChecksumWork
   return ZB200_OK;
 }
 
+
+// ---- large members as parallel segments ----
+// A DEFLATE stream is serial, and one member is decoded by one 8-lane group: a single multi-MiB
+// member would crawl.  But this library's own multi-chunk members (and zlib's Z_FULL_FLUSH /
+// pigz -i streams) are chains of INDEPENDENT, byte-aligned pieces, each ending with the empty
+// stored block 00 00 ff ff.  So a large member is handled speculatively: find every 00 00 ff ff
+// in its payload, decode the pieces between them as separate raw-deflate segments (a count pass
+// for the sizes, then the real pass at the prefix-summed positions), and accept the result only
+// if every segment decodes cleanly, only the last one holds the final block, and the sizes add up
+// inside the member's capacity.  Anything else (a false 00 00 ff ff inside data, a back-reference
+// across a boundary, a corrupt stream) leaves the member to the ordinary serial decode, which
+// also produces the reference's error for it.  The trailer check runs on the output either way.
+struct HostWrapper {
+  int fmt;
+  uint64_t pos, end;  // payload [pos, end) inside the member
+  uint32_t expect, isize;
+};
+
+// zippy.nim:100-165 + gzip.nim:3-66 on the first hn bytes / last 8 bytes of a member; false when
+// the member is not acceptable or the header does not fit in hn (then the serial path decides).
+bool host_parse_wrapper(const uint8_t *h, size_t hn, const uint8_t *t8, uint64_t len, int fmt, uint64_t raw_pos,
+                        HostWrapper &w) {
+  auto le32 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+  if (fmt == ZB200_DF_DETECT) {
+    if (len > 18 && hn >= 4 && h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 0xe0) == 0) fmt = ZB200_DF_GZIP;
+    else if (len > 6 && hn >= 2 && (h[0] & 0x0f) == 8 && (h[0] >> 4) <= 7 && (((uint32_t)h[0] * 256u) + h[1]) % 31u == 0)
+      fmt = ZB200_DF_ZLIB;
+    else return false;
+  }
+  w.fmt = fmt;
+  w.expect = w.isize = 0;
+  if (fmt == ZB200_DF_GZIP) {
+    if (len < 18 || hn < 10) return false;
+    uint32_t flg = h[3];
+    if (h[0] != 31 || h[1] != 139 || h[2] != 8 || (flg & 0xe0) || (flg & 4)) return false;
+    uint64_t p = 10;
+    for (int pass = 0; pass < 2; pass++)
+      if ((pass == 0 && (flg & 8)) || (pass == 1 && (flg & 16))) {
+        while (p < hn && h[p] != 0) p++;
+        if (p >= hn) return false;
+        p++;
+      }
+    if (flg & 2) p += 2;
+    if (p + 8 >= len) return false;
+    w.pos = p;
+    w.end = len - 8;
+    w.expect = le32(t8);
+    w.isize = le32(t8 + 4);
+    return true;
+  }
+  if (fmt == ZB200_DF_ZLIB) {
+    if (len < 6 || hn < 2) return false;
+    uint32_t cmf = h[0], flg = h[1];
+    if ((cmf & 0x0f) != 8 || (cmf >> 4) > 7 || (cmf * 256u + flg) % 31u != 0 || (flg & 0x20)) return false;
+    w.pos = 2;
+    w.end = len - 4;
+    w.expect = ((uint32_t)t8[4] << 24) | ((uint32_t)t8[5] << 16) | ((uint32_t)t8[6] << 8) | t8[7];
+    return true;
+  }
+  if (fmt == ZB200_DF_DEFLATE) {
+    if (raw_pos > len) return false;
+    w.pos = raw_pos;
+    w.end = len;
+    return true;
+  }
+  return false;
+}
+
+struct BigResult {
+  size_t member;
+  uint64_t out_len;
+  uint32_t kind, expect;
+};
+
+// Tries every large member; `done` gets the members that were fully decoded here (their output
+// is in place; status / length / kind / expect still have to be written to the device arrays).
+int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n, int data_format,
+                        uint64_t raw_pos, uint8_t *d_dst, const uint64_t *dst_offsets, bool count_only,
+                        std::vector<BigResult> &done) {
+  cudaStream_t s = ctx->stream;
+  for (size_t m = 0; m < n; m++) {
+    const uint64_t m0 = src_offsets[m], len = src_offsets[m + 1] - m0;
+    if (len < ctx->big_member_bytes) continue;
+    uint8_t head[1024], tail[8];
+    const size_t hn = (size_t)std::min<uint64_t>(len, sizeof(head));
+    CK(cudaMemcpyAsync(head, d_src + m0, hn, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(tail, d_src + m0 + len - 8, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    HostWrapper hw;
+    if (!host_parse_wrapper(head, hn, tail, len, data_format, raw_pos, hw)) continue;
+    if (count_only && hw.fmt == ZB200_DF_GZIP) continue;  // ISIZE answers that (gzip.nim:66)
+    if (hw.end <= hw.pos + 4) continue;
+    // 1. candidate boundaries
+    const uint32_t cap = (uint32_t)std::min<uint64_t>((hw.end - hw.pos) / 32 + 64, 1u << 26);
+    ENSURE(ctx->seg_cand, (size_t)cap * 8 + 16);
+    ENSURE(ctx->counter, 64);
+    uint32_t *d_cnt = (uint32_t *)ctx->counter.p + 8;
+    CK(zb_launch_find_sync(d_src + m0, hw.pos, hw.end, (uint64_t *)ctx->seg_cand.p, cap, d_cnt, s));
+    uint32_t cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (cnt == 0 || cnt > cap) continue;
+    std::vector<uint64_t> bounds(cnt + 2);
+    CK(cudaMemcpyAsync(bounds.data() + 1, ctx->seg_cand.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::sort(bounds.begin() + 1, bounds.begin() + 1 + cnt);
+    bounds[0] = hw.pos;
+    size_t S = cnt + 1;
+    if (bounds[cnt] >= hw.end) S = cnt;  // the payload ends with a marker: no trailing segment
+    else bounds[cnt + 1] = hw.end;
+    if (S < 2) continue;
+    for (size_t j = 0; j <= S; j++) bounds[j] += m0;  // absolute in d_src
+    ENSURE(ctx->seg_src, (S + 1) * 8);
+    ENSURE(ctx->seg_dst, (S + 1) * 8);
+    ENSURE(ctx->seg_len, S * 8);
+    ENSURE(ctx->seg_status, S * 4);
+    ENSURE(ctx->seg_kind, S * 4);
+    ENSURE(ctx->seg_expect, S * 4);
+    CK(cudaMemcpyAsync(ctx->seg_src.p, bounds.data(), (S + 1) * 8, cudaMemcpyHostToDevice, s));
+    ZbInflateWork w;
+    memset(&w, 0, sizeof(w));
+    w.src = d_src;
+    w.src_off = (const uint64_t *)ctx->seg_src.p;
+    w.dst = d_dst;
+    w.dst_off = (const uint64_t *)ctx->seg_dst.p;
+    w.out_len = (uint64_t *)ctx->seg_len.p;
+    w.status = (int *)ctx->seg_status.p;
+    w.expect = (uint32_t *)ctx->seg_expect.p;
+    w.kind = (uint32_t *)ctx->seg_kind.p;
+    w.counter = (uint32_t *)ctx->counter.p + 4;
+    w.tabs = ctx->d_tabs;
+    w.n = (uint32_t)S;
+    w.data_format = ZB200_DF_DEFLATE;
+    w.pos = 0;
+    w.seg_mode = 1;
+    std::vector<uint64_t> sl(S), dof(S + 1);
+    std::vector<int> sst(S);
+    std::vector<uint32_t> sk(S);
+    auto fetch = [&]() -> int {
+      CK(cudaMemcpyAsync(sl.data(), ctx->seg_len.p, S * 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(sst.data(), ctx->seg_status.p, S * 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(sk.data(), ctx->seg_kind.p, S * 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      return ZB200_OK;
+    };
+    const uint64_t dst0 = count_only ? 0 : dst_offsets[m], mcap = count_only ? ~0ull : dst_offsets[m + 1] - dst_offsets[m];
+    bool ok = false;
+    int rc;
+    // 2. the optimistic pass: this library's own members have 64 KiB of output per segment (the
+    // last one takes what is left); if every segment agrees, one pass was enough
+    if (!count_only && (S - 1) * (uint64_t)ZB_CHUNK_BYTES < mcap) {
+      for (size_t j = 0; j < S; j++) dof[j] = dst0 + j * (uint64_t)ZB_CHUNK_BYTES;
+      dof[S] = dst0 + mcap;
+      CK(cudaMemcpyAsync(ctx->seg_dst.p, dof.data(), (S + 1) * 8, cudaMemcpyHostToDevice, s));
+      w.count_only = 0;
+      CK(zb_launch_inflate(w, s));
+      rc = fetch();
+      if (rc) return rc;
+      ctx->timing.kernel_launches += 2;
+      ok = true;
+      for (size_t j = 0; j < S && ok; j++)
+        ok = sst[j] == ZB200_OK && (sk[j] != 0) == (j + 1 == S) && (j + 1 == S || sl[j] == (uint64_t)ZB_CHUNK_BYTES);
+      if (ok) dof[S] = dof[S - 1] + sl[S - 1];
+    }
+    if (!ok) {
+      // 3. sizes from a count pass, then the real pass with every segment at its place
+      w.count_only = 1;
+      CK(zb_launch_inflate(w, s));
+      rc = fetch();
+      if (rc) return rc;
+      ctx->timing.kernel_launches += 2;
+      ok = true;
+      dof[0] = dst0;
+      for (size_t j = 0; j < S && ok; j++) {
+        ok = sst[j] == ZB200_OK && (sk[j] != 0) == (j + 1 == S);
+        dof[j + 1] = dof[j] + sl[j];
+      }
+      if (!ok || dof[S] - dst0 > mcap || dof[S] - dst0 > 0xfffffdffull) continue;
+      if (!count_only) {
+        std::vector<uint64_t> want = sl;
+        CK(cudaMemcpyAsync(ctx->seg_dst.p, dof.data(), (S + 1) * 8, cudaMemcpyHostToDevice, s));
+        w.count_only = 0;
+        CK(zb_launch_inflate(w, s));
+        rc = fetch();
+        if (rc) return rc;
+        ctx->timing.kernel_launches += 1;
+        for (size_t j = 0; j < S && ok; j++) ok = sst[j] == ZB200_OK && sl[j] == want[j];
+        if (!ok) continue;
+      }
+    }
+    BigResult r;
+    r.member = m;
+    r.out_len = dof[S] - dst0;
+    r.kind = (uint32_t)hw.fmt;
+    r.expect = hw.expect;
+    done.push_back(r);
+  }
+  return ZB200_OK;
+}
+
 // ---- uncompress, device-resident ----
 int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                              int data_format, uint64_t raw_pos, uint8_t *d_dst, const uint64_t *dst_offsets,
@@ -440,6 +642,8 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
   w.data_format = data_format;
   w.pos = raw_pos;
   w.count_only = count_only ? 1 : 0;
+  w.skip = nullptr;
+  w.seg_mode = 0;
   ZbChecksumWork cw;
   memset(&cw, 0, sizeof(cw));
   if (!count_only) {  // piece table for the verification pass, uploaded before anything is launched
@@ -447,6 +651,29 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
     if (rc) return rc;
   }
   CK(cudaEventRecord(ctx->ev[0], s));
+  // large members first, as parallel segments where their streams allow it; the rest (and every
+  // large member that did not work out) goes through the ordinary launch below
+  std::vector<BigResult> big;
+  std::vector<uint8_t> skip_host;
+  {
+    int rc = inflate_big_members(ctx, d_src, src_offsets, n, data_format, raw_pos, d_dst, dst_offsets, count_only, big);
+    if (rc) return rc;
+    if (!big.empty()) {
+      skip_host.assign(n, 0);
+      ENSURE(ctx->skip_mask, n);
+      for (const BigResult &r : big) {
+        skip_host[r.member] = 1;
+        const int ok = ZB200_OK;
+        CK(cudaMemcpyAsync((int *)ctx->status.p + r.member, &ok, 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync((uint64_t *)ctx->out_len.p + r.member, &r.out_len, 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync((uint32_t *)ctx->kind.p + r.member, &r.kind, 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync((uint32_t *)ctx->expect.p + r.member, &r.expect, 4, cudaMemcpyHostToDevice, s));
+      }
+      CK(cudaMemcpyAsync(ctx->skip_mask.p, skip_host.data(), n, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+      w.skip = (const uint8_t *)ctx->skip_mask.p;
+    }
+  }
   CK(zb_launch_inflate(w, s));
   CK(cudaEventRecord(ctx->ev[1], s));
   if (!count_only) {
@@ -560,6 +787,10 @@ int zb200_init(int device, zb200_ctx **out) {
   if (const char *e = getenv("ZB200_GROUP_CHUNKS")) {  // test hook: force small launch groups
     long v = atol(e);
     if (v > 0) ctx->dev_group_chunks = ctx->host_group_chunks = (size_t)v;
+  }
+  if (const char *e = getenv("ZB200_BIG_MEMBER_BYTES")) {  // test hook: segment path for small members too
+    long long v = atoll(e);
+    if (v > 0) ctx->big_member_bytes = (uint64_t)v;
   }
   if (const char *e = getenv("ZB200_UNC_GROUP_BYTES")) {  // test hook: small pipelined groups in the host uncompress
     long long v = atoll(e);

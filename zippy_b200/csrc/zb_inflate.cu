@@ -737,6 +737,8 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
       i = g_shfl(i, 0);
       if (i >= w.n) {
         g.st = ST_EXIT;
+      } else if (w.skip && w.skip[i]) {
+        // handled elsewhere (a large member decoded as parallel segments): fetch the next one
       } else {
         const uint64_t s0 = w.src_off[i], s1 = w.src_off[i + 1];
         g.idx = i;
@@ -772,6 +774,9 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
           g.st = ST_BLOCK;
         }
       }
+    } else if (g.st == ST_BLOCK && w.seg_mode && br_consumed_abs(g.b) == g.b.end_bit) {
+      fin = true;  // the segment's input is used up at a block boundary
+      done = ZB_OK;
     } else if (g.st == ST_BLOCK) {
       int r = begin_block<COUNT_ONLY>(g, gs);
       if (r >= 0) {
@@ -788,7 +793,7 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
       if (lane == 0) {
         w.status[g.idx] = done;
         w.out_len[g.idx] = done == ZB_OK ? (uint64_t)g.op : 0ull;
-        w.kind[g.idx] = g.kind;
+        w.kind[g.idx] = w.seg_mode ? (uint32_t)g.final_block : g.kind;
         w.expect[g.idx] = g.expect;
       }
       g.st = ST_FETCH;
@@ -810,7 +815,7 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
         if (lane == 0) {
           w.status[g.idx] = st;
           w.out_len[g.idx] = st == ZB_OK ? (uint64_t)g.op : 0ull;
-          w.kind[g.idx] = g.kind;
+          w.kind[g.idx] = w.seg_mode ? (uint32_t)g.final_block : g.kind;
           w.expect[g.idx] = g.expect;
         }
         g.st = ST_FETCH;
@@ -1008,6 +1013,29 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------------
+// Candidate segment boundaries of a large member (see zb_kernels.h).
+__global__ void __launch_bounds__(256) k_find_sync(const uint8_t *src, uint64_t lo, uint64_t hi, uint64_t *out, uint32_t cap,
+                                                   uint32_t *count) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p + 4 <= hi; p += stride) {
+    if (src[p + 2] == 0xffu && src[p + 3] == 0xffu && src[p] == 0u && src[p + 1] == 0u) {
+      const uint32_t k = atomicAdd(count, 1u);
+      if (k < cap) out[k] = p + 4;
+    }
+  }
+}
+
+cudaError_t zb_launch_find_sync(const uint8_t *src, uint64_t lo, uint64_t hi, uint64_t *out, uint32_t cap,
+                                uint32_t *count, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  if (hi < lo + 4) return cudaSuccess;
+  uint64_t blocks = (hi - lo + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_find_sync<<<(uint32_t)blocks, 256, 0, s>>>(src, lo, hi, out, cap, count);
+  return cudaGetLastError();
+}
+
 cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s) {
   if (w.n == 0) return cudaSuccess;
   const int smem = (int)(INF_GROUPS * sizeof(GroupSmem)) + 256;

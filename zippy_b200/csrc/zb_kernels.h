@@ -70,8 +70,17 @@ struct ZbInflateWork {
   int data_format;             // requested (may be ZB_DF_DETECT)
   uint64_t pos;                // payload start for raw ZB_DF_DEFLATE members (zb200_inflate's `pos`)
   int count_only;
+  const uint8_t *skip;         // device [n] or null: members with skip[i] != 0 are left alone
+  int seg_mode;                // members are independently decodable SEGMENTS of one raw deflate stream:
+                               // a segment also ends, successfully, when its input is used up at a block
+                               // boundary; kind[i] reports whether a final block was seen
 };
 cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s);
+// positions just past every byte sequence 00 00 ff ff (the empty stored block that byte-aligns a
+// stream: zlib's sync / full flush, and the joint between this library's 64 KiB chunks) inside
+// src[lo, hi): unordered, *count may exceed cap (then the list is incomplete)
+cudaError_t zb_launch_find_sync(const uint8_t *src, uint64_t lo, uint64_t hi, uint64_t *out, uint32_t cap,
+                                uint32_t *count, cudaStream_t s);
 
 // ---- checksums over a batch of buffers (standalone crc32/adler32, and the trailer
 // verification after inflate) ----
