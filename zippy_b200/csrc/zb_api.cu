@@ -489,9 +489,19 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
                         uint64_t raw_pos, uint8_t *d_dst, const uint64_t *dst_offsets, bool count_only,
                         std::vector<BigResult> &done) {
   cudaStream_t s = ctx->stream;
+  // Every large member costs a few host round trips here, while a batch of thousands of members
+  // already fills the GPU with one group per member: with many large members only the huge ones
+  // (minutes of serial decode) take this path.
+  uint64_t min_len = ctx->big_member_bytes;
+  {
+    size_t count = 0;
+    for (size_t m = 0; m < n; m++) count += (src_offsets[m + 1] - src_offsets[m]) >= min_len;
+    if (count == 0) return ZB200_OK;
+    if (count > 256) min_len = std::max<uint64_t>(min_len, 64ull << 20);
+  }
   for (size_t m = 0; m < n; m++) {
     const uint64_t m0 = src_offsets[m], len = src_offsets[m + 1] - m0;
-    if (len < ctx->big_member_bytes) continue;
+    if (len < min_len) continue;
     uint8_t head[1024], tail[8];
     const size_t hn = (size_t)std::min<uint64_t>(len, sizeof(head));
     CK(cudaMemcpyAsync(head, d_src + m0, hn, cudaMemcpyDeviceToHost, s));
