@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--members", type=int, default=65536)
     ap.add_argument("--tiles", type=int, default=6118)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--c5-blocks", type=int, default=131072, help="blocks of this GPU's shard of config 5 (1048576 / 8)")
+    ap.add_argument("--c5-first", type=int, default=0, help="global index of the shard's first block")
     args = ap.parse_args()
     import torch
     import zippy_b200 as z
@@ -93,6 +95,72 @@ def main():
                 print(json.dumps({"workload": "checksum %s, %s" % (kind, label), "ms": ms, "GB_s": gbs,
                                   "hbm_peak_GB_s": peak, "frac_of_hbm_peak": gbs / peak, "value0": int(out[0])}))
         del d_src
+
+    if "c5" in args.what:
+        # BASELINE config 5, one GPU's shard: 131072 x 64 KiB blocks of mixed entropy (SURVEY 8d:
+        # class = sm64(0xC5 + i) mod 8: 0-3 text, 4 urls.10K window, 5 html window, 6 random bytes,
+        # 7 run-length blob), level 1 gzip, then the GPU inflates everything back.
+        corpus = util.load_corpus()
+        T = util.text_corpus(corpus)
+        nb = args.c5_blocks
+        first = args.c5_first
+        cls = np.array([util._sm64(0xC5 + first + i) % 8 for i in range(nb)], dtype=np.int64)
+        d_src = torch.empty(nb * 65536, dtype=torch.uint8, device=dev)
+        view = d_src.view(nb, 65536)
+        for name, sel in (("text", cls < 4), ("urls", cls == 4), ("html", cls == 5)):
+            raw = T if name == "text" else corpus["urls.10K" if name == "urls" else "html"]
+            idx = np.nonzero(sel)[0]
+            if not len(idx):
+                continue
+            offs_b = np.array([(util._sm64(0xC5C5 + first + int(i)) >> 3) % (len(raw) - 65536) for i in idx], dtype=np.int64)
+            win = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev).unfold(0, 65536, 1)
+            for s0 in range(0, len(idx), 4096):
+                rows = torch.index_select(win, 0, torch.from_numpy(offs_b[s0:s0 + 4096]).to(dev))
+                view[torch.from_numpy(idx[s0:s0 + 4096]).to(dev)] = rows
+        g = torch.Generator(device=dev)
+        g.manual_seed(0xC5 + first)
+        idx = torch.from_numpy(np.nonzero(cls == 6)[0]).to(dev)
+        view[idx] = torch.randint(0, 256, (len(idx), 65536), dtype=torch.uint8, device=dev, generator=g)
+        idx = torch.from_numpy(np.nonzero(cls == 7)[0]).to(dev)
+        need = len(idx) * 65536
+        runs = torch.randint(1, 256, (need // 100 + 1024,), device=dev, generator=g)
+        vals = torch.randint(0, 256, (len(runs),), dtype=torch.uint8, device=dev, generator=g)
+        blob = torch.repeat_interleave(vals, runs)[:need]
+        assert blob.numel() == need
+        view[idx] = blob.view(len(idx), 65536)
+        offs = np.arange(nb + 1, dtype=np.uint64) * 65536
+        cap = nb * (65536 + 96) + 4096
+        d_dst = torch.empty(cap, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            oo = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfGzip, d_dst.data_ptr(), cap)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            oo = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfGzip, d_dst.data_ptr(), cap)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        c_ms = e0.elapsed_time(e1) / args.steps
+        sizes = np.diff(oo.astype(np.int64))
+        per_class = {int(k): float(sizes[cls == k].sum()) / (float((cls == k).sum()) * 65536.0) for k in range(8) if (cls == k).any()}
+        d_back = torch.empty(nb * 65536, dtype=torch.uint8, device=dev)
+        lens, st = ctx.uncompress_batch_device(d_dst.data_ptr(), oo, z.dfDetect, d_back.data_ptr(), offs)
+        assert not st.any() and (lens == 65536).all() and torch.equal(d_back, d_src)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        ctx.uncompress_batch_device(d_dst.data_ptr(), oo, z.dfDetect, d_back.data_ptr(), offs)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        u_ms = e0.elapsed_time(e1)
+        for i in (int(np.nonzero(cls == k)[0][0]) for k in range(8) if (cls == k).any()):   # one block per class through the oracle
+            m = d_dst[int(oo[i]):int(oo[i + 1])].cpu().numpy().tobytes()
+            assert o.uncompress(m) == d_src[i * 65536:(i + 1) * 65536].cpu().numpy().tobytes()
+        print(json.dumps({"workload": "C5 shard: %d x 64 KiB mixed-entropy blocks (first block %d), level 1 gzip" % (nb, first),
+                          "in_bytes": nb * 65536, "out_bytes": int(oo[nb]), "compress_ms": c_ms,
+                          "compress_in_gibs": nb * 65536 / GIB / (c_ms / 1e3), "ratio": int(oo[nb]) / float(nb * 65536),
+                          "ratio_by_class": per_class, "uncompress_ms": u_ms,
+                          "uncompress_out_gibs": nb * 65536 / GIB / (u_ms / 1e3),
+                          "parity": "GPU round trip bit-exact over the shard; one block per class through the oracle"}))
+        del d_src, d_dst, d_back
 
     if "big" in args.what:
         # ONE large input -> one gzip member of 64 KiB chunks -> back, device-resident;
