@@ -115,9 +115,9 @@ __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32
     uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, a = 0;
     uint64_t b = 0;
     const uint32_t o = off + 4u * (uint32_t)lane, rel0 = 4u * (uint32_t)lane;
-#pragma unroll 2
     constexpr uint32_t QR = ZB_SUB_BYTES / 512;  // rows of 128 B per quarter
     constexpr uint32_t QB = ZB_SUB_BYTES / 4;    // bytes per quarter
+#pragma unroll 2
     for (uint32_t k = 0; k < QR; k++) {
       const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (QR + k));
       const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (2u * QR + k)), w3 = zb_ld32_unaligned(base, o + 128u * (3u * QR + k));

@@ -1,5 +1,5 @@
-// zb_inflate.cu -- batched inflate for sm_100a: one compressed member per warp,
-// members pulled from a device work queue.
+// zb_inflate.cu -- batched inflate for sm_100a: 8 lanes per compressed member, 4 members per
+// warp decoded in lockstep, members pulled from a device work queue.
 //
 // Follows the behaviour (not the code) of the reference decoder:
 //   format detect + wrappers : src/zippy.nim:100-165, src/zippy/gzip.nim:3-88
@@ -9,11 +9,14 @@
 //   canonical decode         : inflate.nim:24-102 (same accept/reject set: over-subscribed
 //                              length sets are rejected, incomplete ones accepted, an
 //                              undecodable code is an error)
-// B200 formulation: the bit window lives in registers across the warp (two 128-byte
-// lines, one word per lane, refilled by coalesced loads and read with shuffles); the
-// canonical decode is lane-parallel (lane L tests the L-bit prefix; a ballot picks the
-// code length), so the only per-warp shared memory is the sorted-symbol table; LZ
-// back-copies are done by all 32 lanes reading the already-written output.
+// B200 formulation (profiles/r1_v4_summary.md): a DEFLATE stream is one long
+// dependency chain, so the kernel is built around (a) keeping that chain short -- a register bit
+// window per member, table entries that carry the number of bits a token occupies, two literals
+// per slot -- (b) making every warp instruction advance four members at once (a predicated
+// token loop that all groups of a warp run together) and (c) doing everything that is not on
+// the chain lane-parallel afterwards (32 raw tokens per member are validated, placed by a prefix
+// sum and copied one lane per token).  Large members are split at sync markers into segments
+// that run through the same kernel in parallel (zb_api.cu: inflate_big_members).
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 
@@ -40,7 +43,6 @@ __device__ __forceinline__ int g_lane() { return (int)(threadIdx.x & (INF_G - 1)
 __device__ __forceinline__ uint32_t g_shift() { return threadIdx.x & 31u & ~(uint32_t)(INF_G - 1); }
 __device__ __forceinline__ uint32_t g_mask() { return (INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u)) << g_shift(); }
 __device__ __forceinline__ uint32_t g_shfl(uint32_t v, int idx) { return __shfl_sync(g_mask(), v, idx, INF_G); }
-__device__ __forceinline__ uint32_t g_shfl_up(uint32_t v, int d) { return __shfl_up_sync(g_mask(), v, d, INF_G); }
 __device__ __forceinline__ uint32_t g_ballot(bool p) {
   return (__ballot_sync(g_mask(), p) >> g_shift()) & (INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u));
 }
