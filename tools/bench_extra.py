@@ -85,9 +85,11 @@ def main():
         for label, offs in (("%d x 64 KiB" % n, np.arange(n + 1, dtype=np.uint64) * 65536),
                             ("1 x %d MiB" % (n // 16), np.array([0, n * 65536], dtype=np.uint64))):
             for kind in ("crc32", "adler32"):
-                for _ in range(2):
+                times = []
+                for _ in range(5):   # the first calls also pay for the piece table upload and cold TLBs
                     out = ctx.checksum_batch_device(d_src.data_ptr(), offs, kind)
-                ms = ctx.timing()["checksum_ms"]
+                    times.append(ctx.timing()["checksum_ms"])
+                ms = float(np.median(times[2:]))
                 h = d_src[:65536].cpu().numpy().tobytes() if len(offs) > 2 else None
                 if h is not None:
                     assert int(out[0]) == (zlib.crc32(h) if kind == "crc32" else zlib.adler32(h))
