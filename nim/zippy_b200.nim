@@ -99,3 +99,30 @@ proc compress*(src: string, level = DefaultCompression, dataFormat = dfGzip): st
 
 # uncompress*: zippy.nim:100-165 and gzip.nim:3-88 carry over verbatim with `inflate`,
 # `crc32`, `adler32` bound as above (header checks and trailer verification stay host-side).
+
+# ---- batch (no counterpart in zippy.nim; what ziparchives.nim:505-540 should call instead of a
+# per-entry loop of crc32 + compress): N independent inputs, one GPU launch sequence ----
+proc zb200_compress_bound(len: csize_t, dataFormat: cint): csize_t {.importc, cdecl, dynlib: lib.}
+proc zb200_compress_batch(ctx: Zb200Ctx, srcBase: pointer, srcOffsets: ptr uint64, n: csize_t,
+                          level, dataFormat: cint, fnameLens: pointer,
+                          dstBase: pointer, dstCap: csize_t, dstOffsets: ptr uint64,
+                          statuses: ptr cint): cint {.importc, cdecl, dynlib: lib.}
+
+proc compressBatch*(items: openArray[string], level = DefaultCompression,
+                    dataFormat = dfGzip): seq[string] {.raises: [ZippyError].} =
+  var
+    base: string
+    offs = newSeq[uint64](items.len + 1)
+    outOffs = newSeq[uint64](items.len + 1)
+    bound = 64
+  for i, item in items:
+    base.add item
+    offs[i + 1] = base.len.uint64
+    bound += zb200_compress_bound(item.len.csize_t, dataFormat.cint).int + 64
+  var dst = newString(bound)
+  if base.len == 0: base.add '\0'
+  check zb200_compress_batch(getCtx(), base[0].addr, offs[0].addr, items.len.csize_t,
+                             level.cint, dataFormat.cint, nil, dst[0].addr, dst.len.csize_t,
+                             outOffs[0].addr, nil)
+  for i in 0 ..< items.len:
+    result.add dst[outOffs[i].int ..< outOffs[i + 1].int]
