@@ -219,9 +219,6 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
     m0 = m1;
   }
   const size_t ng = groups.size(), nc_all = desc.size(), nfirst = first.size();
-  uint64_t bound_total = 0;
-  for (auto &g : groups) bound_total += g.bound;
-  const bool known_fit = bound_total <= dst_cap;
 
   ENSURE(ctx->desc, nc_all * sizeof(ZbChunkDesc));
   ENSURE(ctx->member_first, nfirst * sizeof(uint32_t));
@@ -252,7 +249,6 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   if (fname_lens && data_format == ZB200_DF_GZIP)
     CK(cudaMemcpyAsync(ctx->fname.p, fname_lens, n, cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(ctx->group_end.p, 0, sizeof(uint64_t), s));
-  if (known_fit) CK(cudaMemsetAsync(d_dst, 0, (size_t)bound_total, s));  // the packer ORs bits into zeros
   if (h_src || h_dst) {
     // the transfer streams must not run ahead of the setup above
     CK(cudaEventRecord(ctx->gev[3 * ng], s));
@@ -265,6 +261,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
     ZbCompressWork w;
     w.src = d_src;
     w.dst = d_dst;
+    w.dst_cap = dst_cap;
     w.desc = (const ZbChunkDesc *)ctx->desc.p + g.c0;
     w.member_first = (const uint32_t *)ctx->member_first.p + g.first0;
     w.fname_len = (fname_lens && data_format == ZB200_DF_GZIP) ? (const uint8_t *)ctx->fname.p + g.m0 : nullptr;
@@ -289,7 +286,6 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   };
 
   // ---- enqueue every group ----
-  size_t zeroed_upto = 0;
   size_t d2h_done = 0;  // groups whose output has been handed to the D2H stream
   uint64_t total_out = 0;
   auto drain_d2h = [&](size_t upto) -> int {  // enqueue D2H for groups [d2h_done, upto)
@@ -334,22 +330,15 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
     CK(cudaMemcpyAsync(pin_off + g.first0, w.member_off, (w.n_members + 1) * sizeof(uint64_t),
                        cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->gev[3 * gi + 2], s));
-    if (!known_fit) {
-      // caller's buffer is smaller than the worst case: learn the real extent before zeroing it
-      CK(cudaEventSynchronize(ctx->gev[3 * gi + 2]));
-      const uint64_t lo = pin_off[g.first0], hi = pin_off[g.first0 + w.n_members];
-      if (hi > dst_cap) return ZB200_ERR_DST_TOO_SMALL;
-      const size_t z0 = (size_t)lo & ~(size_t)3, z1 = std::min<size_t>(((size_t)hi + 3) & ~(size_t)3, dst_cap);
-      // a word shared with the previous group was zeroed (and possibly written) already
-      const size_t zs = std::max(z0, zeroed_upto);
-      if (z1 > zs) CK(cudaMemsetAsync(d_dst + zs, 0, z1 - zs, s));
-      zeroed_upto = std::max(zeroed_upto, z1);
-    }
     if (timed) CK(cudaEventRecord(ctx->ev[4], s));
+    // the packer ORs bits into zeros: clear exactly this group's extent, which only the device
+    // knows at this point -- no host round trip, whether or not the worst case would fit
+    CK(zb_launch_zero_range(d_dst, (const uint64_t *)ctx->group_end.p + gi, (const uint64_t *)ctx->group_end.p + gi + 1,
+                            dst_cap, s));
     CK(zb_launch_pack(w, s));
     if (timed) CK(cudaEventRecord(ctx->ev[5], s));
     CK(cudaEventRecord(ctx->gev[3 * gi + 1], s));
-    ctx->timing.kernel_launches += 5;
+    ctx->timing.kernel_launches += 6;
     ctx->timing.n_chunks += (uint32_t)g.nc;
     // keep at most two groups of output waiting on the device before draining to the host
     if (h_dst && gi >= 2) {
@@ -512,7 +501,7 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
     if (count_only && hw.fmt == ZB200_DF_GZIP) continue;  // ISIZE answers that (gzip.nim:66)
     if (hw.end <= hw.pos + 4) continue;
     // 1. candidate boundaries
-    const uint32_t cap = (uint32_t)std::min<uint64_t>((hw.end - hw.pos) / 32 + 64, 1u << 26);
+    const uint32_t cap = (uint32_t)std::min<uint64_t>((hw.end - hw.pos) / 32 + 64, 1u << 24);
     ENSURE(ctx->seg_cand, (size_t)cap * 8 + 16);
     ENSURE(ctx->counter, 64);
     uint32_t *d_cnt = (uint32_t *)ctx->counter.p + 8;

@@ -715,6 +715,9 @@ __global__ void __launch_bounds__(LZ_THREADS)
   __shared__ uint32_t codes[288 + 32];  // [0,288) litlen, [288,320) dist: code | len << 16
   __shared__ uint32_t rows_all[ZB_WARPS_PER_CHUNK * PK_ROW_WORDS * 32];
 
+  // a launch group whose output would end beyond the destination is not written at all (its
+  // extent was not zero-filled either); the host call then returns DST_TOO_SMALL
+  if (w.member_off[w.n_members] > w.dst_cap) return;
   const uint32_t chunk = blockIdx.x;
   const ZbChunkDesc d = w.desc[chunk];
   const ZbCodebook *cb = &w.cb[chunk];
@@ -904,6 +907,26 @@ cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s) {
 cudaError_t zb_launch_scan(const ZbCompressWork &w, cudaStream_t s) {
   k_scan<<<1, SCAN_THREADS, 0, s>>>(w);
   if (w.n_members) k_member_check<<<(w.n_members + 3) / 4, 128, 0, s>>>(w);  // one warp per member
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) k_zero_range(uint8_t *dst, const uint64_t *lo_p, const uint64_t *hi_p, uint64_t cap) {
+  if (*hi_p > cap) return;  // the group does not fit: k_pack skips it too
+  const uint64_t lo = (*lo_p + 3ull) & ~3ull, hi = (*hi_p + 3ull) & ~3ull;  // the word holding *lo belongs to the previous group
+  if (hi <= lo) return;
+  uint32_t *w = reinterpret_cast<uint32_t *>(dst + lo);
+  const uint64_t nwords = (hi - lo) >> 2;
+  const uint64_t head = min(nwords, (uint64_t)(((16u - (uint32_t)((uintptr_t)w & 15u)) & 15u) >> 2));
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+  if (tid < head) w[tid] = 0u;
+  uint4 *v = reinterpret_cast<uint4 *>(w + head);
+  const uint64_t nvec = (nwords - head) >> 2;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (uint64_t i = tid; i < nvec; i += stride) v[i] = z;
+  const uint64_t done = head + nvec * 4;
+  if (tid < nwords - done) w[done + tid] = 0u;
+}
+cudaError_t zb_launch_zero_range(uint8_t *dst, const uint64_t *lo, const uint64_t *hi, uint64_t cap, cudaStream_t s) {
+  k_zero_range<<<148 * 8, 256, 0, s>>>(dst, lo, hi, cap);
   return cudaGetLastError();
 }
 cudaError_t zb_launch_pack(const ZbCompressWork &w, cudaStream_t s) {

@@ -26,7 +26,8 @@ struct ZbChunkCheck {
 // All device scratch for one compress batch (arrays sized by n_chunks / n_members).
 struct ZbCompressWork {
   const uint8_t *src;          // device
-  uint8_t *dst;                // device, zero-filled up to the batch's total before packing
+  uint8_t *dst;                // device; each launch group's extent is zero-filled before it is packed
+  uint64_t dst_cap;            // bytes (multiple of 4): a group that would end beyond this is not written at all
   const ZbChunkDesc *desc;     // [n_chunks]
   const uint32_t *member_first;// [n_members + 1] first chunk index of each member
   const uint8_t *fname_len;    // [n_members] gzip FNAME letters (0..25) or nullptr
@@ -53,6 +54,10 @@ cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_scan(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_pack(const ZbCompressWork &w, cudaStream_t s);
+// zero dst[ceil4(*lo) .. ceil4(*hi)): the packer ORs bits into zeros; the extent of a launch group's
+// output is only known on the device (k_scan), so the fill reads it there; nothing at or beyond cap
+// is touched (a group that does not fit is not written: the call then fails with DST_TOO_SMALL)
+cudaError_t zb_launch_zero_range(uint8_t *dst, const uint64_t *lo, const uint64_t *hi, uint64_t cap, cudaStream_t s);
 
 // ---- inflate ----
 struct ZbInflateWork {
