@@ -199,6 +199,31 @@ def cpu_baseline(T, n_blocks_hint, seconds=12.0, threads=None, level=1):
             "ratio": float(total) / (nb * BLOCK)}, nb, dt
 
 
+def cpu_uncompress_baseline(T, seconds=4.0, threads=None):
+    """Oracle inflate (port of inflate.nim) of level-1 gzip members of C2 blocks, all host cores."""
+    from oracle import oracle as o
+    cores = threads or os.cpu_count() or 1
+    offs = block_offsets(len(T), 0, 512)
+    members = [o.compress(T[int(s):int(s) + BLOCK], 1, o.dfGzip) for s in offs]
+    reps = max(1, (cores * 8 + len(members) - 1) // len(members))
+    lens = np.array([len(m) for m in members] * reps, dtype=np.uint64)
+    base = np.frombuffer(b"".join(members) * reps, dtype=np.uint8)
+    mo = np.zeros(len(lens) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=mo[1:])
+    t0 = time.perf_counter()
+    total, _, st = o.uncompress_batch(base, mo, o.dfGzip, threads=cores)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rounds = int(max(1, min(64, seconds / dt)))
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        total, _, st = o.uncompress_batch(base, mo, o.dfGzip, threads=cores)
+    dt = time.perf_counter() - t0
+    assert not st.any() and int(total) == len(lens) * BLOCK
+    return {"out_gibs": rounds * len(lens) * BLOCK / GIB / dt, "in_gibs": rounds * int(mo[-1]) / GIB / dt, "cores": cores,
+            "kind": "port", "sample": "%d gzip members of C2 blocks x %d rounds, oracle inflate, %d threads, %.1f s"
+            % (len(lens), rounds, cores, dt)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU arm.  Rank 0 only."""
     if rank != 0:
@@ -224,6 +249,7 @@ def run_reference(args, rank, world):
                                       "all %d host threads" % (int(np.mean(nbs)), cores)},
            "e2e": {"value": val, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    out["uncompress"] = {"cpu_baseline": cpu_uncompress_baseline(T, seconds=3.0, threads=cores)}
     print(json.dumps(out))
 
 
@@ -444,8 +470,10 @@ def main():
         pass
 
     cpu = None
+    cpu_unc = None
     if not args.no_cpu:
         cpu, _, _ = cpu_baseline(T, n, level=args.level)
+        cpu_unc = cpu_uncompress_baseline(T)
 
     out = {"metric": "compress_level1_gzip_input_throughput", "value": value, "unit": "GiB/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -455,7 +483,7 @@ def main():
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
            "uncompress": {"out_gibs": n * BLOCK / GIB / (inflate_ms / 1e3), "in_gibs": comp_bytes / GIB / (inflate_ms / 1e3),
                           "ms": inflate_ms, "note": "GPU inflate + CRC verify of this batch's own members (device-resident)",
-                          "e2e": unc_e2e}}
+                          "e2e": unc_e2e, "cpu_baseline": cpu_unc}}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
