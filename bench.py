@@ -169,10 +169,25 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source, "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """Threads the CPU arm may really use: the affinity mask, capped by a cgroup CPU quota if there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(int(q) / float(p) + 0.5)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_baseline(T, n_blocks_hint, seconds=12.0, threads=None, level=1):
     """Oracle (port of the reference's level-1 path) over independent blocks on all host cores."""
     from oracle import oracle as o
-    cores = threads or os.cpu_count() or 1
+    cores = threads or host_threads()
     offs = block_offsets(len(T), 0, 4096)
     Tn = np.frombuffer(T, dtype=np.uint8)
 
@@ -202,7 +217,7 @@ def cpu_baseline(T, n_blocks_hint, seconds=12.0, threads=None, level=1):
 def cpu_uncompress_baseline(T, seconds=4.0, threads=None):
     """Oracle inflate (port of inflate.nim) of level-1 gzip members of C2 blocks, all host cores."""
     from oracle import oracle as o
-    cores = threads or os.cpu_count() or 1
+    cores = threads or host_threads()
     offs = block_offsets(len(T), 0, 512)
     members = [o.compress(T[int(s):int(s) + BLOCK], 1, o.dfGzip) for s in offs]
     reps = max(1, (cores * 8 + len(members) - 1) // len(members))
@@ -229,7 +244,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     T = text_corpus()
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     per_step = max(6.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     times, nbs = [], []
     for s in range(args.warmup + args.steps):
