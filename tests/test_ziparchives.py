@@ -146,6 +146,26 @@ def test_zip_reads_zipfile_archives_cpu():
     assert r.extract_file("a/b.txt") == b"hello " * 1000 and r.extract_file("stored.bin") == b"\x00\x01\x02"
 
 
+def test_zip64_many_entries_cpu():
+    """More than 65 535 entries: only the ZIP64 end-of-central-directory record can count them
+    (ziparchives.nim:595-618 always writes it; the reader takes the counts from it, :203-236)."""
+    za = _za()
+    ctx = ZlibCtx()
+    entries = {"d%03d/f%05d.txt" % (i % 200, i): (b"entry %d\n" % i) * (i % 3) for i in range(70000)}
+    blob = za.create_zip_archive(entries, ctx)
+    r = za.open_zip_archive(blob, ctx)
+    assert len(r.records) == 70000
+    names = list(r.walk_files())
+    assert names == list(entries)[::-1]
+    pick = names[::997]
+    got = r.extract_files(pick)
+    for k in pick:
+        assert got[k] == entries[k]
+    with zipfile.ZipFile(io.BytesIO(blob)) as zf:
+        assert len(zf.infolist()) == 70000
+        assert zf.read(names[12345]) == entries[names[12345]]
+
+
 @pytest.mark.gpu
 def test_zip_fixtures_gpu():
     import zippy_b200 as z
