@@ -166,6 +166,46 @@ def test_zip64_many_entries_cpu():
         assert zf.read(names[12345]) == entries[names[12345]]
 
 
+def _zipfile_made_archive(path):
+    buf = io.BytesIO()
+    with zipfile.ZipFile(buf, "w", zipfile.ZIP_DEFLATED) as zf:
+        zf.comment = b"archive comment"
+        zf.writestr("a/b.txt", b"hello " * 1000)
+        zf.writestr(zipfile.ZipInfo("stored.bin"), b"\x00\x01\x02", compress_type=zipfile.ZIP_STORED)
+        zf.writestr("a/", b"")
+        zf.writestr("caf\u00e9.txt", "na\u00efve".encode("utf-8"))
+    with open(path, "wb") as f:
+        f.write(b"JUNK" * 100 + buf.getvalue())     # appended to another file: offsets are off by 400
+
+
+def _run_cpp_zip(tmp_path, link_args):
+    """include/zippy_b200_zip.hpp (the C++ form of ziparchives.nim) through tests/native/cpp_zip_test.cpp."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "cpp_zip_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(HERE, "native", "cpp_zip_test.cpp")] + link_args)
+    src, dst = str(tmp_path / "in.zip"), str(tmp_path / "out.zip")
+    _zipfile_made_archive(src)
+    out = subprocess.run([exe, src, dst], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), (out.stdout, out.stderr)
+    with zipfile.ZipFile(dst) as zf:                  # an independent reader accepts what the C++ side wrote
+        assert zf.testzip() is None
+        assert [i.filename for i in zf.infolist()] == ["caf\u00e9.txt", "dir/sub/data.bin", "dir/empty.bin", "README.txt"]
+        assert zf.read("README.txt") == b"Hello, World!" and len(zf.read("dir/sub/data.bin")) == 300 * 256
+    return root
+
+
+def test_cpp_zip_layer_container_logic_cpu(tmp_path):
+    # zlib-backed stand-in for the C ABI (tests/native/mock_abi_zlib.cpp): container logic without a GPU
+    _run_cpp_zip(tmp_path, [os.path.join(HERE, "native", "mock_abi_zlib.cpp"), "-lz"])
+
+
+@pytest.mark.gpu
+def test_cpp_zip_layer_gpu(tmp_path):
+    libdir = os.path.join(os.path.dirname(HERE), "zippy_b200")
+    _run_cpp_zip(tmp_path, ["-L" + libdir, "-l:libzippy_b200.so", "-Wl,-rpath," + libdir])
+
+
 @pytest.mark.gpu
 def test_zip_fixtures_gpu():
     import zippy_b200 as z
