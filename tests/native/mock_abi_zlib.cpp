@@ -27,6 +27,48 @@ int zb200_checksum_batch(zb200_ctx *, const uint8_t *base, const uint64_t *off, 
   }
   return ZB200_OK;
 }
+int zb200_crc32(zb200_ctx *, const void *src, size_t len, uint32_t *out) {
+  *out = (uint32_t)crc32(0L, static_cast<const Bytef *>(src), (uInt)len);
+  return ZB200_OK;
+}
+int zb200_adler32(zb200_ctx *, const void *src, size_t len, uint32_t *out) {
+  *out = (uint32_t)adler32(1L, static_cast<const Bytef *>(src), (uInt)len);
+  return ZB200_OK;
+}
+static int raw_inflate(const uint8_t *src, size_t len, size_t pos, std::vector<uint8_t> &out) {
+  z_stream zs;
+  std::memset(&zs, 0, sizeof(zs));
+  if (pos > len || inflateInit2(&zs, -15) != Z_OK) return ZB200_ERR_UNCOMPRESS;
+  zs.next_in = const_cast<Bytef *>(src + pos);
+  zs.avail_in = (uInt)(len - pos);
+  out.resize(1 << 16);
+  int rc;
+  for (;;) {
+    zs.next_out = out.data() + zs.total_out;
+    zs.avail_out = (uInt)(out.size() - zs.total_out);
+    rc = inflate(&zs, Z_NO_FLUSH);
+    if (rc != Z_OK || zs.avail_out != 0) break;
+    out.resize(out.size() * 2);
+  }
+  out.resize(zs.total_out);
+  inflateEnd(&zs);
+  return rc == Z_STREAM_END ? ZB200_OK : ZB200_ERR_UNCOMPRESS;
+}
+int zb200_inflate_size(zb200_ctx *, const uint8_t *src, size_t len, size_t pos, size_t *n) {
+  std::vector<uint8_t> out;
+  int rc = raw_inflate(src, len, pos, out);
+  *n = out.size();
+  return rc;
+}
+int zb200_inflate(zb200_ctx *, const uint8_t *src, size_t len, size_t pos, uint8_t *dst, size_t cap, size_t *n) {
+  std::vector<uint8_t> out;
+  int rc = raw_inflate(src, len, pos, out);
+  if (rc) return rc;
+  if (out.size() > cap) return ZB200_ERR_DST_TOO_SMALL;
+  if (!out.empty()) std::memcpy(dst, out.data(), out.size());
+  *n = out.size();
+  return ZB200_OK;
+}
 int zb200_compress_batch(zb200_ctx *, const uint8_t *base, const uint64_t *off, size_t n, int, int fmt, const uint8_t *,
                          uint8_t *dst, size_t cap, uint64_t *dst_off, int *st) {
   if (fmt != ZB200_DF_DEFLATE) return ZB200_ERR_INVALID_FORMAT;

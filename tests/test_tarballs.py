@@ -90,6 +90,39 @@ def test_tar_rejects_unsafe_paths_cpu(tmp_path):
     assert not (tmp_path / "out").exists()
 
 
+def _run_cpp_tar(tmp_path, link_args):
+    """include/zippy_b200_tar.hpp (the C++ form of tarballs.nim) through tests/native/cpp_tar_test.cpp:
+    its view of a GNU-format .tar.gz must equal tarfile's, entry by entry."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "cpp_tar_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(here, "native", "cpp_tar_test.cpp")] + link_args)
+    p = _make(tmp_path, tarfile.GNU_FORMAT, True)
+    out = subprocess.run([exe, str(p)], capture_output=True, text=True, timeout=600)
+    lines = out.stdout.strip().split("\n")
+    assert out.returncode == 0 and lines[-1] == "OK", (out.stdout, out.stderr)
+    want = []
+    with tarfile.open(p) as tf:
+        for m in tf.getmembers():
+            kind = "f" if m.isfile() else "d" if m.isdir() else "l"
+            data = tf.extractfile(m).read() if m.isfile() else (m.linkname.encode() if m.issym() else b"")
+            name = m.name + ("/" if m.isdir() else "")
+            want.append("%s|%s|%d|%d|%o|%d" % (kind, name, len(data), zlib.crc32(data) if m.isfile() else 0, m.mode & 0o777,
+                                               int(m.mtime)))
+    assert lines[:-1] == want
+
+
+def test_cpp_tar_layer_header_walk_cpu(tmp_path):
+    here = os.path.dirname(os.path.abspath(__file__))
+    _run_cpp_tar(tmp_path, [os.path.join(here, "native", "mock_abi_zlib.cpp"), "-lz"])
+
+
+@pytest.mark.gpu
+def test_cpp_tar_layer_gpu(tmp_path):
+    libdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "zippy_b200")
+    _run_cpp_tar(tmp_path, ["-L" + libdir, "-l:libzippy_b200.so", "-Wl,-rpath," + libdir])
+
+
 @pytest.mark.gpu
 def test_tar_gz_extract_gpu(tmp_path):
     _run(tmp_path, tarfile.GNU_FORMAT, True, None)
