@@ -22,6 +22,7 @@ namespace zippy {
 namespace zipdetail {
 constexpr uint32_t kLocal = 0x04034b50u, kCentral = 0x02014b50u, kEocd = 0x06054b50u, kEocd64 = 0x06064b50u,
                    kLoc64 = 0x07064b50u;
+constexpr uint64_t kMaxExtractBytes = 1ull << 40;  // one extract call never sizes a buffer beyond this
 [[noreturn]] inline void fail(const std::string &msg) { throw ZippyError(ZB200_ERR_UNCOMPRESS, msg); }
 [[noreturn]] inline void eof() { fail("Attempted to read past end of file, corrupted archive?"); }
 inline uint16_t u16(const std::string &d, size_t p) {
@@ -120,16 +121,22 @@ class ZipArchiveReader {
     std::vector<const Record *> deflated;
     for (const Record *r : recs) {
       size_t pos = (size_t)r->headerOffset;
-      if (pos + 30 > d_.size()) eof();
+      if (pos > d_.size() || d_.size() - pos < 30) eof();
       if (u32(d_, pos) != kLocal) fail("Invalid file header");
       const uint16_t method = u16(d_, pos + 8);
       pos += 30 + (size_t)u16(d_, pos + 26) + u16(d_, pos + 28);
-      if (pos + r->compressedSize > d_.size()) eof();
+      // sizes come from the archive: no unchecked arithmetic on them
+      if (pos > d_.size() || r->compressedSize > d_.size() - pos) eof();
       if (method == 0) out[r->path] = d_.substr(pos, (size_t)r->compressedSize);
       else if (method == 8) {
         packed.append(d_, pos, (size_t)r->compressedSize);
         so.push_back(packed.size());
-        dofs.push_back(dofs.back() + r->uncompressedSize);
+        // DEFLATE cannot expand more than 1032:1: a larger directory claim can only end in a
+        // failed inflate, so never size a buffer by it (same clamp as the Python mirror)
+        const uint64_t lim = r->compressedSize * 1032ull + 1024ull;
+        const uint64_t want = r->uncompressedSize < lim ? r->uncompressedSize : lim;
+        if (want > (uint64_t)kMaxExtractBytes - dofs.back()) fail("Archive too large to extract in one call");
+        dofs.push_back(dofs.back() + want);
         deflated.push_back(r);
       } else fail("Unsupported archive, compression method");
     }
@@ -181,7 +188,7 @@ class ZipArchiveReader {
       if (u32(d_, eocd - 16) != 0) fail("Unsupported archive, disk number");
       const uint64_t pos = u64(d_, eocd - 12);
       if (u32(d_, eocd - 4) != 1) fail("Unsupported archive, num disks");
-      if (pos + 64 > size) eof();
+      if (pos > size || size - pos < 64) eof();
       if (u32(d_, (size_t)pos) != kEocd64) fail("Invalid central directory file header");
       disk = u32(d_, (size_t)pos + 16);
       startDisk = u32(d_, (size_t)pos + 20);

@@ -38,7 +38,7 @@ struct zb200_ctx {
   DevBuf in_stage, out_stage, lz2_tables;
   DevBuf seg_src, seg_dst, seg_len, seg_status, seg_kind, seg_expect, seg_cand, skip_mask;  // large-member segments
   uint64_t big_member_bytes = 512ull << 10;  // members at least this long are tried as parallel segments
-  cudaEvent_t ev[10];
+  cudaEvent_t ev[10] = {};
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> gev;   // per-group events (H2D done, compute done, offsets ready)
   void *pin = nullptr;            // pinned host scratch for descriptors / offsets
@@ -754,6 +754,31 @@ int stage_in(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offset
   return ZB200_OK;
 }
 
+// An error return must not leave copies that use the caller's buffers in flight.
+void quiesce(zb200_ctx *ctx) {
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+  cudaGetLastError();
+}
+
+// No C++ exception crosses the C ABI (std::vector growth on attacker-sized inputs, ...).
+template <class F>
+int guarded(zb200_ctx *ctx, F &&f) {
+  int rc;
+  try {
+    rc = f();
+  } catch (const std::bad_alloc &) {
+    if (ctx) ctx->last_err = "host allocation failed";
+    rc = ZB200_ERR_NOMEM;
+  } catch (const std::exception &e) {
+    if (ctx) ctx->last_err = e.what();
+    rc = ZB200_ERR_ARG;
+  }
+  if (rc != ZB200_OK && ctx) quiesce(ctx);
+  return rc;
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -806,6 +831,8 @@ int zb200_init(int device, zb200_ctx **out) {
   if (ok) ok = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; ok && i < 10; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   if (ok) ok = cudaMalloc((void **)&ctx->d_tabs, sizeof(ZbCrcTables)) == cudaSuccess;
+  // kernel attributes are per device (and cheap to set again): every ctx sets them for its own
+  if (ok) ok = zb_setup_deflate_attrs() == cudaSuccess && zb_setup_inflate_attrs() == cudaSuccess;
   if (ok) {
     ZbCrcTables t;
     zb_crc_build_tables(&t);
@@ -813,7 +840,7 @@ int zb200_init(int device, zb200_ctx **out) {
   }
   if (!ok) {
     cudaGetLastError();
-    delete ctx;
+    zb200_shutdown(ctx);  // releases whatever was created
     return ZB200_ERR_CUDA;
   }
   *out = ctx;
@@ -823,21 +850,24 @@ int zb200_init(int device, zb200_ctx **out) {
 void zb200_shutdown(zb200_ctx *ctx) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->desc, &ctx->member_first, &ctx->fname, &ctx->masks, &ctx->recs, &ctx->hist, &ctx->chk,
                     &ctx->cb, &ctx->chunk_off, &ctx->member_off, &ctx->member_check, &ctx->member_isize,
                     &ctx->src_off, &ctx->dst_off, &ctx->out_len, &ctx->status, &ctx->expect, &ctx->kind,
-                    &ctx->counter, &ctx->ck_out, &ctx->ck_pieces, &ctx->ck_first, &ctx->ck_piece_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables};
+                    &ctx->counter, &ctx->ck_out, &ctx->ck_pieces, &ctx->ck_first, &ctx->ck_piece_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables,
+                    &ctx->seg_src, &ctx->seg_dst, &ctx->seg_len, &ctx->seg_status, &ctx->seg_kind, &ctx->seg_expect, &ctx->seg_cand, &ctx->skip_mask};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_tabs) cudaFree(ctx->d_tabs);
-  for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 10; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (cudaEvent_t e : ctx->gev) cudaEventDestroy(e);
   if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->group_end.p) cudaFree(ctx->group_end.p);
-  cudaStreamDestroy(ctx->own_stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  cudaGetLastError();
   delete ctx;
 }
 
@@ -893,17 +923,20 @@ size_t zb200_compress_bound(size_t len, int data_format) {
 int zb200_compress_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                                 int level, int data_format, const uint8_t *fname_lens, uint8_t *d_dst,
                                 size_t dst_cap, uint64_t *dst_offsets, int *statuses) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !dst_offsets || (n && (!d_src || !d_dst))) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   ctx->timing.kernel_launches = 0;
   return compress_locked(ctx, d_src, nullptr, src_offsets, n, level, data_format, fname_lens, d_dst, dst_cap, nullptr,
                          0, dst_offsets, statuses, ctx->dev_group_chunks);
+  });
 }
 
 int zb200_compress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offsets, size_t n, int level,
                          int data_format, const uint8_t *fname_lens, uint8_t *dst_base, size_t dst_cap,
                          uint64_t *dst_offsets, int *statuses) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !dst_offsets || (n && (!src_base || !dst_base))) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
@@ -929,11 +962,13 @@ int zb200_compress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t
   ctx->timing.h2d_bytes = in_bytes;
   ctx->timing.d2h_bytes = dst_offsets[n];
   return ZB200_OK;
+  });
 }
 
 int zb200_uncompress_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                                   int data_format, uint8_t *d_dst, const uint64_t *dst_offsets, uint64_t *dst_lens,
                                   int *statuses) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !dst_offsets || !dst_lens || (n && !d_src)) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
@@ -941,10 +976,12 @@ int zb200_uncompress_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const ui
   ctx->timing.inflate_ms = ctx->timing.verify_ms = 0.f;
   return uncompress_device_locked(ctx, d_src, src_offsets, n, data_format, 0, d_dst, dst_offsets, dst_lens, statuses,
                                   false);
+  });
 }
 
 int zb200_uncompress_sizes_device(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                                   int data_format, uint64_t *sizes, int *statuses) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !sizes || (n && !d_src)) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
@@ -952,10 +989,12 @@ int zb200_uncompress_sizes_device(zb200_ctx *ctx, const uint8_t *d_src, const ui
   ctx->timing.inflate_ms = ctx->timing.verify_ms = 0.f;
   return uncompress_device_locked(ctx, d_src, src_offsets, n, data_format, 0, nullptr, nullptr, sizes, statuses,
                                   true);
+  });
 }
 
 int zb200_uncompress_sizes(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offsets, size_t n,
                            int data_format, uint64_t *sizes, int *statuses) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !sizes || (n && !src_base)) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
@@ -965,11 +1004,13 @@ int zb200_uncompress_sizes(zb200_ctx *ctx, const uint8_t *src_base, const uint64
   if (rc) return rc;
   return uncompress_device_locked(ctx, (const uint8_t *)ctx->in_stage.p, reb.data(), n, data_format, 0, nullptr,
                                   nullptr, sizes, statuses, true);
+  });
 }
 
 int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offsets, size_t n,
                            int data_format, uint8_t *dst_base, const uint64_t *dst_offsets, uint64_t *dst_lens,
                            int *statuses) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !dst_offsets || !dst_lens || (n && !src_base)) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
@@ -1053,19 +1094,23 @@ int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64
   ctx->timing.h2d_bytes = shi - slo;
   ctx->timing.d2h_bytes = hi - lo;
   return ZB200_OK;
+  });
 }
 
 int zb200_checksum_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n, int kind,
                                 uint32_t *out) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !out || (n && !d_src)) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   ctx->timing.kernel_launches = 0;
   return checksum_device_locked(ctx, d_src, src_offsets, n, kind, out);
+  });
 }
 
 int zb200_checksum_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offsets, size_t n, int kind,
                          uint32_t *out) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !out || (n && !src_base)) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
@@ -1074,6 +1119,7 @@ int zb200_checksum_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t
   int rc = stage_in(ctx, src_base, src_offsets, n, reb);
   if (rc) return rc;
   return checksum_device_locked(ctx, (const uint8_t *)ctx->in_stage.p, reb.data(), n, kind, out);
+  });
 }
 
 // ---- the single-input seam ----
@@ -1092,6 +1138,7 @@ int zb200_deflate(zb200_ctx *ctx, const uint8_t *src, size_t len, int level, uin
 
 static int inflate_one(zb200_ctx *ctx, const uint8_t *src, size_t len, size_t pos, uint8_t *dst, size_t dst_cap,
                        size_t *dst_len, bool count_only) {
+  return guarded(ctx, [&]() -> int {
   if (!ctx || !dst_len || (len && !src)) return ZB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
@@ -1114,6 +1161,7 @@ static int inflate_one(zb200_ctx *ctx, const uint8_t *src, size_t len, size_t po
   }
   *dst_len = (size_t)dl;
   return ZB200_OK;
+  });
 }
 
 int zb200_inflate(zb200_ctx *ctx, const uint8_t *src, size_t len, size_t pos, uint8_t *dst, size_t dst_cap,

@@ -877,14 +877,14 @@ size_t zb_lz2_table_bytes(int *grid_out) {
   if (grid_out) *grid_out = grid;
   return (size_t)grid * ZB_WARPS_PER_CHUNK * LZ2_BUCKETS * sizeof(uint2);
 }
+// function attributes are per device: zb200_init calls this once for the ctx's device
+cudaError_t zb_setup_deflate_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(k_lz<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz2, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ2_SM_TOTAL);
+  return e;
+}
 cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_lz<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
-    cudaFuncSetAttribute(k_lz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
-    cudaFuncSetAttribute(k_lz2, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ2_SM_TOTAL);
-    attr_set = true;
-  }
   if (w.n_chunks == 0) return cudaSuccess;
   if (zb_is_lz_level(w.level)) {
     int grid = 0;

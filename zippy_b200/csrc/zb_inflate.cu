@@ -1038,16 +1038,18 @@ cudaError_t zb_launch_find_sync(const uint8_t *src, uint64_t lo, uint64_t hi, ui
   return cudaGetLastError();
 }
 
+// function attributes are per device: zb200_init calls this once for the ctx's device
+cudaError_t zb_setup_inflate_attrs() {
+  const int smem = (int)(INF_GROUPS * sizeof(GroupSmem)) + 256;
+  cudaError_t e = cudaFuncSetAttribute(k_inflate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_piece_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL);
+  return e;
+}
+
 cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s) {
   if (w.n == 0) return cudaSuccess;
   const int smem = (int)(INF_GROUPS * sizeof(GroupSmem)) + 256;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(k_inflate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    done = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1065,12 +1067,6 @@ cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s) {
 
 cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s) {
   if (w.n == 0) return cudaSuccess;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(k_piece_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL);
-    if (e != cudaSuccess) return e;
-    done = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

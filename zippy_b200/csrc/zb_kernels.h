@@ -49,6 +49,9 @@ struct ZbCompressWork {
   int level, data_format;
 };
 
+// per-device kernel attributes (dynamic shared memory limits); call with the device current
+cudaError_t zb_setup_deflate_attrs();
+cudaError_t zb_setup_inflate_attrs();
 size_t zb_lz2_table_bytes(int *grid_out);
 cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s);
