@@ -132,6 +132,14 @@ int zb200_checksum_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t
 int zb200_compress_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                                 int level, int data_format, const uint8_t *fname_lens,
                                 uint8_t *d_dst, size_t dst_cap, uint64_t *dst_offsets, int *statuses);
+/* host inputs -> members left in DEVICE memory (H2D pipelined with the kernels).  The sharded
+ * multi-GPU path uses it: compress, exchange the sizes, then copy each shard to its place. */
+int zb200_compress_batch_h2d(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offsets, size_t n,
+                             int level, int data_format, const uint8_t *fname_lens,
+                             uint8_t *d_dst, size_t dst_cap, uint64_t *dst_offsets, int *statuses);
+/* device -> host copy on the ctx stream (returns when it has landed): the second half of the sharded
+ * path, once the size exchange has said where a shard goes in the concatenated host stream */
+int zb200_download(zb200_ctx *ctx, const uint8_t *d_src, uint8_t *h_dst, size_t bytes);
 int zb200_uncompress_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                                   int data_format, uint8_t *d_dst, const uint64_t *dst_offsets,
                                   uint64_t *dst_lens, int *statuses);
@@ -139,6 +147,13 @@ int zb200_uncompress_sizes_device(zb200_ctx *ctx, const uint8_t *d_src, const ui
                                   int data_format, uint64_t *sizes, int *statuses);
 int zb200_checksum_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                                 int kind, uint32_t *out);
+
+/* ---- host memory ----
+ * The host-buffer calls overlap their copies with the kernels only for page-locked memory.  A caller
+ * that reuses a buffer (a Nim string it keeps, an mmap) can page-lock it once with these; buffers that
+ * are not page-locked are staged through an internal pinned ring instead (slower than PCIe). */
+int zb200_host_register(void *ptr, size_t bytes);
+int zb200_host_unregister(void *ptr);
 
 /* ---- instrumentation (bench.py): device time in ms of the kernels of the last batch call,
  * measured with CUDA events on the ctx stream, and how many kernels it launched. ---- */

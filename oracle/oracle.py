@@ -46,6 +46,9 @@ def lib():
         L.zo_crc32.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         L.zo_adler32.restype = ctypes.c_uint32
         L.zo_adler32.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        for nm in ("zo_crc32_scalar", "zo_adler32_scalar"):
+            getattr(L, nm).restype = ctypes.c_uint32
+            getattr(L, nm).argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         L.zo_deflate.argtypes = [ctypes.POINTER(_Buf), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
         L.zo_inflate.argtypes = [ctypes.POINTER(_Buf), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t]
         L.zo_compress.argtypes = [ctypes.POINTER(_Buf), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,

@@ -160,11 +160,8 @@ static inline uint64_t rd64(const uint8_t *p) {
 /* ------------------------------------------------------------------ */
 /* checksums                                                           */
 /* ------------------------------------------------------------------ */
-/* crc.nim:29-51 slice-by-8, wrapped by :53-72 (the SIMD prefix computes the
- * same function, so the scalar form is the whole restatement). */
-uint32_t zo_crc32(const uint8_t *src, size_t len) {
-  ensure_tables();
-  uint32_t crc = ~0u;
+/* crc.nim:29-51 slice-by-8 with a running (pre-inverted) state. */
+static uint32_t crc32_scalar_state(const uint8_t *src, size_t len, uint32_t crc) {
   size_t i = 0;
   for (size_t n = len / 8; n > 0; n--) {
     uint32_t one = rd32(src + i) ^ crc;
@@ -176,11 +173,132 @@ uint32_t zo_crc32(const uint8_t *src, size_t len) {
     i += 8;
   }
   for (; i < len; i++) crc = crc_tables[0][(crc ^ src[i]) & 255] ^ (crc >> 8);
+  return crc;
+}
+uint32_t zo_crc32_scalar(const uint8_t *src, size_t len) {
+  ensure_tables();
+  return ~crc32_scalar_state(src, len, ~0u);
+}
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+/* crc32_simd.nim:39-144 (crc32_sse41_pcmul): carry-less-multiply folding of four 128-bit
+ * lanes (constants :43-46 are x^(512+-32), x^(128+-32), x^64 mod P and the Barrett pair), then
+ * 128 -> 64 -> 32 bit reduction.  len >= 64 and a multiple of 16; crc is the running state. */
+__attribute__((target("sse4.1,pclmul")))
+static uint32_t crc32_pclmul_state(const uint8_t *p, size_t len, uint32_t crc) {
+  const __m128i k12 = _mm_set_epi64x(0x01c6e41596ll, 0x0154442bd4ll);
+  const __m128i k34 = _mm_set_epi64x(0x00ccaa009ell, 0x01751997d0ll);
+  const __m128i k5 = _mm_set_epi64x(0, 0x0163cd6124ll);
+  const __m128i mu = _mm_set_epi64x(0x01f7011641ll, 0x01db710641ll);
+  const __m128i lo32 = _mm_setr_epi32(~0, 0, ~0, 0);
+  __m128i a = _mm_loadu_si128((const __m128i *)(p + 0)), b = _mm_loadu_si128((const __m128i *)(p + 16));
+  __m128i c = _mm_loadu_si128((const __m128i *)(p + 32)), d = _mm_loadu_si128((const __m128i *)(p + 48));
+  a = _mm_xor_si128(a, _mm_cvtsi32_si128((int)crc));
+  p += 64;
+  len -= 64;
+#define ZO_FOLD(x, k, in) \
+  _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x, k, 0x00), _mm_clmulepi64_si128(x, k, 0x11)), in)
+  while (len >= 64) { /* :67-92 */
+    a = ZO_FOLD(a, k12, _mm_loadu_si128((const __m128i *)(p + 0)));
+    b = ZO_FOLD(b, k12, _mm_loadu_si128((const __m128i *)(p + 16)));
+    c = ZO_FOLD(c, k12, _mm_loadu_si128((const __m128i *)(p + 32)));
+    d = ZO_FOLD(d, k12, _mm_loadu_si128((const __m128i *)(p + 48)));
+    p += 64;
+    len -= 64;
+  }
+  a = ZO_FOLD(a, k34, b); /* :94-110 */
+  a = ZO_FOLD(a, k34, c);
+  a = ZO_FOLD(a, k34, d);
+  while (len >= 16) { /* :112-121 */
+    a = ZO_FOLD(a, k34, _mm_loadu_si128((const __m128i *)p));
+    p += 16;
+    len -= 16;
+  }
+#undef ZO_FOLD
+  /* :123-142 */
+  __m128i t = _mm_clmulepi64_si128(a, k34, 0x10);
+  a = _mm_xor_si128(_mm_srli_si128(a, 8), t);
+  t = _mm_srli_si128(a, 4);
+  a = _mm_xor_si128(_mm_clmulepi64_si128(_mm_and_si128(a, lo32), k5, 0x00), t);
+  t = _mm_and_si128(a, lo32);
+  t = _mm_clmulepi64_si128(t, mu, 0x10);
+  t = _mm_and_si128(t, lo32);
+  t = _mm_clmulepi64_si128(t, mu, 0x00);
+  a = _mm_xor_si128(a, t);
+  return (uint32_t)_mm_extract_epi32(a, 1);
+}
+
+/* adler32_simd.nim:45-120 (adler32_ssse3): 32-byte blocks, sad for s1, maddubs taps 32..1 for
+ * s2, modulo every nmax/32 blocks. */
+__attribute__((target("ssse3")))
+static uint32_t adler32_ssse3(const uint8_t *src, size_t len) {
+  const uint32_t block = 32, nmax = 5552;
+  uint32_t s1 = 1, s2 = 0;
+  size_t pos = 0;
+  size_t blocks = len / block, remaining = len - blocks * block;
+  const __m128i tap1 = _mm_setr_epi8(32, 31, 30, 29, 28, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18, 17);
+  const __m128i tap2 = _mm_setr_epi8(16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1);
+  const __m128i zero = _mm_setzero_si128(), ones = _mm_set1_epi16(1);
+  while (blocks > 0) {
+    size_t n = nmax / block;
+    if (n > blocks) n = blocks;
+    blocks -= n;
+    __m128i ps = _mm_set_epi32(0, 0, 0, (int)(s1 * (uint32_t)n));
+    __m128i v2 = _mm_set_epi32(0, 0, 0, (int)s2), v1 = zero;
+    for (; n > 0; n--, pos += 32) {
+      const __m128i b1 = _mm_loadu_si128((const __m128i *)(src + pos));
+      const __m128i b2 = _mm_loadu_si128((const __m128i *)(src + pos + 16));
+      ps = _mm_add_epi32(ps, v1);
+      v1 = _mm_add_epi32(v1, _mm_sad_epu8(b1, zero));
+      v2 = _mm_add_epi32(v2, _mm_madd_epi16(_mm_maddubs_epi16(b1, tap1), ones));
+      v1 = _mm_add_epi32(v1, _mm_sad_epu8(b2, zero));
+      v2 = _mm_add_epi32(v2, _mm_madd_epi16(_mm_maddubs_epi16(b2, tap2), ones));
+    }
+    v2 = _mm_add_epi32(v2, _mm_slli_epi32(ps, 5));
+    v1 = _mm_add_epi32(v1, _mm_shuffle_epi32(v1, _MM_SHUFFLE(2, 3, 0, 1)));
+    v1 = _mm_add_epi32(v1, _mm_shuffle_epi32(v1, _MM_SHUFFLE(1, 0, 3, 2)));
+    s1 += (uint32_t)_mm_cvtsi128_si32(v1);
+    v2 = _mm_add_epi32(v2, _mm_shuffle_epi32(v2, _MM_SHUFFLE(2, 3, 0, 1)));
+    v2 = _mm_add_epi32(v2, _mm_shuffle_epi32(v2, _MM_SHUFFLE(1, 0, 3, 2)));
+    s2 = (uint32_t)_mm_cvtsi128_si32(v2);
+    s1 %= 65521;
+    s2 %= 65521;
+  }
+  for (size_t i = 0; i < remaining; i++) {
+    s1 += src[pos + i];
+    s2 += s1;
+  }
+  s1 %= 65521;
+  s2 %= 65521;
+  return (s2 << 16) | s1;
+}
+static int cpu_has_pclmul(void) { return __builtin_cpu_supports("sse4.1") && __builtin_cpu_supports("pclmul"); }
+static int cpu_has_ssse3(void) { return __builtin_cpu_supports("ssse3"); }
+#else
+static int cpu_has_pclmul(void) { return 0; }
+static int cpu_has_ssse3(void) { return 0; }
+#endif
+
+/* crc.nim:53-72: the SIMD prefix (16-byte multiple, len >= 64, amd64 with SSE4.1 + PCLMUL),
+ * then the scalar tail -- what the reference really runs on the bench hosts. */
+uint32_t zo_crc32(const uint8_t *src, size_t len) {
+  ensure_tables();
+  uint32_t crc = ~0u;
+  size_t pos = 0;
+#if defined(__x86_64__)
+  if (len >= 64 && cpu_has_pclmul()) {
+    const size_t simd_len = (len / 16) * 16;
+    crc = crc32_pclmul_state(src, simd_len, crc);
+    pos = simd_len;
+  }
+#endif
+  if (pos < len) crc = crc32_scalar_state(src + pos, len - pos, crc);
   return ~crc;
 }
 
-/* adler32.nim:6-63 (NMAX = 5552 deferred modulo). */
-uint32_t zo_adler32(const uint8_t *src, size_t len) {
+/* adler32.nim:17-63 scalar form (NMAX = 5552 deferred modulo). */
+uint32_t zo_adler32_scalar(const uint8_t *src, size_t len) {
   const size_t nmax = 5552;
   uint32_t s1 = 1, s2 = 0;
   size_t pos = 0, l = len;
@@ -201,6 +319,13 @@ uint32_t zo_adler32(const uint8_t *src, size_t len) {
   s1 %= 65521;
   s2 %= 65521;
   return (s2 << 16) | s1;
+}
+/* adler32.nim:6-15: the SSSE3 path is always taken on amd64 when the CPU has SSSE3. */
+uint32_t zo_adler32(const uint8_t *src, size_t len) {
+#if defined(__x86_64__)
+  if (cpu_has_ssse3() && len <= 0xffffffffu) return len ? adler32_ssse3(src, len) : 1u;
+#endif
+  return zo_adler32_scalar(src, len);
 }
 
 /* ------------------------------------------------------------------ */

@@ -64,6 +64,10 @@ void zo_buf_free(zo_buf *b);
 
 uint32_t zo_crc32(const uint8_t *src, size_t len);   /* crc.nim:53-72 */
 uint32_t zo_adler32(const uint8_t *src, size_t len); /* adler32.nim:6-63 */
+/* the scalar bodies alone (crc.nim:29-51, adler32.nim:17-63): what zo_crc32 / zo_adler32 fall back
+ * to without SSE4.1+PCLMUL / SSSE3; the SIMD forms are checked against them in tests/test_oracle.py */
+uint32_t zo_crc32_scalar(const uint8_t *src, size_t len);
+uint32_t zo_adler32_scalar(const uint8_t *src, size_t len);
 
 /* deflate.nim:207-467: appends raw RFC1951 bytes to dst. */
 int zo_deflate(zo_buf *dst, const uint8_t *src, size_t len, int level);

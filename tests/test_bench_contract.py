@@ -8,8 +8,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _latest_line():
+    """The newest committed bench line (profiles/bench_r<N>_final.json)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r*_final.json")),
+                   key=lambda f: int(re.search(r"bench_r(\d+)_final", f).group(1)))
+    return json.load(open(files[-1]))
+
+
 def test_committed_bench_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r1_final.json")))
+    d = _latest_line()
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k

@@ -141,3 +141,19 @@ def test_batch_threads_match_single(corpus):
     t4, l4, s4 = o.compress_batch(base, offs, 1, o.dfGzip, threads=4)
     assert t1 == t4 and (l1 == l4).all() and not s1.any() and not s4.any()
     assert int(l1[0]) == len(o.compress(blocks[0], 1, o.dfGzip))
+
+
+def test_simd_checksums_match_scalar_and_zlib():
+    """The CPU arm runs what the reference runs on amd64 (PCLMUL CRC-32 crc32_simd.nim:39-144, SSSE3
+    Adler-32 adler32_simd.nim:45-120); both are checked against the scalar restatement and zlib."""
+    import random
+    from oracle import oracle as o
+    L = o.lib()
+    rng = random.Random(7)
+    blob = bytes(rng.randrange(256) for _ in range(70001))
+    for n in list(range(0, 200)) + [1000, 5551, 5552, 5553, 65535, 65536, 70001]:
+        b = blob[:n]
+        assert o.crc32(b) == zlib.crc32(b) == L.zo_crc32_scalar(b, n), n
+        assert o.adler32(b) == zlib.adler32(b) == L.zo_adler32_scalar(b, n), n
+    big = blob * 40
+    assert o.crc32(big) == zlib.crc32(big) and o.adler32(big) == zlib.adler32(big)

@@ -170,6 +170,23 @@ class Context:
                                                        out_offs.ctypes.data, None))
         return out_offs
 
+    def compress_batch_h2d(self, h_src, offsets, level, dataFormat, d_dst, dst_cap, fname_lens=None):
+        """Host inputs (raw pointer; page-locked memory lets the copies overlap the kernels) -> members left
+        in device memory at d_dst.  Returns the member offsets (uint64[n+1])."""
+        L = _native.lib()
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out_offs = np.zeros(n + 1, dtype=np.uint64)
+        fl = np.ascontiguousarray(fname_lens, dtype=np.uint8) if fname_lens is not None else None
+        _check(self._h, L.zb200_compress_batch_h2d(self._h, h_src, offsets.ctypes.data, n, level, dataFormat,
+                                                    fl.ctypes.data if fl is not None else None, d_dst, dst_cap,
+                                                    out_offs.ctypes.data, None))
+        return out_offs
+
+    def download(self, d_src, h_dst, nbytes):
+        """Device -> host copy on the ctx stream; returns when the bytes have landed."""
+        _check(self._h, _native.lib().zb200_download(self._h, d_src, h_dst, nbytes))
+
     def uncompress_batch_device(self, d_src, offsets, dataFormat, d_dst, dst_offsets):
         L = _native.lib()
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -238,6 +255,15 @@ class Context:
         v = ctypes.c_uint32(0)
         _check(self._h, _native.lib().zb200_adler32(self._h, src.ctypes.data, src.size, ctypes.byref(v)))
         return v.value
+
+
+def host_register(ptr, nbytes):
+    """Page-lock a caller-owned host range (cudaHostRegister) so host-buffer calls overlap their copies."""
+    _check(None, _native.lib().zb200_host_register(ptr, nbytes))
+
+
+def host_unregister(ptr):
+    _check(None, _native.lib().zb200_host_unregister(ptr))
 
 
 _default = None

@@ -38,6 +38,11 @@ SYMBOLS = {
     "zb200_adler32": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, ctypes.POINTER(ctypes.c_uint32)]),
     "zb200_compress_batch": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, c_int, c_u8p, c_u8p, c_size_t,
                                      c_u64p, c_intp]),
+    "zb200_compress_batch_h2d": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, c_int, c_u8p, c_u8p, c_size_t,
+                                         c_u64p, c_intp]),
+    "zb200_download": (c_int, [ctypes.c_void_p, c_u8p, c_u8p, c_size_t]),
+    "zb200_host_register": (c_int, [ctypes.c_void_p, c_size_t]),
+    "zb200_host_unregister": (c_int, [ctypes.c_void_p]),
     "zb200_uncompress_sizes": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, c_u64p, c_intp]),
     "zb200_uncompress_batch": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, c_u8p, c_u64p, c_u64p, c_intp]),
     "zb200_checksum_batch": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, ctypes.c_void_p]),

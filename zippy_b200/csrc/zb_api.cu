@@ -965,6 +965,66 @@ int zb200_compress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t
   });
 }
 
+// host inputs (pipelined H2D over launch groups) -> members left in device memory: the sharded
+// multi-GPU path compresses this way, exchanges the sizes, and only then knows where each shard's
+// bytes go in the concatenated host stream
+int zb200_compress_batch_h2d(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offsets, size_t n, int level,
+                             int data_format, const uint8_t *fname_lens, uint8_t *d_dst, size_t dst_cap,
+                             uint64_t *dst_offsets, int *statuses) {
+  return guarded(ctx, [&]() -> int {
+    if (!ctx || !src_offsets || !dst_offsets || (n && (!src_base || !d_dst))) return ZB200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    if (n == 0) {
+      dst_offsets[0] = 0;
+      return ZB200_OK;
+    }
+    for (size_t i = 0; i < n; i++)
+      if (src_offsets[i + 1] < src_offsets[i]) return ZB200_ERR_ARG;
+    const uint64_t in_bytes = src_offsets[n] - src_offsets[0];
+    ENSURE(ctx->in_stage, (size_t)in_bytes + 64);
+    int rc = compress_locked(ctx, (const uint8_t *)ctx->in_stage.p, src_base, src_offsets, n, level, data_format,
+                             fname_lens, d_dst, dst_cap, nullptr, 0, dst_offsets, statuses, ctx->host_group_chunks);
+    if (rc) return rc;
+    ctx->timing.h2d_ms = ev_ms(ctx->ev[6], ctx->ev[7]);
+    ctx->timing.h2d_bytes = in_bytes;
+    return ZB200_OK;
+  });
+}
+
+// second half of the sharded path: once the size exchange has told a rank where its shard lands in
+// the concatenated stream, its device-resident members go straight to that place in host memory
+int zb200_download(zb200_ctx *ctx, const uint8_t *d_src, uint8_t *h_dst, size_t bytes) {
+  return guarded(ctx, [&]() -> int {
+    if (!ctx || (bytes && (!d_src || !h_dst))) return ZB200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (bytes) CK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZB200_OK;
+  });
+}
+
+// page-lock a caller-owned host range so that the host-buffer calls can overlap their copies with
+// the kernels (cudaHostRegister; a Nim string / malloc'd buffer is pageable otherwise)
+int zb200_host_register(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return ZB200_ERR_ARG;
+  if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return ZB200_ERR_CUDA;
+  }
+  return ZB200_OK;
+}
+int zb200_host_unregister(void *ptr) {
+  if (!ptr) return ZB200_ERR_ARG;
+  if (cudaHostUnregister(ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return ZB200_ERR_CUDA;
+  }
+  return ZB200_OK;
+}
+
 int zb200_uncompress_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                                   int data_format, uint8_t *d_dst, const uint64_t *dst_offsets, uint64_t *dst_lens,
                                   int *statuses) {
