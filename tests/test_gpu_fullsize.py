@@ -62,6 +62,11 @@ def test_c2_full_size_properties(env):
     d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
     oo = ctx.compress_batch_device(d_src.data_ptr(), src_offsets, 1, z.dfGzip, d_dst.data_ptr(), cap)
     assert (np.diff(oo.astype(np.int64)) > 18).all()
+    # determinism at full size: a second run into a dirty buffer yields the same bytes and offsets
+    d_dst2 = torch.full((cap,), 0x5A, dtype=torch.uint8, device="cuda")
+    oo2 = ctx.compress_batch_device(d_src.data_ptr(), src_offsets, 1, z.dfGzip, d_dst2.data_ptr(), cap)
+    assert (oo2 == oo).all() and torch.equal(d_dst[:int(oo[n])], d_dst2[:int(oo[n])]), "level-1 output differs run to run"
+    del d_dst2
     # checksum of checksums: trailers written by the compress kernels vs the checksum kernels
     crc = ctx.checksum_batch_device(d_src.data_ptr(), src_offsets, "crc32")
     ends = torch.from_numpy(oo[1:].astype(np.int64)).cuda()

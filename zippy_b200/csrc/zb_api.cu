@@ -226,7 +226,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   ENSURE(ctx->fname, n + 16);
   ENSURE(ctx->group_end, (ng + 1) * sizeof(uint64_t));
   ENSURE(ctx->masks, max_nc * ZB_WINDOWS_PER_CHUNK * sizeof(uint2));
-  ENSURE(ctx->recs, max_nc * (size_t)ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS * sizeof(uint32_t));
+  ENSURE(ctx->recs, max_nc * (size_t)ZB_RECS_PER_CHUNK * sizeof(uint32_t));
   ENSURE(ctx->hist, max_nc * (size_t)ZB_WARPS_PER_CHUNK * ZB_HIST_SYMS * sizeof(uint16_t));
   ENSURE(ctx->chk, max_nc * sizeof(ZbChunkCheck));
   ENSURE(ctx->cb, max_nc * sizeof(ZbCodebook));
@@ -331,14 +331,10 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
                        cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->gev[3 * gi + 2], s));
     if (timed) CK(cudaEventRecord(ctx->ev[4], s));
-    // the packer ORs bits into zeros: clear exactly this group's extent, which only the device
-    // knows at this point -- no host round trip, whether or not the worst case would fit
-    CK(zb_launch_zero_range(d_dst, (const uint64_t *)ctx->group_end.p + gi, (const uint64_t *)ctx->group_end.p + gi + 1,
-                            dst_cap, s));
     CK(zb_launch_pack(w, s));
     if (timed) CK(cudaEventRecord(ctx->ev[5], s));
     CK(cudaEventRecord(ctx->gev[3 * gi + 1], s));
-    ctx->timing.kernel_launches += 6;
+    ctx->timing.kernel_launches += 5;
     ctx->timing.n_chunks += (uint32_t)g.nc;
     // keep at most two groups of output waiting on the device before draining to the host
     if (h_dst && gi >= 2) {

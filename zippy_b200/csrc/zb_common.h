@@ -21,6 +21,8 @@
 #define ZB_WINDOWS_PER_CHUNK (ZB_CHUNK_BYTES / ZB_WINDOW)   // 2048
 #define ZB_WINDOWS_PER_SUB (ZB_SUB_BYTES / ZB_WINDOW)       // 256
 #define ZB_MATCH_SLOTS 8          // a 32-byte window starts at most 8 matches (min length 4)
+#define ZB_RECS_PER_SUB (ZB_SUB_BYTES / 4)    // match records a sub-chunk can hold (matches are >= 4 bytes), dense
+#define ZB_RECS_PER_CHUNK (ZB_WARPS_PER_CHUNK * ZB_RECS_PER_SUB)
 
 #define ZB_NUM_LITLEN 286
 #define ZB_NUM_DIST 30

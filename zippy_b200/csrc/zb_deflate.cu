@@ -119,10 +119,14 @@ __device__ __forceinline__ void lz_select(const uint8_t *data, uint32_t off0, ui
 }
 
 // One lane per window: publish the window's masks, turn its raw match records into the
-// packer's records and count every token in the sub-chunk histogram.
+// packer's records and count every token in the sub-chunk histogram.  The records of a
+// sub-chunk form one DENSE stream in window order (grecs_sub[rec_base ...]): a warp prefix sum
+// of the windows' match counts places them, and the packer recomputes the same prefix from
+// the masks.  (Eight fixed slots per window made every record a 4-byte write into its own
+// 32-byte sector: 2.3x the algorithmic DRAM traffic.)
 __device__ __forceinline__ void lz_batch_pass(const uint8_t *wdata, bool active, uint32_t ksel, uint32_t kism,
                                               const uint32_t *ring_lane, uint32_t *whist, uint2 *gmask_w,
-                                              uint32_t *grecs_w) {
+                                              uint32_t *grecs_sub, uint32_t &rec_base) {
   if (active) *gmask_w = make_uint2(ksel, kism);
   const uint32_t im = active ? kism : 0u;
   uint32_t s = active ? (ksel & ~kism) : 0u;  // literal tokens
@@ -133,6 +137,14 @@ __device__ __forceinline__ void lz_batch_pass(const uint8_t *wdata, bool active,
     atomicAdd(&whist[sy >> 1], 1u << ((sy & 1u) * 16u));
   }
   const uint32_t nmatch = (uint32_t)__popc(im);
+  uint32_t incl = nmatch;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(ZB_FULL, incl, o);
+    if (zb_lane() >= o) incl += t;
+  }
+  uint32_t *grecs_w = grecs_sub + rec_base + incl - nmatch;
+  rec_base += __shfl_sync(ZB_FULL, incl, 31);
   for (uint32_t k = 0; k < nmatch; k++) {
     const uint32_t raw = ring_lane[k];
     int lc, dc;
@@ -231,7 +243,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     uint32_t entry = b0;
     uint32_t ksel = 0, kism = 0;  // lane i keeps the masks of window i of the current batch of 32
     uint2 *gmask = masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
-    uint32_t *grecs = recs + (size_t)chunk * ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS;
+    uint32_t *grecs = recs + (size_t)chunk * ZB_RECS_PER_CHUNK + (size_t)warp * ZB_RECS_PER_SUB;
+    uint32_t rec_base = 0;
     for (uint32_t wb = b0; wb < b1; wb += 32) {
       const uint32_t win = wb >> 5, slot = win & 31u;
       uint32_t sel = 0, ism = 0;
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
         __syncwarp();
         const uint32_t bwin = win - slot + (uint32_t)lane;  // this lane's window
         lz_batch_pass(data + mis + (bwin << 5), (uint32_t)lane <= slot, ksel, kism, ring + (uint32_t)lane * ZB_MATCH_SLOTS,
-                      whist, gmask + bwin, grecs + bwin * ZB_MATCH_SLOTS);
+                      whist, gmask + bwin, grecs, rec_base);
         ksel = kism = 0;
         __syncwarp();
       }
@@ -320,21 +333,33 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 // ------------------------------------------------------------------------------------
 // k_lz2: the matcher for the LZ levels (-1, 2..9; replaces encodeLz77, lz77.nim:10-130, whose
 // head/chain arrays -- 256 KiB + 64 KiB per block -- do not fit next to the data).
-// Same CTA = chunk / warp = 8 KiB sub-chunk mapping as k_lz, with three differences:
-//  * the chunk is staged together with up to 32 KiB of the member's preceding bytes, so a
-//    match can reach back the full DEFLATE window across chunk boundaries;
-//  * each warp's dictionary is a private 8192-bucket x 4-way table of the most recent
-//    positions per hash (one 8-byte bucket = one 64-bit access), kept in global memory
-//    (64 KiB per warp, one slot per resident CTA: the grid is persistent) and
-//    pre-seeded with the 32 KiB before the sub-chunk; every candidate in the bucket -- plus
-//    the nearest same-hash position inside the current window -- is verified and extended
-//    against shared memory and the longest wins (the reference walks up to 128 chain links);
-//  * one-step lazy evaluation: a match shorter than 16 is dropped when the next position
-//    has a longer one (the reference is greedy; this recovers what the shallower search loses).
+// Same CTA = chunk / warp = 8 KiB sub-chunk mapping as k_lz; the chunk is staged together with up
+// to 32 KiB of the member's preceding bytes so a match can reach back the full DEFLATE window across
+// chunk boundaries.  The dictionary is cut into 8 KiB SEGMENTS (= sub-chunks), one 2048-bucket x
+// 4-way table of u16 positions per segment (as many slots as positions; a bucket keeps the most
+// recent four of its hash), all in global memory / L2, one set per resident CTA:
+//  * phase 1, BUILD: the segments that lie BEFORE some sub-chunk of this chunk (the staged history
+//    and all but the last sub-chunk) get a static table, each built once by one warp inserting the
+//    segment's positions in order.  (The first version gave every warp a private table pre-seeded
+//    with its own 32 KiB of history: every position was inserted five times and the 155 MB of tables
+//    thrashed the L2 -- 80 % of that kernel was pre-seeding.)
+//  * phase 2, PARSE: a warp walks its sub-chunk 32 positions per step; a lane's candidates are the
+//    nearest same-hash position inside the window, the four ways of its bucket in the warp's own
+//    incremental table (positions of this sub-chunk seen so far) and the four ways of its bucket in
+//    each of the four preceding segments' static tables -- five independent 8-byte loads instead of
+//    a dependent chain walk (the reference follows up to `chain` links, lz77.nim:88-109).  Candidates
+//    are verified / extended against shared memory nearest first under the level's budget:
+//    at most `maxcand` verified candidates, one more once a match of `good` bytes is in hand
+//    (lz77.nim:104 quarters its budget there); the longest wins;
+//  * one-step lazy evaluation: a match shorter than `lazy` is dropped when the next position has a
+//    longer one (the reference is greedy; this recovers what the bounded search loses).
 #define LZ2_HIST 32768
-#define LZ2_BUCKETS 8192
+#define LZ2_SEG_BYTES ZB_SUB_BYTES
+#define LZ2_SEGS ((ZB_CHUNK_BYTES + LZ2_HIST) / LZ2_SEG_BYTES)     // 12 segments per staged region
+#define LZ2_BUCKET_BITS 11
+#define LZ2_BUCKETS (1 << LZ2_BUCKET_BITS)                          // per table (own and static)
+#define LZ2_TABLES_PER_CTA (ZB_WARPS_PER_CHUNK + LZ2_SEGS)          // 8 own + 12 static
 #define LZ2_RING_WINDOWS 16
-#define LZ2_LAZY_MAX 16
 #define LZ2_SM_DATA_BYTES (ZB_CHUNK_BYTES + LZ2_HIST + 64 + 384)
 #define LZ2_SM_HIST (LZ2_SM_DATA_BYTES)
 #define LZ2_SM_RING (LZ2_SM_HIST + LZ_SM_HIST_BYTES)
@@ -346,7 +371,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 #define LZ2_SM_TOTAL (LZ2_SM_BAR + 16)
 static_assert(2 * (LZ2_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
 
-__device__ __forceinline__ uint32_t lz2_hash(uint32_t v) { return (v * 0x9E3779B1u) >> 19; }  // 13 bits
+__device__ __forceinline__ uint32_t lz2_hash(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - LZ2_BUCKET_BITS); }
 
 // shift `e` into way 0 of a bucket of four u16 entries (most recent first)
 __device__ __forceinline__ uint2 lz2_push(uint2 b, uint32_t e) {
@@ -356,11 +381,19 @@ __device__ __forceinline__ uint2 lz2_push(uint2 b, uint32_t e) {
   return r;
 }
 
-// Insert the window's positions into the warp's table; returns each lane's bucket as it was
-// before this window (the lookup) and the mask of lanes sharing the lane's hash.
-__device__ __forceinline__ uint2 lz2_probe_insert(uint2 *tab, uint32_t v, bool can, uint32_t qwin, uint32_t &grp) {
+__device__ __forceinline__ void lz2_clear_table(uint2 *tab) {
+  const uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u);
+  uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+  for (int i = zb_lane(); i < LZ2_BUCKETS / 2; i += 32) __stcg(&t4[i], ff);
+}
+
+// Insert the window's positions (qwin + lane, for lanes with `can`) into a table in stream order;
+// returns each lane's bucket as it was before this window (the lookup) and the mask of lanes
+// sharing the lane's hash.  Positions are stored modulo 2^16: a candidate's distance is
+// (q - entry) & 0xffff, and since every candidate is verified against the data at that distance
+// a stale alias can only cost a compare, never correctness.
+__device__ __forceinline__ uint2 lz2_probe_insert(uint2 *tab, uint32_t h, bool can, uint32_t qwin, uint32_t &grp) {
   const int lane = zb_lane();
-  const uint32_t h = lz2_hash(v);
   grp = __match_any_sync(ZB_FULL, can ? h : (0x80000000u | (uint32_t)lane));
   uint2 old = make_uint2(~0u, ~0u);
   if (can) old = __ldcg(&tab[h]);
@@ -374,18 +407,23 @@ __device__ __forceinline__ uint2 lz2_probe_insert(uint2 *tab, uint32_t v, bool c
   return old;
 }
 
-// Verify and extend one candidate at distance dcand against the lane's position; keep it if
-// it beats the best match so far.  Position x of the chunk lives at data[off0 + x].
+// Verify and extend one candidate at distance dcand against the lane's position; keep it if it
+// beats the best match so far.  Position x of the chunk lives at data[off0 + x].  `budget` counts
+// verified candidates (the 4-byte check passed).
 __device__ __forceinline__ void lz2_eval(const uint8_t *data, uint32_t poff, uint32_t q, uint32_t v, uint32_t limit,
-                                         uint32_t dcand, uint32_t &m, uint32_t &dist) {
+                                         uint32_t dcand, uint32_t good, uint32_t &m, uint32_t &dist, int &budget) {
   if (dcand == 0 || dcand > ZB_MAX_DIST || dcand > q) return;
   const uint32_t co = poff - dcand;
-  if (m >= 4 && data[co + m] != data[poff + m]) return;  // cannot beat the best so far
   const uint32_t *wp = reinterpret_cast<const uint32_t *>(data) + (poff >> 2);
   const uint32_t *wc = reinterpret_cast<const uint32_t *>(data) + (co >> 2);
   const uint32_t sp = (poff & 3u) * 8u, sc = (co & 3u) * 8u;
   uint32_t hp = wp[1], hc = wc[1];
   if (__funnelshift_r(wc[0], hc, sc) != v) return;
+  budget--;
+  if (m >= 4 && data[co + m] != data[poff + m]) {  // cannot beat the best so far
+    if (m >= good && budget > 1) budget = 1;
+    return;
+  }
   uint32_t mc = 4;
 #pragma unroll 1
   for (int j = 2; j <= LZ_LANE_CAP / 4; j++) {
@@ -404,12 +442,23 @@ __device__ __forceinline__ void lz2_eval(const uint8_t *data, uint32_t poff, uin
     m = mc;
     dist = dcand;
   }
+  if (m >= good && budget > 1) budget = 1;
+}
+
+// the four ways of one bucket, most recent first
+__device__ __forceinline__ void lz2_try_bucket(const uint8_t *data, uint32_t poff, uint32_t q, uint32_t v, uint32_t limit,
+                                               uint32_t stop, uint2 b, uint32_t good, uint32_t &m, uint32_t &dist, int &budget) {
+  const uint32_t e0 = b.x & 0xffffu, e1 = b.x >> 16, e2 = b.y & 0xffffu, e3 = b.y >> 16;
+  if (e0 != 0xffffu && budget > 0 && m < stop) lz2_eval(data, poff, q, v, limit, (q - e0) & 0xffffu, good, m, dist, budget);
+  if (e1 != 0xffffu && budget > 0 && m < stop) lz2_eval(data, poff, q, v, limit, (q - e1) & 0xffffu, good, m, dist, budget);
+  if (e2 != 0xffffu && budget > 0 && m < stop) lz2_eval(data, poff, q, v, limit, (q - e2) & 0xffffu, good, m, dist, budget);
+  if (e3 != 0xffffu && budget > 0 && m < stop) lz2_eval(data, poff, q, v, limit, (q - e3) & 0xffffu, good, m, dist, budget);
 }
 
 __global__ void __launch_bounds__(LZ_THREADS, 2)
     k_lz2(const uint8_t *__restrict__ src, const ZbChunkDesc *__restrict__ desc, uint2 *__restrict__ masks,
           uint32_t *__restrict__ recs, uint16_t *__restrict__ hist, ZbChunkCheck *__restrict__ chk,
-          const ZbCrcTables *__restrict__ tabs, uint2 *__restrict__ tables, uint32_t n_chunks) {
+          const ZbCrcTables *__restrict__ tabs, uint2 *__restrict__ tables, uint32_t n_chunks, ZbLz2Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *data = smem;
   uint32_t *hist_all = reinterpret_cast<uint32_t *>(smem + LZ2_SM_HIST);
@@ -421,7 +470,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *whist = hist_all + warp * ZB_HIST_WORDS;
   uint32_t *ring = ring_all + warp * LZ2_RING_WINDOWS * ZB_MATCH_SLOTS;
-  uint2 *tab = tables + ((size_t)blockIdx.x * ZB_WARPS_PER_CHUNK + (size_t)warp) * LZ2_BUCKETS;
+  uint2 *cta_tabs = tables + (size_t)blockIdx.x * LZ2_TABLES_PER_CTA * LZ2_BUCKETS;
+  uint2 *own = cta_tabs + (size_t)warp * LZ2_BUCKETS;              // this warp's incremental table
+  uint2 *stat = cta_tabs + (size_t)ZB_WARPS_PER_CHUNK * LZ2_BUCKETS;  // static table of region segment s at stat + s * LZ2_BUCKETS
 
   if (tid == 0) {
     zb_mbar_init(bar, 1);
@@ -436,18 +487,16 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
   uint32_t phase = 0;
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const ZbChunkDesc d = desc[chunk];
-    const uint32_t len = d.len, hb = d.pad;  // pad = bytes of history staged in front of the chunk
+    const uint32_t len = d.len, hb = d.pad;  // pad = bytes of history staged in front of the chunk (a multiple of the segment size)
     const uint8_t *rsrc = src + d.src_off - hb;
     const uint32_t mis = (uint32_t)((uintptr_t)rsrc & 15u);
     const uint32_t off0 = mis + hb;           // chunk position x lives at data[off0 + x]
-    if (tid == 0 && hb + len) zb_stage_chunk(data, rsrc, hb + len, bar);
+    const uint32_t rlen = hb + len;           // staged bytes; region position q = hb + chunk position
+    if (tid == 0 && rlen) zb_stage_chunk(data, rsrc, rlen, bar);
     for (int i = tid; i < ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS; i += LZ_THREADS) hist_all[i] = 0;
-    {  // empty this warp's dictionary
-      uint2 ff = make_uint2(~0u, ~0u);
-      for (int i = lane; i < LZ2_BUCKETS; i += 32) __stcg(&tab[i], ff);
-    }
+    lz2_clear_table(own);
     __syncthreads();
-    if (hb + len) {
+    if (rlen) {
       zb_mbar_wait(bar, phase);
       phase ^= 1u;
     }
@@ -476,64 +525,72 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
       __syncwarp();
     }
 
-    if (b0 < len) {
-      const uint32_t rlen = hb + len;  // staged bytes; region position q = hb + chunk position
-      {
-        // pre-seed with (up to) the 32 KiB before this sub-chunk
-        const uint32_t q0 = hb + b0;
+    // ---- phase 1: static tables of every segment that precedes some sub-chunk of this chunk ----
+    {
+      const uint32_t nseg = (rlen + LZ2_SEG_BYTES - 1) / LZ2_SEG_BYTES;  // segments of the region; the last is never history
+      for (uint32_t sg = (uint32_t)warp; sg + 1 < nseg; sg += ZB_WARPS_PER_CHUNK) {
+        uint2 *tab = stat + (size_t)sg * LZ2_BUCKETS;
+        lz2_clear_table(tab);
+        __syncwarp();
+        const uint32_t q0 = sg * LZ2_SEG_BYTES, q1 = q0 + LZ2_SEG_BYTES;  // a full segment (only the last one can be short)
         uint32_t grp;
-        for (uint32_t s = q0 > LZ2_HIST ? q0 - LZ2_HIST : 0u; s < q0; s += 32) {
+        for (uint32_t s = q0; s < q1; s += 32) {
           const uint32_t q = s + (uint32_t)lane;
-          const bool can = q < q0 && q + 4 <= rlen;
           const uint32_t v = zb_ld32_unaligned(data, mis + q);
-          (void)lz2_probe_insert(tab, v, can, s, grp);
+          (void)lz2_probe_insert(tab, lz2_hash(v), q + 4 <= rlen, s, grp);
         }
       }
+    }
+    __syncthreads();  // every static table is complete (bar.sync orders the global writes inside the CTA)
+
+    // ---- phase 2: parse ----
+    if (b0 < len) {
+      const uint32_t myseg = (hb + b0) / LZ2_SEG_BYTES;
       uint32_t entry = b0;
       uint32_t ksel = 0, kism = 0;
       uint2 *gmask = masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
-      uint32_t *grecs = recs + (size_t)chunk * ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS;
+      uint32_t *grecs = recs + (size_t)chunk * ZB_RECS_PER_CHUNK + (size_t)warp * ZB_RECS_PER_SUB;
+      uint32_t rec_base = 0;
       for (uint32_t wb = b0; wb < b1; wb += 32) {
         const uint32_t win = wb >> 5, slot = win & (LZ2_RING_WINDOWS - 1u);
         const uint32_t p = wb + (uint32_t)lane;
         const uint32_t q = hb + p;               // region position of this lane
         const uint32_t v = zb_ld32_unaligned(data, off0 + p);
         const bool can = (p + 4 <= len);
+        const uint32_t h = lz2_hash(v);
+        const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
+        const bool search = entry < wb + 32 && can && p >= entry && limit >= ZB_MIN_MATCH;
+        // history buckets: four independent loads, in flight while the own table is updated
+        uint2 hbk[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          hbk[j] = make_uint2(~0u, ~0u);
+          if (search && myseg > (uint32_t)j) hbk[j] = __ldcg(&stat[(size_t)(myseg - 1u - (uint32_t)j) * LZ2_BUCKETS + h]);
+        }
         uint32_t grp;
-        const uint2 bucket = lz2_probe_insert(tab, v, can, hb + wb, grp);
+        const uint2 bucket = lz2_probe_insert(own, h, can, q - (uint32_t)lane, grp);
         uint32_t sel = 0, ism = 0;
         if (entry < wb + 32) {
           const uint32_t nvalid = min(32u, b1 - wb);
           const uint32_t cur = entry - wb;
-          const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
           uint32_t m = 0, dist = 1;
-          if (can && p >= entry && limit >= ZB_MIN_MATCH) {
-            // candidates, nearest first: the closest same-hash position inside this window, then
-            // the bucket's four ways (most recent first).  Once a match of 8+ is in hand only one
-            // more candidate is tried (the reference quarters its chain budget there, lz77.nim:104).
-            const uint32_t poff = off0 + p;
+          int budget = search ? (int)prm.maxcand : 0;
+          const uint32_t poff = off0 + p;
+          const uint32_t stop = min(limit, (uint32_t)LZ_LANE_CAP);
+          if (search) {
+            // nearest first: the closest same-hash position inside this window, then the own bucket
             const uint32_t lower = grp & ((1u << lane) - 1u);
-            if (lower) lz2_eval(data, poff, q, v, limit, (uint32_t)lane - (uint32_t)(31 - __clz((int)lower)), m, dist);
-            const uint32_t e0 = bucket.x & 0xffffu, e1 = bucket.x >> 16, e2 = bucket.y & 0xffffu, e3 = bucket.y >> 16;
-            const uint32_t stop = min(limit, (uint32_t)LZ_LANE_CAP);
-            int budget = 4;
-            if (e0 != 0xffffu && m < stop) {
-              lz2_eval(data, poff, q, v, limit, (q - e0) & 0xffffu, m, dist);
-              if (m >= 8) budget = 2;
-            }
-            if (e1 != 0xffffu && m < stop && budget > 1) {
-              lz2_eval(data, poff, q, v, limit, (q - e1) & 0xffffu, m, dist);
-              if (m >= 8) budget = min(budget, 3);
-            }
-            if (e2 != 0xffffu && m < stop && budget > 2) {
-              lz2_eval(data, poff, q, v, limit, (q - e2) & 0xffffu, m, dist);
-              if (m >= 8) budget = min(budget, 3);
-            }
-            if (e3 != 0xffffu && m < stop && budget > 3) lz2_eval(data, poff, q, v, limit, (q - e3) & 0xffffu, m, dist);
+            if (lower) lz2_eval(data, poff, q, v, limit, (uint32_t)lane - (uint32_t)(31 - __clz((int)lower)), prm.good, m, dist, budget);
+            lz2_try_bucket(data, poff, q, v, limit, stop, bucket, prm.good, m, dist, budget);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (__any_sync(ZB_FULL, budget > 0 && m < stop))
+              lz2_try_bucket(data, poff, q, v, limit, stop, hbk[j], prm.good, m, dist, budget);
           }
           // one-step lazy evaluation (zlib's max_lazy idea)
           const uint32_t mnext = __shfl_down_sync(ZB_FULL, m, 1);
-          if (lane < 31 && m != 0 && m < LZ2_LAZY_MAX && mnext > m) m = 0;
+          if (lane < 31 && m != 0 && m < prm.lazy && mnext > m) m = 0;
           uint32_t endw;
           lz_select(data, off0, wb, b1, cur, nvalid, m, dist, ring + slot * ZB_MATCH_SLOTS, sel, ism, endw);
           entry = wb + max(endw, nvalid);
@@ -547,7 +604,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           const uint32_t bwin = win - slot + (uint32_t)lane;
           lz_batch_pass(data + off0 + (bwin << 5), (uint32_t)lane <= slot, ksel, kism,
                         ring + ((uint32_t)lane & (LZ2_RING_WINDOWS - 1u)) * ZB_MATCH_SLOTS, whist, gmask + bwin,
-                        grecs + bwin * ZB_MATCH_SLOTS);
+                        grecs, rec_base);
           ksel = kism = 0;
           __syncwarp();
         }
@@ -571,7 +628,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
       cc.adler = zb_adler_from_sums(a % ZB_ADLER_MOD, b % ZB_ADLER_MOD, len);
       chk[chunk] = cc;
     }
-    __syncthreads();  // shared memory is reused by the next chunk
+    __syncthreads();  // shared memory and the CTA's tables are reused by the next chunk
   }
 }
 
@@ -693,30 +750,84 @@ __global__ void __launch_bounds__(128)
 
 // ------------------------------------------------------------------------------------
 #define PK_ROW_WORDS 17   // a 32-byte window encodes to at most 32 x 15 bits = 15 words (+ partial)
-#define PK_SM_CODES_BYTES ((288 + 32) * 4)
-#define PK_SM_ROWS_BYTES (ZB_WARPS_PER_CHUNK * PK_ROW_WORDS * 32 * 4)
+#define PK_STG_WORDS (PK_ROW_WORDS * 32 + 4)   // one batch of 32 rows + the carried partial word
+#define PK_EDGES 10       // piece boundaries of a chunk: header+warp 0, warps 1..7, tail, end
 
-// OR `nbits` (<= 32) bits of v into the global bitstream at absolute bit position gb.
-__device__ __forceinline__ void or_bits_global(uint32_t *dstw, uint64_t gb, uint32_t v, uint32_t nbits) {
-  if (nbits == 0) return;
-  if (nbits < 32) v &= (1u << nbits) - 1u;
-  uint64_t word = gb >> 5;
-  uint32_t sh = (uint32_t)(gb & 31u);
-  atomicOr(&dstw[word], v << sh);
-  if (sh && sh + nbits > 32) atomicOr(&dstw[word + 1], v >> (32u - sh));
+// Token -> bits, written with plain coalesced stores (no zero-fill, no global atomics).
+// A chunk's stream is a sequence of bit PIECES: [block header + warp 0's tokens], warp 1..7's
+// tokens, [end-of-block + byte-aligning tail]; k_huff fixed where each one starts.  A warp turns
+// 32 windows at a time into bits -- one LANE per 32-byte window walks the window's tokens and
+// concatenates codes into its private row of shared memory; a warp prefix sum of the 32 row
+// lengths places the rows -- and ORs the rows into a warp-private staging buffer in shared
+// memory that is aligned with the 32-bit words of the output; complete words leave with one
+// coalesced store per 32 words, the partial last word is carried into the next batch.  Only the
+// words that hold a piece boundary (at most ten per chunk, and the chunk's first and last word,
+// which neighbouring chunks / the framing bytes share at byte granularity) are merged in a small
+// shared-memory edge table and written at the end, byte-wise where the word leaves the chunk.
+struct PkEdges {
+  uint32_t word[PK_EDGES];   // relative word index that holds boundary k (sorted)
+  uint32_t val[PK_EDGES];
+  uint32_t used[PK_EDGES];
+};
+__device__ __forceinline__ void pk_edge_or(PkEdges *ed, uint32_t relword, uint32_t bits) {
+  int k = 0;
+#pragma unroll
+  for (int i = PK_EDGES - 1; i >= 0; i--)
+    if (ed->word[i] == relword) k = i;   // the first boundary in this word owns the slot
+  atomicOr(&ed->val[k], bits);
+  ed->used[k] = 1u;
 }
 
-// Token -> bits.  One LANE per 32-byte window: the lane walks the window's tokens,
-// concatenating codes into its private row of shared memory; a warp prefix sum of the
-// 32 row lengths gives every row its bit offset (the sub-chunk's own offset was fixed by
-// k_huff), and the rows are OR-ed into the zero-filled output stream.
+// One warp: append a batch of rows (lane i: `mybits` bits in rows[k * 32 + i]) at relative bit
+// `bitcur`, flush the words that became complete.  stg[0] is relative word sw0.
+__device__ __forceinline__ void pk_append(uint32_t *stg, const uint32_t *rows, uint32_t mybits, uint32_t &bitcur,
+                                          uint32_t &sw0, uint32_t piece_start, uint32_t *dstw_rel, PkEdges *ed) {
+  const int lane = zb_lane();
+  uint32_t incl = mybits;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(ZB_FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(ZB_FULL, incl, 31);
+  uint32_t pos = bitcur + incl - mybits - sw0 * 32u;   // bit offset of this lane's row inside stg
+  for (uint32_t k = 0; k * 32u < mybits; k++) {
+    const uint32_t nb = min(32u, mybits - k * 32u);
+    uint32_t v = rows[k * 32 + lane];
+    if (nb < 32u) v &= (1u << nb) - 1u;
+    const uint32_t wi = pos >> 5, sh = pos & 31u;
+    atomicOr(&stg[wi], v << sh);
+    if (sh && sh + nb > 32u) atomicOr(&stg[wi + 1u], v >> (32u - sh));
+    pos += 32u;
+  }
+  __syncwarp();
+  bitcur += total;
+  const uint32_t nfull = (bitcur >> 5) - sw0;
+  const uint32_t carry = stg[nfull];
+  for (uint32_t i = (uint32_t)lane; i < nfull; i += 32) {
+    const uint32_t rel = sw0 + i, val = stg[i];
+    if (rel * 32u >= piece_start) dstw_rel[rel] = val;   // wholly inside this piece
+    else pk_edge_or(ed, rel, val);                        // the piece's first word, shared with its predecessor
+    stg[i] = 0u;
+  }
+  __syncwarp();
+  if (lane == 0 && nfull) {
+    stg[nfull] = 0u;
+    stg[0] = carry;
+  }
+  sw0 += nfull;
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(LZ_THREADS)
     k_pack(ZbCompressWork w) {
   __shared__ uint32_t codes[288 + 32];  // [0,288) litlen, [288,320) dist: code | len << 16
   __shared__ uint32_t rows_all[ZB_WARPS_PER_CHUNK * PK_ROW_WORDS * 32];
+  __shared__ uint32_t stg_all[ZB_WARPS_PER_CHUNK * PK_STG_WORDS];
+  __shared__ PkEdges ed;
 
-  // a launch group whose output would end beyond the destination is not written at all (its
-  // extent was not zero-filled either); the host call then returns DST_TOO_SMALL
+  // a launch group whose output would end beyond the destination is not written at all;
+  // the host call then returns DST_TOO_SMALL
   if (w.member_off[w.n_members] > w.dst_cap) return;
   const uint32_t chunk = blockIdx.x;
   const ZbChunkDesc d = w.desc[chunk];
@@ -725,18 +836,21 @@ __global__ void __launch_bounds__(LZ_THREADS)
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t btype = cb->block_type;
   const uint64_t out0 = w.chunk_off[chunk];  // byte offset of this chunk's deflate bytes
-  uint32_t *dstw = reinterpret_cast<uint32_t *>(w.dst);
   const uint8_t *src = w.src + d.src_off;
 
   for (int i = tid; i < 320; i += LZ_THREADS) codes[i] = i < 288 ? cb->ll[i] : cb->dd[i - 288];
+  for (int i = tid; i < ZB_WARPS_PER_CHUNK * PK_STG_WORDS; i += LZ_THREADS) stg_all[i] = 0u;
 
-  // ---- framing bytes (zippy.nim:21-42, 50-58, 60-78) ----
+  // ---- framing bytes (zippy.nim:21-42, 50-58, 60-78): every byte written explicitly ----
   if (tid == 32 && (d.flags & ZB_CHUNK_FIRST)) {
     uint8_t *h = w.dst + w.member_off[d.member];
     if (w.data_format == ZB_DF_GZIP) {
       h[0] = 31; h[1] = 139; h[2] = 8; h[3] = 8;  // FNAME flag set, as the reference does
+      h[4] = h[5] = h[6] = h[7] = 0;              // MTIME
+      h[8] = 0; h[9] = 0;                         // XFL, OS (zippy.nim:22-27 writes zeros)
       uint32_t k = w.fname_len ? w.fname_len[d.member] : 0u;
       for (uint32_t i = 0; i < k; i++) h[10 + i] = (uint8_t)(97 + i);
+      h[10 + k] = 0;
     } else if (w.data_format == ZB_DF_ZLIB) {
       h[0] = 0x78; h[1] = 0x01;
     }
@@ -752,7 +866,6 @@ __global__ void __launch_bounds__(LZ_THREADS)
       t[0] = (uint8_t)(ck >> 24); t[1] = (uint8_t)(ck >> 16); t[2] = (uint8_t)(ck >> 8); t[3] = (uint8_t)ck;
     }
   }
-  __syncthreads();
 
   if (btype == 0) {
     // stored blocks (deflate.nim:179-205): 1 header byte, LEN, NLEN, bytes
@@ -771,111 +884,167 @@ __global__ void __launch_bounds__(LZ_THREADS)
     return;
   }
 
+  // ---- geometry: bits are counted from the 32-bit word that holds the chunk's first byte ----
   const uint64_t gbit0 = out0 * 8ull;
-  // ---- block header + dynamic tables ----
-  if (warp == 0) {
-    uint32_t hb = cb->hdr_bits;
-    for (uint32_t k = (uint32_t)lane; k * 32u < hb; k += 32) {
-      uint32_t piece = 0;
-      for (int j = 0; j < 4; j++) piece |= (uint32_t)cb->hdr[k * 4 + j] << (8 * j);
-      uint32_t nb = min(32u, hb - k * 32u);
-      or_bits_global(dstw, gbit0 + k * 32ull, piece, nb);
-    }
+  const uint32_t B0 = (uint32_t)(gbit0 & 31ull);                       // relative bit of the chunk's first bit
+  uint32_t *dstw_rel = reinterpret_cast<uint32_t *>(w.dst) + (gbit0 >> 5);  // relative word 0
+  const uint32_t end_bit = B0 + cb->total_bytes * 8u;
+  if (tid < PK_EDGES) {
+    uint32_t b = tid == 0 ? B0 : tid <= 7 ? B0 + cb->warp_bit_start[tid] : tid == 8 ? B0 + cb->eob_bit_start : end_bit;
+    ed.word[tid] = b >> 5;
+    ed.val[tid] = 0u;
+    ed.used[tid] = 0u;
   }
-  // ---- end of block (+ byte-aligning empty stored block when more chunks follow) ----
-  if (tid == 96) {
-    uint32_t e = codes[256];
-    uint64_t eb = gbit0 + cb->eob_bit_start;
-    or_bits_global(dstw, eb, e & 0xffffu, e >> 16);
-    if (!cb->is_final) {
-      uint64_t after = cb->eob_bit_start + (e >> 16) + 3u;
-      uint64_t byte_al = (after + 7u) >> 3;
-      uint8_t *o = w.dst + out0 + byte_al;
-      o[2] = 0xff;
-      o[3] = 0xff;
-    }
-  }
-  // ---- tokens of this warp's sub-chunk ----
-  const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES;
-  if (b0 >= len) return;
-  const uint32_t b1 = min(b0 + ZB_SUB_BYTES, len);
-  uint32_t *rows = rows_all + warp * PK_ROW_WORDS * 32;  // word k of lane i at rows[k * 32 + i]
-  uint64_t bitpos = gbit0 + cb->warp_bit_start[warp];
-  const uint2 *gmask = w.masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
-  const uint32_t *grecs = w.recs + (size_t)chunk * ZB_WINDOWS_PER_CHUNK * ZB_MATCH_SLOTS;
-  const uint32_t nwin = (b1 - b0 + 31u) >> 5;
-  for (uint32_t wbase = 0; wbase < nwin; wbase += 32) {
-    const uint32_t widx = wbase + (uint32_t)lane;      // window within the sub-chunk
-    const uint32_t win = (b0 >> 5) + widx;              // window within the chunk
-    uint2 mk = make_uint2(0u, 0u);
-    if (widx < nwin) mk = gmask[win];
-    uint32_t s = mk.x;
-    const uint32_t im = mk.y;
-    const uint8_t *wdata = src + ((size_t)win << 5);
-    const uint32_t *wrec = grecs + (size_t)win * ZB_MATCH_SLOTS;
-    uint64_t acc = 0;
-    uint32_t accn = 0, nw = 0, mcnt = 0;
-    while (s) {
-      const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
-      s &= s - 1;
-      uint32_t v1, n1;
-      if ((im >> bit) & 1u) {
-        const uint32_t rec = wrec[mcnt++];
-        const uint32_t lc = rec & 31u, dc = (rec >> 10) & 31u;
-        const uint32_t e1 = codes[257 + lc], e2 = codes[288 + dc];
-        v1 = (e1 & 0xffffu) | (((rec >> 5) & 31u) << (e1 >> 16));
-        n1 = (e1 >> 16) + (uint32_t)zb_len_extra_bits((int)lc);
-        acc |= (uint64_t)v1 << accn;
-        accn += n1;
-        if (accn >= 32) {
-          rows[nw * 32 + lane] = (uint32_t)acc;
-          nw++;
-          acc >>= 32;
-          accn -= 32;
+  __syncthreads();
+
+  // ---- this warp's piece ----
+  const uint32_t piece_start = warp == 0 ? B0 : B0 + cb->warp_bit_start[warp];
+  {
+    uint32_t *rows = rows_all + warp * PK_ROW_WORDS * 32;  // word k of lane i at rows[k * 32 + i]
+    uint32_t *stg = stg_all + warp * PK_STG_WORDS;
+    uint32_t bitcur = piece_start, sw0 = piece_start >> 5;
+    if (warp == 0) {
+      // block header + dynamic tables: 32 bits per lane and batch
+      const uint32_t hb = cb->hdr_bits;
+      for (uint32_t base = 0; base < hb; base += 1024u) {
+        const uint32_t k = (base >> 5) + (uint32_t)lane;
+        uint32_t piece = 0, nb = 0;
+        if (k * 32u < hb) {
+          for (int j = 0; j < 4; j++) piece |= (uint32_t)cb->hdr[k * 4 + j] << (8 * j);
+          nb = min(32u, hb - k * 32u);
         }
-        v1 = (e2 & 0xffffu) | ((rec >> 15) << (e2 >> 16));
-        n1 = (e2 >> 16) + (uint32_t)zb_dist_extra_bits((int)dc);
-      } else {
-        const uint32_t e = codes[wdata[bit]];
-        v1 = e & 0xffffu;
-        n1 = e >> 16;
-      }
-      acc |= (uint64_t)v1 << accn;
-      accn += n1;
-      if (accn >= 32) {
-        rows[nw * 32 + lane] = (uint32_t)acc;
-        nw++;
-        acc >>= 32;
-        accn -= 32;
+        rows[lane] = piece;
+        __syncwarp();
+        pk_append(stg, rows, nb, bitcur, sw0, piece_start, dstw_rel, &ed);
       }
     }
-    if (accn) rows[nw * 32 + lane] = (uint32_t)acc;
-    const uint32_t mybits = nw * 32u + accn;
-    uint32_t incl = mybits;
+    const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES;
+    if (b0 < len) {
+      const uint32_t b1 = min(b0 + ZB_SUB_BYTES, len);
+      const uint2 *gmask = w.masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
+      const uint32_t *grecs = w.recs + (size_t)chunk * ZB_RECS_PER_CHUNK + (size_t)warp * ZB_RECS_PER_SUB;
+      const uint32_t nwin = (b1 - b0 + 31u) >> 5;
+      uint32_t rec_base = 0;
+      for (uint32_t wbase = 0; wbase < nwin; wbase += 32) {
+        const uint32_t widx = wbase + (uint32_t)lane;      // window within the sub-chunk
+        const uint32_t win = (b0 >> 5) + widx;              // window within the chunk
+        uint2 mk = make_uint2(0u, 0u);
+        if (widx < nwin) mk = gmask[win];
+        uint32_t s = mk.x;
+        const uint32_t im = mk.y;
+        // this window's records: dense stream in window order
+        const uint32_t nmatch = (uint32_t)__popc(im);
+        uint32_t rincl = nmatch;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(ZB_FULL, incl, o);
-      if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(ZB_FULL, rincl, o);
+          if (lane >= o) rincl += t;
+        }
+        const uint32_t *wrec = grecs + rec_base + rincl - nmatch;
+        rec_base += __shfl_sync(ZB_FULL, rincl, 31);
+        const uint8_t *wdata = src + ((size_t)win << 5);
+        uint64_t acc = 0;
+        uint32_t accn = 0, nw = 0, mcnt = 0;
+        while (s) {
+          const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
+          s &= s - 1;
+          uint32_t v1, n1;
+          if ((im >> bit) & 1u) {
+            const uint32_t rec = wrec[mcnt++];
+            const uint32_t lc = rec & 31u, dc = (rec >> 10) & 31u;
+            const uint32_t e1 = codes[257 + lc], e2 = codes[288 + dc];
+            v1 = (e1 & 0xffffu) | (((rec >> 5) & 31u) << (e1 >> 16));
+            n1 = (e1 >> 16) + (uint32_t)zb_len_extra_bits((int)lc);
+            acc |= (uint64_t)v1 << accn;
+            accn += n1;
+            if (accn >= 32) {
+              rows[nw * 32 + lane] = (uint32_t)acc;
+              nw++;
+              acc >>= 32;
+              accn -= 32;
+            }
+            v1 = (e2 & 0xffffu) | ((rec >> 15) << (e2 >> 16));
+            n1 = (e2 >> 16) + (uint32_t)zb_dist_extra_bits((int)dc);
+          } else {
+            const uint32_t e = codes[wdata[bit]];
+            v1 = e & 0xffffu;
+            n1 = e >> 16;
+          }
+          acc |= (uint64_t)v1 << accn;
+          accn += n1;
+          if (accn >= 32) {
+            rows[nw * 32 + lane] = (uint32_t)acc;
+            nw++;
+            acc >>= 32;
+            accn -= 32;
+          }
+        }
+        if (accn) rows[nw * 32 + lane] = (uint32_t)acc;
+        __syncwarp();
+        pk_append(stg, rows, nw * 32u + accn, bitcur, sw0, piece_start, dstw_rel, &ed);
+      }
     }
-    const uint32_t total = __shfl_sync(ZB_FULL, incl, 31);
-    uint64_t gb = bitpos + (incl - mybits);
-    for (uint32_t k = 0; k * 32u < mybits; k++) {
-      or_bits_global(dstw, gb, rows[k * 32 + lane], min(32u, mybits - k * 32u));
-      gb += 32;
+    // the piece's last, partial word (shared with its successor)
+    if (lane == 0 && (bitcur & 31u)) pk_edge_or(&ed, sw0, stg[0]);
+  }
+  // ---- end of block + tail: pad to a byte (final block) or the byte-aligning empty stored block
+  //      000 + pad + 00 00 ff ff (more chunks of this member follow) ----
+  if (tid == 96) {
+    const uint32_t e = codes[256];
+    uint32_t pos = B0 + cb->eob_bit_start;
+    unsigned long long tv = (unsigned long long)(e & 0xffffu);
+    uint32_t nb = e >> 16;
+    if (!cb->is_final) {
+      nb += 3u;
+      nb += (8u - ((pos + nb) & 7u)) & 7u;   // to the byte boundary
+      tv |= 0xffff0000ull << nb;
+      nb += 32u;
+    } else {
+      nb += (8u - ((pos + nb) & 7u)) & 7u;
     }
-    bitpos += total;
+    while (nb) {
+      const uint32_t rel = pos >> 5, sh = pos & 31u, take = min(nb, 32u - sh);
+      const uint32_t bits = (uint32_t)(tv & ((1ull << take) - 1ull)) << sh;
+      if (sh == 0 && take == 32u) dstw_rel[rel] = bits;
+      else pk_edge_or(&ed, rel, bits);
+      tv >>= take;
+      pos += take;
+      nb -= take;
+    }
+  }
+  __syncthreads();
+  // ---- the words that hold piece boundaries: whole where they lie inside the chunk, byte-wise at its two ends ----
+  if (tid < PK_EDGES && ed.used[tid] && (tid == 0 || ed.word[tid] != ed.word[tid - 1])) {
+    const uint32_t rel = ed.word[tid], val = ed.val[tid];
+    const uint32_t lo = rel * 32u, hi = lo + 32u;
+    if (lo >= B0 && hi <= end_bit) dstw_rel[rel] = val;
+    else {
+      uint8_t *bp = reinterpret_cast<uint8_t *>(dstw_rel + rel);
+      for (uint32_t j = 0; j < 4; j++)
+        if (lo + 8u * j >= B0 && lo + 8u * j + 8u <= end_bit) bp[j] = (uint8_t)(val >> (8u * j));
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------
 static bool zb_is_lz_level(int level) { return level == -1 || level >= 2; }
+// Search effort per level, after the reference's configurationTable (internal.nim:177-189: good / lazy / nice /
+// chain per level; lz77.nim:97-109 walks `chain` links and quarters the rest at `good`).  Here the candidates
+// come from 4-way buckets instead of a chain, so the budget is the number of VERIFIED candidates per position,
+// `good` keeps its meaning and `lazy` is the one-step lazy threshold; effort and compressed size are
+// monotone in the level.
+ZbLz2Params zb_lz2_params(int level) {
+  static const ZbLz2Params table[10] = {{8, 8, 16},  {8, 8, 16},  {2, 4, 0},   {3, 4, 6},   {4, 4, 8},
+                                        {6, 8, 16},  {8, 8, 16},  {12, 8, 32}, {21, 16, 32}, {21, 32, 64}};
+  return table[(level >= 2 && level <= 9) ? level : 6];  // -1 (Default) = level 6
+}
 size_t zb_lz2_table_bytes(int *grid_out) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = 2 * sms;
   if (grid_out) *grid_out = grid;
-  return (size_t)grid * ZB_WARPS_PER_CHUNK * LZ2_BUCKETS * sizeof(uint2);
+  return (size_t)grid * LZ2_TABLES_PER_CTA * LZ2_BUCKETS * sizeof(uint2);
 }
 // function attributes are per device: zb200_init calls this once for the ctx's device
 cudaError_t zb_setup_deflate_attrs() {
@@ -891,7 +1060,7 @@ cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s) {
     (void)zb_lz2_table_bytes(&grid);
     if ((uint32_t)grid > w.n_chunks) grid = (int)w.n_chunks;
     k_lz2<<<grid, LZ_THREADS, LZ2_SM_TOTAL, s>>>(w.src, w.desc, w.masks, w.recs, w.hist, w.chk, w.tabs, w.lz2_tables,
-                                                 w.n_chunks);
+                                                 w.n_chunks, zb_lz2_params(w.level));
   } else if (w.level == -2 || w.level == 0) {
     k_lz<0><<<w.n_chunks, LZ_THREADS, LZ_SM_TOTAL, s>>>(w.src, w.desc, w.masks, w.recs, w.hist, w.chk, w.tabs);
   } else {
@@ -907,26 +1076,6 @@ cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s) {
 cudaError_t zb_launch_scan(const ZbCompressWork &w, cudaStream_t s) {
   k_scan<<<1, SCAN_THREADS, 0, s>>>(w);
   if (w.n_members) k_member_check<<<(w.n_members + 3) / 4, 128, 0, s>>>(w);  // one warp per member
-  return cudaGetLastError();
-}
-__global__ void __launch_bounds__(256) k_zero_range(uint8_t *dst, const uint64_t *lo_p, const uint64_t *hi_p, uint64_t cap) {
-  if (*hi_p > cap) return;  // the group does not fit: k_pack skips it too
-  const uint64_t lo = (*lo_p + 3ull) & ~3ull, hi = (*hi_p + 3ull) & ~3ull;  // the word holding *lo belongs to the previous group
-  if (hi <= lo) return;
-  uint32_t *w = reinterpret_cast<uint32_t *>(dst + lo);
-  const uint64_t nwords = (hi - lo) >> 2;
-  const uint64_t head = min(nwords, (uint64_t)(((16u - (uint32_t)((uintptr_t)w & 15u)) & 15u) >> 2));
-  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
-  if (tid < head) w[tid] = 0u;
-  uint4 *v = reinterpret_cast<uint4 *>(w + head);
-  const uint64_t nvec = (nwords - head) >> 2;
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (uint64_t i = tid; i < nvec; i += stride) v[i] = z;
-  const uint64_t done = head + nvec * 4;
-  if (tid < nwords - done) w[done + tid] = 0u;
-}
-cudaError_t zb_launch_zero_range(uint8_t *dst, const uint64_t *lo, const uint64_t *hi, uint64_t cap, cudaStream_t s) {
-  k_zero_range<<<148 * 8, 256, 0, s>>>(dst, lo, hi, cap);
   return cudaGetLastError();
 }
 cudaError_t zb_launch_pack(const ZbCompressWork &w, cudaStream_t s) {

@@ -26,13 +26,13 @@ struct ZbChunkCheck {
 // All device scratch for one compress batch (arrays sized by n_chunks / n_members).
 struct ZbCompressWork {
   const uint8_t *src;          // device
-  uint8_t *dst;                // device; each launch group's extent is zero-filled before it is packed
+  uint8_t *dst;                // device, 4-byte aligned; every byte of the output is written explicitly by k_pack
   uint64_t dst_cap;            // bytes (multiple of 4): a group that would end beyond this is not written at all
   const ZbChunkDesc *desc;     // [n_chunks]
   const uint32_t *member_first;// [n_members + 1] first chunk index of each member
   const uint8_t *fname_len;    // [n_members] gzip FNAME letters (0..25) or nullptr
   uint2 *masks;                // [n_chunks][2048] (token-start mask, is-match mask) per 32-byte window
-  uint32_t *recs;              // [n_chunks][2048][8] match records
+  uint32_t *recs;              // [n_chunks][8 sub-chunks][2048] match records, one dense stream per sub-chunk
   uint16_t *hist;              // [n_chunks][8][316]
   ZbChunkCheck *chk;           // [n_chunks]
   ZbCodebook *cb;              // [n_chunks]
@@ -44,7 +44,7 @@ struct ZbCompressWork {
   const uint64_t *out_base_ptr;// ... or, when non-null, a device word holding it (the previous group's end),
                                // so consecutive groups can be enqueued without a host round trip
   const ZbCrcTables *tabs;     // device
-  uint2 *lz2_tables;           // k_lz2 dictionaries: [grid][8 warps][4096 buckets x 4 ways] (LZ levels only)
+  uint2 *lz2_tables;           // k_lz2 dictionaries: [grid][8 own + 12 segment tables][2048 buckets x 4 ways] (LZ levels only)
   uint32_t n_chunks, n_members;
   int level, data_format;
 };
@@ -52,16 +52,17 @@ struct ZbCompressWork {
 // per-device kernel attributes (dynamic shared memory limits); call with the device current
 cudaError_t zb_setup_deflate_attrs();
 cudaError_t zb_setup_inflate_attrs();
+struct ZbLz2Params {
+  uint32_t maxcand;  // verified candidates per position
+  uint32_t good;     // a match this long leaves room for one more candidate only
+  uint32_t lazy;     // matches shorter than this yield to a longer match at the next position (0: greedy)
+};
+ZbLz2Params zb_lz2_params(int level);
 size_t zb_lz2_table_bytes(int *grid_out);
 cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_huff(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_scan(const ZbCompressWork &w, cudaStream_t s);
 cudaError_t zb_launch_pack(const ZbCompressWork &w, cudaStream_t s);
-// zero dst[ceil4(*lo) .. ceil4(*hi)): the packer ORs bits into zeros; the extent of a launch group's
-// output is only known on the device (k_scan), so the fill reads it there; nothing at or beyond cap
-// is touched (a group that does not fit is not written: the call then fails with DST_TOO_SMALL)
-cudaError_t zb_launch_zero_range(uint8_t *dst, const uint64_t *lo, const uint64_t *hi, uint64_t cap, cudaStream_t s);
-
 // ---- inflate ----
 struct ZbInflateWork {
   const uint8_t *src;          // device
