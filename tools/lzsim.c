@@ -29,6 +29,8 @@
 #define MAXM 258
 
 static int P_sub = 8192, P_seg = 8192, P_sbits = 10, P_slong = 0, P_sways = 1, P_obits = 10, P_oways = 2, P_olong = 0;
+static int P_slotmode = 0;
+static int P_ownstatic = 0, P_visit = 1000, P_back = 4;
 static int P_preseed = 0, P_hist = 32768, P_lazy = 16, P_min4far = 0, P_near = 1, P_good = 8, P_maxcand = 64, P_minlen = 4;
 
 static const uint8_t *D;   // whole file
@@ -103,9 +105,9 @@ static void tok_match(int len, int dist) {
 }
 
 // ---- dictionaries ----
-typedef struct { uint32_t *e; int bits, ways, nbytes; } Tab;   // entries: position + 1 (0 = empty), ways most recent first
+typedef struct { uint32_t *e; int bits, ways, nbytes, slot; } Tab;   // entries: position + 1 (0 = empty), ways most recent first
 static void tab_init(Tab *t, int bits, int ways, int nbytes) {
-  t->bits = bits; t->ways = ways; t->nbytes = nbytes;
+  t->bits = bits; t->ways = ways; t->nbytes = nbytes; t->slot = 0;
   t->e = calloc((size_t)ways << bits, 4);
 }
 static void tab_clear(Tab *t) { memset(t->e, 0, ((size_t)t->ways << t->bits) * 4); }
@@ -114,8 +116,27 @@ static inline uint32_t tab_hash(const Tab *t, size_t p) {
 }
 static inline void tab_push(Tab *t, size_t p) {
   uint32_t *b = t->e + (size_t)tab_hash(t, p) * t->ways;
+  if (t->slot) {   // slot = window index mod ways: plain store, no read-modify-write
+    b[(p >> 5) & (size_t)(t->ways - 1)] = (uint32_t)p + 1;
+    return;
+  }
   for (int k = t->ways - 1; k > 0; k--) b[k] = b[k - 1];
   b[0] = (uint32_t)p + 1;
+}
+
+// entries of bucket b in recency order into out[] (slotmode: by window residue, most recent first)
+static int bucket_cands(const Tab *t, const uint32_t *b, size_t p, size_t *out) {
+  int n = 0;
+  if (!t->slot) {
+    for (int k = 0; k < t->ways; k++) if (b[k]) out[n++] = b[k] - 1;
+    return n;
+  }
+  size_t win = p >> 5;
+  for (int i = 1; i <= t->ways; i++) {
+    uint32_t e = b[(win - (size_t)i) & (size_t)(t->ways - 1)];
+    if (e) out[n++] = e - 1;
+  }
+  return n;
 }
 
 static int match_len(size_t p, size_t c, int limit) {
@@ -136,7 +157,7 @@ int main(int argc, char **argv) {
     OPT("sub", P_sub); OPT("seg", P_seg); OPT("sbits", P_sbits); OPT("slong", P_slong); OPT("sways", P_sways);
     OPT("obits", P_obits); OPT("oways", P_oways); OPT("olong", P_olong); OPT("preseed", P_preseed); OPT("hist", P_hist);
     OPT("lazy", P_lazy); OPT("min4far", P_min4far); OPT("near", P_near); OPT("good", P_good); OPT("maxcand", P_maxcand);
-    OPT("minlen", P_minlen);
+    OPT("minlen", P_minlen); OPT("ownstatic", P_ownstatic); OPT("visit", P_visit); OPT("back", P_back); OPT("slotmode", P_slotmode);
   }
   FILE *f = fopen(argv[1], "rb");
   if (!f) return 2;
@@ -155,8 +176,10 @@ int main(int argc, char **argv) {
     tab_init(&st4[i], P_sbits, P_sways, 4);
     if (P_slong) tab_init(&stl[i], P_sbits, P_sways, P_slong);
   }
+  for (int i = 0; i < nseg_max; i++) st4[i].slot = P_slotmode != 0;
   Tab own4, ownl;
   tab_init(&own4, P_obits, P_oways, 4);
+  own4.slot = P_slotmode == 1;
   if (P_olong) tab_init(&ownl, P_obits, P_oways, P_olong);
 
   double total_bits = 0;
@@ -216,9 +239,9 @@ int main(int argc, char **argv) {
             for (int j = l - 1; j >= 0; j--)
               if (hh[j] == hh[l]) { cands[nc++] = wb + j; break; }
           }
-          {
+          if (!P_ownstatic) {
             uint32_t *b = own4.e + (size_t)hh[l] * own4.ways;
-            for (int k = 0; k < own4.ways; k++) if (b[k]) cands[nc++] = b[k] - 1;
+            nc += bucket_cands(&own4, b, p, cands + nc);
             if (P_olong) {
               uint32_t *bl = ownl.e + (size_t)tab_hash(&ownl, p) * ownl.ways;
               for (int k = 0; k < ownl.ways; k++) if (bl[k]) cands[nc++] = bl[k] - 1;
@@ -226,11 +249,11 @@ int main(int argc, char **argv) {
           }
           if (P_seg) {
             int sp = (int)((p - r0) / P_seg);
-            int back = 32768 / P_seg;
+            int back = P_back;
             // own segment's static table only helps when sub < seg (positions of the segment before this sub-chunk)
-            for (int s = (P_sub < P_seg ? sp : sp - 1); s >= 0 && s >= sp - back && nc < 60; s--) {
+            for (int s = ((P_sub < P_seg || P_ownstatic) ? sp : sp - 1); s >= 0 && s >= sp - back && nc < 60; s--) {
               uint32_t *b = st4[s].e + (size_t)tab_hash(&st4[s], p) * st4[s].ways;
-              for (int k = 0; k < st4[s].ways; k++) if (b[k]) cands[nc++] = b[k] - 1;
+              nc += bucket_cands(&st4[s], b, (size_t)0, cands + nc);
               if (P_slong) {
                 uint32_t *bl = stl[s].e + (size_t)tab_hash(&stl[s], p) * stl[s].ways;
                 for (int k = 0; k < stl[s].ways; k++) if (bl[k]) cands[nc++] = bl[k] - 1;
@@ -238,8 +261,10 @@ int main(int argc, char **argv) {
             }
           }
           uint32_t v = ld32(p);
-          for (int k = 0; k < nc && budget > 0; k++) {
+          int visits = P_visit;
+          for (int k = 0; k < nc && budget > 0 && visits > 0; k++) {
             size_t c = cands[k];
+            visits--;
             if (c >= p || p - c > 32768 || c < r0) continue;
             if (P_sub < P_seg && c >= b0 && 0) continue;
             int dup = 0;

@@ -407,23 +407,39 @@ __device__ __forceinline__ uint2 lz2_probe_insert(uint2 *tab, uint32_t h, bool c
   return old;
 }
 
-// Verify and extend one candidate at distance dcand against the lane's position; keep it if it
-// beats the best match so far.  Position x of the chunk lives at data[off0 + x].  `budget` counts
-// verified candidates (the 4-byte check passed).
-__device__ __forceinline__ void lz2_eval(const uint8_t *data, uint32_t poff, uint32_t q, uint32_t v, uint32_t limit,
-                                         uint32_t dcand, uint32_t good, uint32_t &m, uint32_t &dist, int &budget) {
-  if (dcand == 0 || dcand > ZB_MAX_DIST || dcand > q) return;
-  const uint32_t co = poff - dcand;
-  const uint32_t *wp = reinterpret_cast<const uint32_t *>(data) + (poff >> 2);
-  const uint32_t *wc = reinterpret_cast<const uint32_t *>(data) + (co >> 2);
-  const uint32_t sp = (poff & 3u) * 8u, sc = (co & 3u) * 8u;
-  uint32_t hp = wp[1], hc = wc[1];
-  if (__funnelshift_r(wc[0], hc, sc) != v) return;
+// Per-position constants of the candidate evaluation.
+struct Lz2Pos {
+  const uint32_t *data32;  // the staged region as words
+  uint32_t poff;           // byte offset of the position in the staged region
+  uint32_t q;              // region position (what the tables store, modulo 2^16)
+  uint32_t v;              // its four bytes
+  uint32_t lim;            // candidates at distance 1..lim are inside the window and the region
+  uint32_t limit, stop;    // longest match allowed here; per-lane extension stops at min(limit, lane cap)
+};
+
+// One candidate, stored as a position modulo 2^16.  Cheap rejection first: the distance test also
+// discards empty entries (0xffff aliases a distance that is out of range, or a real position whose
+// bytes are then compared like any other candidate's), then the candidate's four bytes; `budget` counts
+// the candidates that passed (lz77.nim:97-109 counts chain links).  Survivors are extended against
+// shared memory up to the lane cap; the longest match wins, a match of `good` bytes leaves room for
+// one more candidate only.
+__device__ __forceinline__ void lz2_try(const Lz2Pos &P, const uint8_t *data, uint32_t e, uint32_t good, uint32_t &m,
+                                        uint32_t &dist, int &budget) {
+  const uint32_t d = (P.q - e) & 0xffffu;
+  if ((d - 1u) >= P.lim || budget <= 0 || m >= P.stop) return;
+  const uint32_t co = P.poff - d;
+  const uint32_t *wc = P.data32 + (co >> 2);
+  const uint32_t sc = (co & 3u) * 8u;
+  uint32_t hc = wc[1];
+  if (__funnelshift_r(wc[0], hc, sc) != P.v) return;
   budget--;
-  if (m >= 4 && data[co + m] != data[poff + m]) {  // cannot beat the best so far
+  if (m >= 4 && data[co + m] != data[P.poff + m]) {  // cannot beat the best so far
     if (m >= good && budget > 1) budget = 1;
     return;
   }
+  const uint32_t *wp = P.data32 + (P.poff >> 2);
+  const uint32_t sp = (P.poff & 3u) * 8u;
+  uint32_t hp = wp[1];
   uint32_t mc = 4;
 #pragma unroll 1
   for (int j = 2; j <= LZ_LANE_CAP / 4; j++) {
@@ -437,22 +453,12 @@ __device__ __forceinline__ void lz2_eval(const uint8_t *data, uint32_t poff, uin
     hp = np;
     hc = nq;
   }
-  if (mc < LZ_LANE_CAP) mc = min(mc, limit);
+  if (mc < LZ_LANE_CAP) mc = min(mc, P.limit);
   if (mc > m) {
     m = mc;
-    dist = dcand;
+    dist = d;
   }
   if (m >= good && budget > 1) budget = 1;
-}
-
-// the four ways of one bucket, most recent first
-__device__ __forceinline__ void lz2_try_bucket(const uint8_t *data, uint32_t poff, uint32_t q, uint32_t v, uint32_t limit,
-                                               uint32_t stop, uint2 b, uint32_t good, uint32_t &m, uint32_t &dist, int &budget) {
-  const uint32_t e0 = b.x & 0xffffu, e1 = b.x >> 16, e2 = b.y & 0xffffu, e3 = b.y >> 16;
-  if (e0 != 0xffffu && budget > 0 && m < stop) lz2_eval(data, poff, q, v, limit, (q - e0) & 0xffffu, good, m, dist, budget);
-  if (e1 != 0xffffu && budget > 0 && m < stop) lz2_eval(data, poff, q, v, limit, (q - e1) & 0xffffu, good, m, dist, budget);
-  if (e2 != 0xffffu && budget > 0 && m < stop) lz2_eval(data, poff, q, v, limit, (q - e2) & 0xffffu, good, m, dist, budget);
-  if (e3 != 0xffffu && budget > 0 && m < stop) lz2_eval(data, poff, q, v, limit, (q - e3) & 0xffffu, good, m, dist, budget);
 }
 
 __global__ void __launch_bounds__(LZ_THREADS, 2)
@@ -526,18 +532,22 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     }
 
     // ---- phase 1: static tables of every segment that precedes some sub-chunk of this chunk ----
+    // Slot s of a bucket holds the most recent position whose 32-byte window index is s (mod 4): plain
+    // 2-byte stores, no read-modify-write, so a segment costs ten instructions per 32 positions.
     {
       const uint32_t nseg = (rlen + LZ2_SEG_BYTES - 1) / LZ2_SEG_BYTES;  // segments of the region; the last is never history
       for (uint32_t sg = (uint32_t)warp; sg + 1 < nseg; sg += ZB_WARPS_PER_CHUNK) {
         uint2 *tab = stat + (size_t)sg * LZ2_BUCKETS;
         lz2_clear_table(tab);
         __syncwarp();
+        uint16_t *tab16 = reinterpret_cast<uint16_t *>(tab);
         const uint32_t q0 = sg * LZ2_SEG_BYTES, q1 = q0 + LZ2_SEG_BYTES;  // a full segment (only the last one can be short)
-        uint32_t grp;
+#pragma unroll 4
         for (uint32_t s = q0; s < q1; s += 32) {
           const uint32_t q = s + (uint32_t)lane;
           const uint32_t v = zb_ld32_unaligned(data, mis + q);
-          (void)lz2_probe_insert(tab, lz2_hash(v), q + 4 <= rlen, s, grp);
+          // lanes of one window that share a hash write the same slot in one instruction: one of them lands
+          if (q + 4 <= rlen) tab16[(lz2_hash(v) << 2) + ((s >> 5) & 3u)] = (uint16_t)q;
         }
       }
     }
@@ -565,7 +575,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           hbk[j] = make_uint2(~0u, ~0u);
-          if (search && myseg > (uint32_t)j) hbk[j] = __ldcg(&stat[(size_t)(myseg - 1u - (uint32_t)j) * LZ2_BUCKETS + h]);
+          if (search && myseg > (uint32_t)j && prm.nslots > 5u + 4u * (uint32_t)j)
+            hbk[j] = __ldcg(&stat[(size_t)(myseg - 1u - (uint32_t)j) * LZ2_BUCKETS + h]);
         }
         uint32_t grp;
         const uint2 bucket = lz2_probe_insert(own, h, can, q - (uint32_t)lane, grp);
@@ -575,18 +586,34 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           const uint32_t cur = entry - wb;
           uint32_t m = 0, dist = 1;
           int budget = search ? (int)prm.maxcand : 0;
-          const uint32_t poff = off0 + p;
-          const uint32_t stop = min(limit, (uint32_t)LZ_LANE_CAP);
+          Lz2Pos P;
+          P.data32 = reinterpret_cast<const uint32_t *>(data);
+          P.poff = off0 + p;
+          P.q = q;
+          P.v = v;
+          P.lim = min(q, (uint32_t)ZB_MAX_DIST);
+          P.limit = limit;
+          P.stop = min(limit, (uint32_t)LZ_LANE_CAP);
+          // candidate slots, nearest first; the level decides how many are looked at (nslots):
+          //   0      the closest same-hash position inside this window
+          //   1..4   the own bucket, most recent first
+          //   5..20  the four preceding segments' buckets, each from its most recent window residue down
           if (search) {
-            // nearest first: the closest same-hash position inside this window, then the own bucket
             const uint32_t lower = grp & ((1u << lane) - 1u);
-            if (lower) lz2_eval(data, poff, q, v, limit, (uint32_t)lane - (uint32_t)(31 - __clz((int)lower)), prm.good, m, dist, budget);
-            lz2_try_bucket(data, poff, q, v, limit, stop, bucket, prm.good, m, dist, budget);
+            if (lower) lz2_try(P, data, q - ((uint32_t)lane - (uint32_t)(31 - __clz((int)lower))), prm.good, m, dist, budget);
+            lz2_try(P, data, bucket.x & 0xffffu, prm.good, m, dist, budget);
+            if (prm.nslots > 2) lz2_try(P, data, bucket.x >> 16, prm.good, m, dist, budget);
+            if (prm.nslots > 3) lz2_try(P, data, bucket.y & 0xffffu, prm.good, m, dist, budget);
+            if (prm.nslots > 4) lz2_try(P, data, bucket.y >> 16, prm.good, m, dist, budget);
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            if (__any_sync(ZB_FULL, budget > 0 && m < stop))
-              lz2_try_bucket(data, poff, q, v, limit, stop, hbk[j], prm.good, m, dist, budget);
+            if (prm.nslots > 5u + 4u * (uint32_t)j && __any_sync(ZB_FULL, budget > 0 && m < P.stop)) {
+              lz2_try(P, data, hbk[j].y >> 16, prm.good, m, dist, budget);
+              if (prm.nslots > 6u + 4u * (uint32_t)j) lz2_try(P, data, hbk[j].y & 0xffffu, prm.good, m, dist, budget);
+              if (prm.nslots > 7u + 4u * (uint32_t)j) lz2_try(P, data, hbk[j].x >> 16, prm.good, m, dist, budget);
+              if (prm.nslots > 8u + 4u * (uint32_t)j) lz2_try(P, data, hbk[j].x & 0xffffu, prm.good, m, dist, budget);
+            }
           }
           // one-step lazy evaluation (zlib's max_lazy idea)
           const uint32_t mnext = __shfl_down_sync(ZB_FULL, m, 1);
@@ -1030,12 +1057,14 @@ __global__ void __launch_bounds__(LZ_THREADS)
 static bool zb_is_lz_level(int level) { return level == -1 || level >= 2; }
 // Search effort per level, after the reference's configurationTable (internal.nim:177-189: good / lazy / nice /
 // chain per level; lz77.nim:97-109 walks `chain` links and quarters the rest at `good`).  Here the candidates
-// come from 4-way buckets instead of a chain, so the budget is the number of VERIFIED candidates per position,
-// `good` keeps its meaning and `lazy` is the one-step lazy threshold; effort and compressed size are
-// monotone in the level.
+// come from 4-way buckets instead of a chain, so the budget is how many candidate slots are looked at
+// (nslots: own window, own bucket, then the preceding segments' buckets) and how many of them may pass the
+// 4-byte check (maxcand); `good` keeps its meaning and `lazy` is the one-step lazy threshold.  Effort and
+// compressed size are monotone in the level.
 ZbLz2Params zb_lz2_params(int level) {
-  static const ZbLz2Params table[10] = {{8, 8, 16},  {8, 8, 16},  {2, 4, 0},   {3, 4, 6},   {4, 4, 8},
-                                        {6, 8, 16},  {8, 8, 16},  {12, 8, 32}, {21, 16, 32}, {21, 32, 64}};
+  //                                     nslots maxcand good lazy
+  static const ZbLz2Params table[10] = {{12, 8, 8, 16},  {12, 8, 8, 16},  {5, 2, 4, 0},    {5, 3, 4, 6},    {7, 4, 4, 8},
+                                        {9, 6, 8, 16},   {12, 8, 8, 16},  {14, 12, 8, 32}, {21, 21, 16, 32}, {21, 21, 32, 64}};
   return table[(level >= 2 && level <= 9) ? level : 6];  // -1 (Default) = level 6
 }
 size_t zb_lz2_table_bytes(int *grid_out) {

@@ -53,7 +53,8 @@ struct ZbCompressWork {
 cudaError_t zb_setup_deflate_attrs();
 cudaError_t zb_setup_inflate_attrs();
 struct ZbLz2Params {
-  uint32_t maxcand;  // verified candidates per position
+  uint32_t nslots;   // candidate slots looked at per position (1 + 4 own ways + 4 x 4 ways of the preceding segments)
+  uint32_t maxcand;  // candidates per position that may pass the 4-byte check and be extended
   uint32_t good;     // a match this long leaves room for one more candidate only
   uint32_t lazy;     // matches shorter than this yield to a longer match at the next position (0: greedy)
 };
