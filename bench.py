@@ -431,18 +431,20 @@ def pcie_peaks(e, nbytes=1 << 30):
             t.cuda.synchronize()
             best = min(best, e.ev0.elapsed_time(e.ev1))
         out[name] = nbytes / (best / 1e3) / 1e9
-    # both directions at once (two streams): what a pipelined host call can hope for
+    # both directions at once (two streams), best of 3: what a pipelined host call can hope for
     s2 = t.cuda.Stream()
     h2 = pinned(e, nbytes)
     d2 = t.empty(nbytes, dtype=t.uint8, device=e.dev)
-    t.cuda.synchronize()
-    t0 = time.perf_counter()
-    d.copy_(h, non_blocking=True)
-    with t.cuda.stream(s2):
-        h2.copy_(d2, non_blocking=True)
-    t.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    out["duplex_each_gbs"] = nbytes / dt / 1e9
+    best = 1e9
+    for _ in range(4):
+        t.cuda.synchronize()
+        t0 = time.perf_counter()
+        d.copy_(h, non_blocking=True)
+        with t.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+        t.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    out["duplex_each_gbs"] = nbytes / best / 1e9
     out["bytes"] = nbytes
     return out
 

@@ -93,6 +93,14 @@ int zb200_inflate(zb200_ctx *ctx, const uint8_t *src, size_t len, size_t pos,
                   uint8_t *dst, size_t dst_cap, size_t *dst_len);
 /* size the output of zb200_inflate without producing it */
 int zb200_inflate_size(zb200_ctx *ctx, const uint8_t *src, size_t len, size_t pos, size_t *out_len);
+/* One input whose output size is unknown, decoded ONCE: begin inflates (and verifies the trailer) into
+ * library-owned device memory and reports the size, finish copies the bytes out.  This is what a caller
+ * with a growing destination (the reference's `dst: var string`, inflate.nim:268-291, gzip.nim:3-88) binds
+ * instead of inflate_size + inflate (two decodes).  data_format as for uncompress; `pos` as for inflate
+ * (raw streams only).  A gzip member whose ISIZE understates its content gets the reference's verdict
+ * (data, CRC check, then "Size verification failed"), not "destination too small". */
+int zb200_decode_begin(zb200_ctx *ctx, const uint8_t *src, size_t len, int data_format, size_t pos, size_t *out_len);
+int zb200_decode_finish(zb200_ctx *ctx, uint8_t *dst, size_t dst_cap, size_t *dst_len);
 /* crc.nim:53 / adler32.nim:6 */
 int zb200_crc32(zb200_ctx *ctx, const void *src, size_t len, uint32_t *out);
 int zb200_adler32(zb200_ctx *ctx, const void *src, size_t len, uint32_t *out);

@@ -43,11 +43,12 @@ inline void deflate(std::string &dst, const uint8_t *src, size_t len, int level)
 }
 // inflate.nim:268
 inline void inflate(std::string &dst, const uint8_t *src, size_t len, size_t pos) {
+  // one decode: the library inflates into its own device memory, reports the size, then copies out
   size_t n = 0;
-  check(zb200_inflate_size(ctx(), src, len, pos, &n));
+  check(zb200_decode_begin(ctx(), src, len, ZB200_DF_DEFLATE, pos, &n));
   dst.resize(n);
   uint8_t dummy = 0;
-  check(zb200_inflate(ctx(), src, len, pos, n ? reinterpret_cast<uint8_t *>(&dst[0]) : &dummy, n, &n));
+  check(zb200_decode_finish(ctx(), n ? reinterpret_cast<uint8_t *>(&dst[0]) : &dummy, n, &n));
   dst.resize(n);
 }
 inline uint32_t read32le(const uint8_t *p) {

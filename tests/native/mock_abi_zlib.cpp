@@ -69,6 +69,19 @@ int zb200_inflate(zb200_ctx *, const uint8_t *src, size_t len, size_t pos, uint8
   *n = out.size();
   return ZB200_OK;
 }
+static std::vector<uint8_t> g_pending;
+int zb200_decode_begin(zb200_ctx *, const uint8_t *src, size_t len, int fmt, size_t pos, size_t *n) {
+  if (fmt != ZB200_DF_DEFLATE) return ZB200_ERR_INVALID_FORMAT;  // the mock only serves the raw seam
+  int rc = raw_inflate(src, len, pos, g_pending);
+  *n = g_pending.size();
+  return rc;
+}
+int zb200_decode_finish(zb200_ctx *, uint8_t *dst, size_t cap, size_t *n) {
+  if (g_pending.size() > cap) return ZB200_ERR_DST_TOO_SMALL;
+  if (!g_pending.empty()) std::memcpy(dst, g_pending.data(), g_pending.size());
+  *n = g_pending.size();
+  return ZB200_OK;
+}
 int zb200_compress_batch(zb200_ctx *, const uint8_t *base, const uint64_t *off, size_t n, int, int fmt, const uint8_t *,
                          uint8_t *dst, size_t cap, uint64_t *dst_off, int *st) {
   if (fmt != ZB200_DF_DEFLATE) return ZB200_ERR_INVALID_FORMAT;

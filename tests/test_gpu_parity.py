@@ -475,6 +475,75 @@ def test_output_is_identical_run_to_run(z, corpus):
                 ctx.close()
 
 
+def test_size_claims_get_the_reference_verdict(z, o, corpus):
+    """gzip.nim:80-88 inflates whatever the stream holds, checks the CRC, then ISIZE.  A member whose ISIZE
+    understates (or overstates) its content must therefore end in "Size verification failed" -- not in
+    "destination too small" -- and a wrong CRC in "Checksum verification failed", through the single call and
+    through the batch call, with the same codes as the oracle."""
+    data = corpus["alice29.txt"]
+    good = bytearray(o.compress(data, 1, o.dfGzip))
+    cases = {}
+    for name, delta in (("isize_small", -1000), ("isize_big", 5000), ("isize_zero", -len(data))):
+        m = bytearray(good)
+        m[-4:] = ((len(data) + delta) & 0xffffffff).to_bytes(4, "little")
+        cases[name] = bytes(m)
+    m = bytearray(good)
+    m[-8] ^= 0x55
+    cases["crc"] = bytes(m)
+    m[-4:] = (len(data) - 7).to_bytes(4, "little")
+    cases["crc_and_isize"] = bytes(m)
+    want = {}
+    for name, m in cases.items():
+        with pytest.raises(o.ZippyError) as e:
+            o.uncompress(m)
+        want[name] = e.value.code
+        with pytest.raises(z.ZippyError) as e2:
+            z.uncompress(m)
+        assert e2.value.code == want[name], (name, e2.value.code, want[name])
+    assert want["isize_small"] == 18 and want["crc"] == 14 and want["crc_and_isize"] == 14
+    res = z.uncompress_batch([bytes(good)] + list(cases.values()) + [bytes(good)])
+    assert res[0] == data and res[-1] == data
+    for (name, _), r in zip(cases.items(), res[1:-1]):
+        assert isinstance(r, z.ZippyError) and r.code == want[name], (name, r)
+    # a zlib stream (no size field at all) through the single call: decoded once, sized by the library
+    zs = zlib.compress(corpus["html_x_4"], 6)
+    assert z.uncompress(zs) == corpus["html_x_4"] and z.inflate(zs, 2) == corpus["html_x_4"]
+
+
+def test_two_devices_two_threads(z, o, corpus):
+    """Function attributes (dynamic shared memory limits) are per device: every ctx sets them for its own
+    device in zb200_init.  Two contexts on two devices, driven from two host threads at once."""
+    import threading
+    from zippy_b200 import _native
+    if _native.lib().zb200_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    T = util.text_corpus(corpus)
+    items = [util.c2_block(T, i) for i in range(64)] + [corpus["urls.10K"]]
+    errs = []
+
+    def work(dev):
+        try:
+            ctx = z.Context(dev)
+            base, offs = z._pack(items)
+            for lvl in (1, z.DefaultCompression):
+                out, oo = ctx.compress_batch(base, offs, lvl, z.dfGzip)
+                back, do, lens, st = ctx.uncompress_batch(out, oo)
+                assert not st.any()
+                for i, it in enumerate(items):
+                    assert back[int(do[i]):int(do[i]) + int(lens[i])].tobytes() == it
+            assert ctx.crc32(items[0]) == zlib.crc32(items[0])
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append((dev, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+
+
 def test_cpp_host_mirror():
     """include/zippy_b200.hpp (host framing in C++ as in zippy.nim, codec through the seam)."""
     import subprocess

@@ -13,9 +13,17 @@ import sys
 from collections import defaultdict
 
 rep, cubin, kname = sys.argv[1], sys.argv[2], sys.argv[3]
+rname = os.environ.get("NCU_KERNEL", kname)  # kernel name as ncu prints it (demangled), if it differs from the mangled substring
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
+# a report with several kernels repeats "Kernel Name" + header per kernel: keep the section that matches
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if len(starts) > 1:
+    pick = [i for i in starts if rname in rows[i][1]]
+    i0 = pick[0]
+    i1 = min([j for j in starts if j > i0] + [len(rows)])
+    rows = rows[i0:i1]
 h = rows[1]
 iex, isamp, isrc = h.index("Instructions Executed"), h.index("# Samples"), h.index("Source")
 ncu_ins = [(r[isrc].strip(), int(r[iex] or 0), int(r[isamp] or 0)) for r in rows[2:] if len(r) == len(h)]

@@ -34,6 +34,8 @@ SYMBOLS = {
     "zb200_deflate": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, c_int, c_u8p, c_size_t, ctypes.POINTER(c_size_t)]),
     "zb200_inflate": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, c_size_t, c_u8p, c_size_t, ctypes.POINTER(c_size_t)]),
     "zb200_inflate_size": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, c_size_t, ctypes.POINTER(c_size_t)]),
+    "zb200_decode_begin": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, c_int, c_size_t, ctypes.POINTER(c_size_t)]),
+    "zb200_decode_finish": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, ctypes.POINTER(c_size_t)]),
     "zb200_crc32": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, ctypes.POINTER(ctypes.c_uint32)]),
     "zb200_adler32": (c_int, [ctypes.c_void_p, c_u8p, c_size_t, ctypes.POINTER(ctypes.c_uint32)]),
     "zb200_compress_batch": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, c_int, c_u8p, c_u8p, c_size_t,

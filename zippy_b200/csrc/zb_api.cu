@@ -15,6 +15,7 @@
 
 #include "../../include/zippy_b200.h"
 #include "zb_kernels.h"
+#include "zb_wrapper.h"
 
 namespace {
 
@@ -37,6 +38,10 @@ struct zb200_ctx {
   DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out, ck_pieces, ck_first, ck_piece_out;
   DevBuf in_stage, out_stage, lz2_tables;
   DevBuf seg_src, seg_dst, seg_len, seg_status, seg_kind, seg_expect, seg_cand, skip_mask;  // large-member segments
+  DevBuf order;             // work-queue order of an inflate launch (longest members first)
+  uint64_t pending_len = 0;     // zb200_decode_begin's result, waiting in out_stage for zb200_decode_finish
+  bool pending = false;
+  bool serial_copies = false;  // host pipelines: do not run H2D and D2H at the same time (ZB200_SERIAL_COPIES)
   uint64_t big_member_bytes = 512ull << 10;  // members at least this long are tried as parallel segments
   cudaEvent_t ev[10] = {};
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -604,6 +609,30 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
   return ZB200_OK;
 }
 
+// Work-queue order of one inflate launch: a member is decoded by one 8-lane group from start to end,
+// so a long member that is fetched late finishes long after everything else (the tail of the launch).
+// Members much longer than the average go first, longest first; the rest keep their order.
+// Returns false when no member stands out (then the launch uses index order and nothing is uploaded).
+bool longest_first_order(const uint64_t *src_offsets, size_t n, std::vector<uint32_t> &order) {
+  if (n < 64) return false;
+  const uint64_t total = src_offsets[n] - src_offsets[0];
+  const uint64_t thr = std::max<uint64_t>(4 * (total / n), 32768);
+  std::vector<uint32_t> big;
+  for (size_t i = 0; i < n; i++)
+    if (src_offsets[i + 1] - src_offsets[i] >= thr) big.push_back((uint32_t)i);
+  if (big.empty() || big.size() > n / 2) return false;
+  std::sort(big.begin(), big.end(), [&](uint32_t a, uint32_t b) {
+    const uint64_t la = src_offsets[a + 1] - src_offsets[a], lb = src_offsets[b + 1] - src_offsets[b];
+    return la != lb ? la > lb : a < b;
+  });
+  order.resize(n);
+  size_t k = 0;
+  for (uint32_t i : big) order[k++] = i;
+  for (size_t i = 0; i < n; i++)
+    if (src_offsets[i + 1] - src_offsets[i] < thr) order[k++] = (uint32_t)i;
+  return true;
+}
+
 // ---- uncompress, device-resident ----
 int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n,
                              int data_format, uint64_t raw_pos, uint8_t *d_dst, const uint64_t *dst_offsets,
@@ -639,6 +668,16 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
   w.count_only = count_only ? 1 : 0;
   w.skip = nullptr;
   w.seg_mode = 0;
+  w.order = nullptr;
+  {
+    std::vector<uint32_t> order;
+    if (longest_first_order(src_offsets, n, order)) {
+      ENSURE(ctx->order, n * sizeof(uint32_t));
+      CK(cudaMemcpyAsync(ctx->order.p, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));  // `order` goes out of scope
+      w.order = (const uint32_t *)ctx->order.p;
+    }
+  }
   ZbChecksumWork cw;
   memset(&cw, 0, sizeof(cw));
   if (!count_only) {  // piece table for the verification pass, uploaded before anything is launched
@@ -702,6 +741,153 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
   ctx->timing.kernel_launches += count_only ? 1 : 3;
   for (size_t i = 0; i < n; i++)
     if (st[i] != ZB200_OK) dst_lens[i] = 0;
+  return ZB200_OK;
+}
+
+// ---- uncompress, host buffers, fully asynchronous ----
+// Everything the device needs for the WHOLE batch (offsets, verification pieces, work-queue orders) is
+// built and uploaded once; then every member group is enqueued without a host wait in between:
+//   H2D stream : copy-in of group 0, 1, 2, ... back to back
+//   main stream: wait copy-in(g) -> inflate(g) -> verify(g)
+//   D2H stream : wait verify(g) -> copy-out(g)
+// and the host synchronises once at the end.  (The first version waited for every group's kernels on the
+// host before it built and launched the next group, and each launch carried its own tail of long members.)
+int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::vector<uint64_t> &reb, size_t n,
+                              int data_format, uint8_t *h_dst, const std::vector<uint64_t> &dreb, uint64_t *dst_lens,
+                              int *statuses, const std::vector<size_t> &gb) {
+  const size_t ng = gb.size() - 1;
+  cudaStream_t s = ctx->stream, sh = ctx->h2d_stream, sd = ctx->d2h_stream;
+  const uint8_t *d_src = (const uint8_t *)ctx->in_stage.p;
+  uint8_t *d_dst = (uint8_t *)ctx->out_stage.p;
+  // ---- plan (host) ----
+  std::vector<ZbPiece> pieces;
+  std::vector<uint32_t> first;          // per group: (members + 1) entries relative to the group's first piece
+  std::vector<size_t> piece0(ng + 1), first0(ng + 1);
+  std::vector<uint32_t> order(n);       // per group: entries relative to the group
+  std::vector<uint8_t> has_order(ng, 0);
+  for (size_t gi = 0; gi < ng; gi++) {
+    const size_t m0 = gb[gi], m1 = gb[gi + 1];
+    piece0[gi] = pieces.size();
+    first0[gi] = first.size();
+    for (size_t i = m0; i < m1; i++) {
+      first.push_back((uint32_t)(pieces.size() - piece0[gi]));
+      const uint64_t cap = dreb[i + 1] - dreb[i];
+      uint64_t rel = 0;
+      do {
+        ZbPiece pc;
+        pc.rel = rel;
+        pc.buf = (uint32_t)(i - m0);
+        pc.pad = 0;
+        pieces.push_back(pc);
+        rel += ZB_CHUNK_BYTES;
+      } while (rel < cap);
+    }
+    first.push_back((uint32_t)(pieces.size() - piece0[gi]));
+    std::vector<uint32_t> o;
+    if (longest_first_order(reb.data() + m0, m1 - m0, o)) {
+      has_order[gi] = 1;
+      std::copy(o.begin(), o.end(), order.begin() + m0);
+    }
+  }
+  piece0[ng] = pieces.size();
+  first0[ng] = first.size();
+  // ---- device arrays for the whole batch ----
+  ENSURE(ctx->src_off, (n + 1) * sizeof(uint64_t));
+  ENSURE(ctx->dst_off, (n + 1) * sizeof(uint64_t));
+  ENSURE(ctx->out_len, n * sizeof(uint64_t));
+  ENSURE(ctx->status, n * sizeof(int));
+  ENSURE(ctx->expect, n * sizeof(uint32_t));
+  ENSURE(ctx->kind, n * sizeof(uint32_t));
+  ENSURE(ctx->order, n * sizeof(uint32_t));
+  ENSURE(ctx->counter, (ng + 16) * sizeof(uint32_t));
+  ENSURE(ctx->ck_pieces, pieces.size() * sizeof(ZbPiece));
+  ENSURE(ctx->ck_first, first.size() * sizeof(uint32_t));
+  ENSURE(ctx->ck_piece_out, pieces.size() * sizeof(ZbChunkCheck));
+  {
+    int rc = ensure_group_events(ctx, 2 * ng + 2);
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, n * (sizeof(uint64_t) + sizeof(int)) + 64);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(ctx->src_off.p, reb.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->dst_off.p, dreb.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->ck_pieces.p, pieces.data(), pieces.size() * sizeof(ZbPiece), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->ck_first.p, first.data(), first.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->order.p, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  // the side streams start after whatever the caller's stream already holds (and after the tables above)
+  CK(cudaEventRecord(ctx->gev[2 * ng], s));
+  CK(cudaStreamWaitEvent(sh, ctx->gev[2 * ng], 0));
+  CK(cudaStreamWaitEvent(sd, ctx->gev[2 * ng], 0));
+  CK(cudaEventRecord(ctx->ev[6], sh));
+  CK(cudaEventRecord(ctx->ev[8], sd));
+  for (size_t gi = 0; gi < ng; gi++) {
+    const uint64_t b0 = reb[gb[gi]], b1 = reb[gb[gi + 1]];
+    if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + b0, h_src + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sh));
+    CK(cudaEventRecord(ctx->gev[2 * gi], sh));
+  }
+  CK(cudaEventRecord(ctx->ev[7], sh));
+  if (ctx->serial_copies) CK(cudaStreamWaitEvent(sd, ctx->gev[2 * (ng - 1)], 0));  // copies out start after the last copy in
+  CK(cudaEventRecord(ctx->ev[0], s));
+  for (size_t gi = 0; gi < ng; gi++) {
+    const size_t m0 = gb[gi], m1 = gb[gi + 1], nm = m1 - m0;
+    CK(cudaStreamWaitEvent(s, ctx->gev[2 * gi], 0));
+    ZbInflateWork w;
+    memset(&w, 0, sizeof(w));
+    w.src = d_src;
+    w.src_off = (const uint64_t *)ctx->src_off.p + m0;
+    w.dst = d_dst;
+    w.dst_off = (const uint64_t *)ctx->dst_off.p + m0;
+    w.out_len = (uint64_t *)ctx->out_len.p + m0;
+    w.status = (int *)ctx->status.p + m0;
+    w.expect = (uint32_t *)ctx->expect.p + m0;
+    w.kind = (uint32_t *)ctx->kind.p + m0;
+    w.counter = (uint32_t *)ctx->counter.p + 16 + gi;
+    w.tabs = ctx->d_tabs;
+    w.n = (uint32_t)nm;
+    w.data_format = data_format;
+    w.order = has_order[gi] ? (const uint32_t *)ctx->order.p + m0 : nullptr;
+    CK(zb_launch_inflate(w, s));
+    // gzip.nim:80-88 / zippy.nim:154-162: checksum, then size, of every member that inflated
+    ZbChecksumWork cw;
+    memset(&cw, 0, sizeof(cw));
+    cw.src = d_dst;
+    cw.off = w.dst_off;
+    cw.lens = w.out_len;
+    cw.pieces = (const ZbPiece *)ctx->ck_pieces.p + piece0[gi];
+    cw.first = (const uint32_t *)ctx->ck_first.p + first0[gi];
+    cw.piece_out = (ZbChunkCheck *)ctx->ck_piece_out.p + piece0[gi];
+    cw.status = w.status;
+    cw.expect = w.expect;
+    cw.kinds = w.kind;
+    cw.isize_src = d_src;
+    cw.isize_off = w.src_off;
+    cw.tabs = ctx->d_tabs;
+    cw.n = (uint32_t)nm;
+    cw.n_pieces = (uint32_t)(piece0[gi + 1] - piece0[gi]);
+    CK(zb_launch_checksum(cw, s));
+    CK(cudaEventRecord(ctx->gev[2 * gi + 1], s));
+    CK(cudaStreamWaitEvent(sd, ctx->gev[2 * gi + 1], 0));
+    const uint64_t o0 = dreb[m0], o1 = dreb[m1];
+    if (o1 > o0 && h_dst) CK(cudaMemcpyAsync(h_dst + o0, d_dst + o0, (size_t)(o1 - o0), cudaMemcpyDeviceToHost, sd));
+    ctx->timing.kernel_launches += 3;
+  }
+  CK(cudaEventRecord(ctx->ev[1], s));
+  CK(cudaEventRecord(ctx->ev[9], sd));
+  uint64_t *pl = (uint64_t *)ctx->pin;
+  int *ps = (int *)(pl + n);
+  CK(cudaMemcpyAsync(pl, ctx->out_len.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ps, ctx->status.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  // the caller's stream ends after the last copy out
+  CK(cudaEventRecord(ctx->gev[2 * ng + 1], sd));
+  CK(cudaStreamWaitEvent(s, ctx->gev[2 * ng + 1], 0));
+  CK(cudaStreamSynchronize(s));  // also: the planning vectors above stay alive until their uploads are done
+  CK(cudaStreamSynchronize(sh));
+  for (size_t i = 0; i < n; i++) {
+    dst_lens[i] = ps[i] == ZB200_OK ? pl[i] : 0;
+    if (statuses) statuses[i] = ps[i];
+  }
+  ctx->timing.inflate_ms = ev_ms(ctx->ev[0], ctx->ev[1]);  // inflate + verify of all groups (includes waits for copy-in)
+  ctx->timing.verify_ms = 0.f;
   return ZB200_OK;
 }
 
@@ -816,6 +1002,7 @@ int zb200_init(int device, zb200_ctx **out) {
     long long v = atoll(e);
     if (v > 0) ctx->unc_group_out_bytes = (uint64_t)v;
   }
+  if (const char *e = getenv("ZB200_SERIAL_COPIES")) ctx->serial_copies = atoi(e) != 0;
   if (const char *e = getenv("ZB200_DEV_GROUP_CHUNKS")) {  // device-resident batches only (bench.py)
     long v = atol(e);
     if (v > 0) ctx->dev_group_chunks = (size_t)v;
@@ -851,7 +1038,7 @@ void zb200_shutdown(zb200_ctx *ctx) {
                     &ctx->cb, &ctx->chunk_off, &ctx->member_off, &ctx->member_check, &ctx->member_isize,
                     &ctx->src_off, &ctx->dst_off, &ctx->out_len, &ctx->status, &ctx->expect, &ctx->kind,
                     &ctx->counter, &ctx->ck_out, &ctx->ck_pieces, &ctx->ck_first, &ctx->ck_piece_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables,
-                    &ctx->seg_src, &ctx->seg_dst, &ctx->seg_len, &ctx->seg_status, &ctx->seg_kind, &ctx->seg_expect, &ctx->seg_cand, &ctx->skip_mask};
+                    &ctx->seg_src, &ctx->seg_dst, &ctx->seg_len, &ctx->seg_status, &ctx->seg_kind, &ctx->seg_expect, &ctx->seg_cand, &ctx->skip_mask, &ctx->order};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_tabs) cudaFree(ctx->d_tabs);
@@ -1052,9 +1239,26 @@ int zb200_uncompress_sizes(zb200_ctx *ctx, const uint8_t *src_base, const uint64
                            int data_format, uint64_t *sizes, int *statuses) {
   return guarded(ctx, [&]() -> int {
   if (!ctx || !src_offsets || !sizes || (n && !src_base)) return ZB200_ERR_ARG;
+  if (data_format < ZB200_DF_DETECT || data_format > ZB200_DF_DEFLATE) return ZB200_ERR_INVALID_FORMAT;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   memset(&ctx->timing, 0, sizeof(ctx->timing));
+  for (size_t i = 0; i < n; i++)
+    if (src_offsets[i + 1] < src_offsets[i]) return ZB200_ERR_ARG;
+  // gzip members answer from their trailer (gzip.nim:66) after the same wrapper checks the device decoder
+  // makes: nothing is copied to the device for them.  Only a batch that holds zlib / raw members needs the
+  // counting pass.
+  bool need_device = false;
+  for (size_t i = 0; i < n && !need_device; i++) {
+    uint64_t payload = 0;
+    uint32_t kind = 0, expect = 0, isize = 0;
+    const int st = zb_parse_wrapper(src_base + src_offsets[i], src_offsets[i + 1] - src_offsets[i], data_format, 0, payload,
+                                    kind, expect, isize);
+    if (st == ZB200_OK && kind != ZB200_DF_GZIP) need_device = true;
+    sizes[i] = st == ZB200_OK ? isize : 0;
+    if (statuses) statuses[i] = st;
+  }
+  if (!need_device) return ZB200_OK;
   std::vector<uint64_t> reb;
   int rc = stage_in(ctx, src_base, src_offsets, n, reb);
   if (rc) return rc;
@@ -1084,13 +1288,13 @@ int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64
   ENSURE(ctx->out_stage, (size_t)(hi - lo) + 64);
   // Member groups: group g inflates while group g + 1 is copied in on the H2D stream and group
   // g - 1 is copied out on the D2H stream.  A launch wants ~7000 members to fill the GPU, so the
-  // groups are big: a quarter of the batch, between 64 MiB and 1 GiB of output.  (The copies only
+  // groups are big: an eighth of the batch, between 64 MiB and 1 GiB of output.  (The copies only
   // run asynchronously for page-locked host buffers; with pageable memory the same code is
   // correct but the copies block this thread.)
   std::vector<size_t> gb(1, 0);
   {
     uint64_t out_cap = ctx->unc_group_out_bytes;
-    if (!out_cap) out_cap = std::min<uint64_t>(std::max<uint64_t>((hi - lo) / 4, 64ull << 20), 1ull << 30);
+    if (!out_cap) out_cap = std::min<uint64_t>(std::max<uint64_t>((hi - lo) / 8, 64ull << 20), 1ull << 30);
     const uint64_t in_cap = out_cap;
     size_t a = 0;
     for (size_t i = 1; i <= n; i++)
@@ -1100,6 +1304,21 @@ int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64
       }
   }
   const size_t ng = gb.size() - 1;
+  {
+    bool any_big = false;
+    for (size_t i = 0; i < n && !any_big; i++) any_big = reb[i + 1] - reb[i] >= ctx->big_member_bytes;
+    if (!any_big) {
+      int rc = uncompress_host_pipelined(ctx, src_base + slo, reb, n, data_format, dst_base ? dst_base + lo : nullptr, dreb,
+                                         dst_lens, statuses, gb);
+      if (rc) return rc;
+      ctx->timing.h2d_ms = ev_ms(ctx->ev[6], ctx->ev[7]);
+      ctx->timing.d2h_ms = ev_ms(ctx->ev[8], ctx->ev[9]);
+      ctx->timing.h2d_bytes = shi - slo;
+      ctx->timing.d2h_bytes = hi - lo;
+      return ZB200_OK;
+    }
+  }
+  // a batch with large members takes the group-by-group path: those members are planned on the host
   int rc = ensure_group_events(ctx, 2 * ng + 2);
   if (rc) return rc;
   cudaStream_t s = ctx->stream, sh = ctx->h2d_stream, sd = ctx->d2h_stream;
@@ -1175,6 +1394,77 @@ int zb200_checksum_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t
   int rc = stage_in(ctx, src_base, src_offsets, n, reb);
   if (rc) return rc;
   return checksum_device_locked(ctx, (const uint8_t *)ctx->in_stage.p, reb.data(), n, kind, out);
+  });
+}
+
+// ---- one input of unknown size, decoded ONCE ----
+// The reference's inflate appends to a string that grows as it goes (inflate.nim:268-291); a fixed-capacity
+// ABI would otherwise need a counting pass before the real one.  decode_begin inflates into library-owned
+// device memory (capacity from the gzip trailer, else a guess that a counting pass corrects only when it
+// was too small) and reports the size; decode_finish copies the bytes to the caller.  Also what gives the
+// reference's answer for a gzip member whose ISIZE understates its content: the data is produced, the CRC
+// is checked, then the size check fails (gzip.nim:80-88), instead of "destination too small".
+int zb200_decode_begin(zb200_ctx *ctx, const uint8_t *src, size_t len, int data_format, size_t pos, size_t *out_len) {
+  return guarded(ctx, [&]() -> int {
+    if (!ctx || !out_len || (len && !src)) return ZB200_ERR_ARG;
+    if (data_format < ZB200_DF_DETECT || data_format > ZB200_DF_DEFLATE) return ZB200_ERR_INVALID_FORMAT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    ctx->pending = false;
+    uint8_t dummy = 0;
+    const uint8_t *sp = src ? src : &dummy;
+    uint64_t payload = 0;
+    uint32_t kind = 0, expect = 0, isize = 0;
+    int st = zb_parse_wrapper(sp, len, data_format, pos, payload, kind, expect, isize);
+    if (st != ZB200_OK) return st;
+    uint64_t cap = kind == ZB200_DF_GZIP ? std::min<uint64_t>(isize, (uint64_t)len * 1032ull + 1024ull)
+                                         : std::min<uint64_t>(std::max<uint64_t>((uint64_t)len * 8ull, 256ull << 10), 1ull << 30);
+    uint64_t so[2] = {0, len};
+    std::vector<uint64_t> reb;
+    int rc = stage_in(ctx, sp, so, 1, reb);
+    if (rc) return rc;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      ENSURE(ctx->out_stage, (size_t)cap + 64);
+      uint64_t dof[2] = {0, cap}, dl = 0;
+      rc = uncompress_device_locked(ctx, (const uint8_t *)ctx->in_stage.p, reb.data(), 1, data_format, pos,
+                                    (uint8_t *)ctx->out_stage.p, dof, &dl, &st, false);
+      if (rc) return rc;
+      if (st != ZB200_ERR_DST_TOO_SMALL || attempt == 1) {
+        if (st != ZB200_OK) return st;
+        ctx->pending = true;
+        ctx->pending_len = dl;
+        *out_len = (size_t)dl;
+        return ZB200_OK;
+      }
+      // too small: count the raw stream from the payload start (a gzip ISIZE is a claim, not a fact)
+      int cst = ZB200_OK;
+      uint64_t real = 0;
+      rc = uncompress_device_locked(ctx, (const uint8_t *)ctx->in_stage.p, reb.data(), 1, ZB200_DF_DEFLATE, payload, nullptr,
+                                    nullptr, &real, &cst, true);
+      if (rc) return rc;
+      if (cst != ZB200_OK) return cst;
+      cap = real;
+    }
+    return ZB200_ERR_UNCOMPRESS;
+  });
+}
+
+int zb200_decode_finish(zb200_ctx *ctx, uint8_t *dst, size_t dst_cap, size_t *dst_len) {
+  return guarded(ctx, [&]() -> int {
+    if (!ctx || !dst_len) return ZB200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (!ctx->pending) return ZB200_ERR_ARG;
+    if (ctx->pending_len > dst_cap) return ZB200_ERR_DST_TOO_SMALL;
+    if (ctx->pending_len && !dst) return ZB200_ERR_ARG;
+    if (ctx->pending_len) {
+      CK(cudaMemcpyAsync(dst, ctx->out_stage.p, (size_t)ctx->pending_len, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *dst_len = (size_t)ctx->pending_len;
+    ctx->pending = false;
+    return ZB200_OK;
   });
 }
 

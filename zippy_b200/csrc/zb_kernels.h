@@ -80,6 +80,7 @@ struct ZbInflateWork {
   int data_format;             // requested (may be ZB_DF_DETECT)
   uint64_t pos;                // payload start for raw ZB_DF_DEFLATE members (zb200_inflate's `pos`)
   int count_only;
+  const uint32_t *order;       // device [n] or null: the work queue hands out members in this order (longest first)
   const uint8_t *skip;         // device [n] or null: members with skip[i] != 0 are left alone
   int seg_mode;                // members are independently decodable SEGMENTS of one raw deflate stream:
                                // a segment also ends, successfully, when its input is used up at a block
