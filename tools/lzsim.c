@@ -29,7 +29,7 @@
 #define MAXM 258
 
 static int P_sub = 8192, P_seg = 8192, P_sbits = 10, P_slong = 0, P_sways = 1, P_obits = 10, P_oways = 2, P_olong = 0;
-static int P_slotmode = 0;
+static int P_slotmode = 0, P_slotcap = 0, P_order = 0;
 static int P_ownstatic = 0, P_visit = 1000, P_back = 4;
 static int P_preseed = 0, P_hist = 32768, P_lazy = 16, P_min4far = 0, P_near = 1, P_good = 8, P_maxcand = 64, P_minlen = 4;
 
@@ -157,7 +157,7 @@ int main(int argc, char **argv) {
     OPT("sub", P_sub); OPT("seg", P_seg); OPT("sbits", P_sbits); OPT("slong", P_slong); OPT("sways", P_sways);
     OPT("obits", P_obits); OPT("oways", P_oways); OPT("olong", P_olong); OPT("preseed", P_preseed); OPT("hist", P_hist);
     OPT("lazy", P_lazy); OPT("min4far", P_min4far); OPT("near", P_near); OPT("good", P_good); OPT("maxcand", P_maxcand);
-    OPT("minlen", P_minlen); OPT("ownstatic", P_ownstatic); OPT("visit", P_visit); OPT("back", P_back); OPT("slotmode", P_slotmode);
+    OPT("minlen", P_minlen); OPT("ownstatic", P_ownstatic); OPT("visit", P_visit); OPT("back", P_back); OPT("slotmode", P_slotmode); OPT("slotcap", P_slotcap); OPT("order", P_order);
   }
   FILE *f = fopen(argv[1], "rb");
   if (!f) return 2;
@@ -262,14 +262,46 @@ int main(int argc, char **argv) {
           }
           uint32_t v = ld32(p);
           int visits = P_visit;
+          if (P_slotcap) {
+            // the kernel's fixed slot list (empties count): slot 0 near, 1..4 own ways, then 4 per history segment
+            size_t sl[21];
+            int ns = 0;
+            const size_t NONE = (size_t)-1;
+            size_t nearc = NONE;
+            for (int j = l - 1; j >= 0; j--) if (hh[j] == hh[l]) { nearc = wb + j; break; }
+            size_t ownc[4] = {NONE, NONE, NONE, NONE};
+            { uint32_t *b = own4.e + (size_t)hh[l] * own4.ways; size_t tmp[8]; int k = bucket_cands(&own4, b, p, tmp); for (int i = 0; i < k && i < 4; i++) ownc[i] = tmp[i]; }
+            size_t hc[4][4];
+            int sp = (int)((p - r0) / P_seg);
+            for (int j = 0; j < 4; j++) {
+              for (int i = 0; i < 4; i++) hc[j][i] = NONE;
+              int sg = sp - 1 - j;
+              if (sg < 0) continue;
+              uint32_t *b = st4[sg].e + (size_t)tab_hash(&st4[sg], p) * st4[sg].ways;
+              // kernel order: residue 3,2,1,0 regardless of emptiness
+              for (int i = 0; i < 4; i++) { uint32_t e = st4[sg].slot ? b[3 - i] : b[i]; if (e) hc[j][i] = e - 1; }
+            }
+            if (P_order == 0) {
+              sl[ns++] = nearc;
+              for (int i = 0; i < 4; i++) sl[ns++] = ownc[i];
+              for (int j = 0; j < 4; j++) for (int i = 0; i < 4; i++) sl[ns++] = hc[j][i];
+            } else {
+              // interleaved: near, own0, own1, then way i of every history segment, own2, own3 after the first round
+              sl[ns++] = nearc; sl[ns++] = ownc[0]; sl[ns++] = ownc[1];
+              for (int j = 0; j < 4; j++) sl[ns++] = hc[j][0];
+              sl[ns++] = ownc[2];
+              for (int j = 0; j < 4; j++) sl[ns++] = hc[j][1];
+              sl[ns++] = ownc[3];
+              for (int j = 0; j < 4; j++) sl[ns++] = hc[j][2];
+              for (int j = 0; j < 4; j++) sl[ns++] = hc[j][3];
+            }
+            nc = 0;
+            for (int k = 0; k < ns && k < P_slotcap; k++) if (sl[k] != NONE) cands[nc++] = sl[k];
+          }
           for (int k = 0; k < nc && budget > 0 && visits > 0; k++) {
             size_t c = cands[k];
             visits--;
             if (c >= p || p - c > 32768 || c < r0) continue;
-            if (P_sub < P_seg && c >= b0 && 0) continue;
-            int dup = 0;
-            for (int j = 0; j < k; j++) if (cands[j] == c) dup = 1;
-            if (dup) continue;
             if (ld32(c) != v) continue;
             cand_evals++;
             budget--;

@@ -38,6 +38,7 @@ struct zb200_ctx {
   DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out, ck_pieces, ck_first, ck_piece_out;
   DevBuf in_stage, out_stage, lz2_tables;
   DevBuf seg_src, seg_dst, seg_len, seg_status, seg_kind, seg_expect, seg_cand, skip_mask;  // large-member segments
+  DevBuf mark_scratch, mark_segs, seg_bits;  // speculative segments of a large member (uint16 symbols, descriptors)
   DevBuf order;             // work-queue order of an inflate launch (longest members first)
   uint64_t pending_len = 0;     // zb200_decode_begin's result, waiting in out_stage for zb200_decode_finish
   bool pending = false;
@@ -473,6 +474,145 @@ struct BigResult {
   uint32_t kind, expect;
 };
 
+// ---- a large member WITHOUT sync markers (any foreign gzip / zlib / raw stream) ----
+// 1. k_find_blocks lists every plausible dynamic-block start in the payload; the list is thinned to one
+//    boundary per >= 16 KiB of input.  2. A counting pass decodes every segment [boundary i, boundary i+1)
+//    in parallel, each from its own block start with an UNKNOWN 32 KiB window (back-references before the
+//    segment's start are allowed, nothing is written): it must end exactly on the next boundary, and only the
+//    last segment may hold the final block -- this is what exposes a false boundary.  3. The sizes give every
+//    segment its place; the segments are decoded again into uint16 symbols, with marker symbols standing in
+//    for the bytes of the unknown window.  4. The markers are resolved: the last 32 KiB of every segment in
+//    order (one CTA), then everything else in parallel.  Anything irregular -- a decode error, a boundary
+//    that is not hit, a marker that points before the start of the stream -- leaves the member to the serial
+//    decode, which also produces the reference's verdict for it.  The trailer check runs on the output
+//    either way.
+int inflate_member_speculative(zb200_ctx *ctx, const uint8_t *d_src, uint64_t m0, const HostWrapper &hw, uint8_t *d_dst,
+                               uint64_t dst0, uint64_t mcap, bool count_only, bool &ok, uint64_t &out_len) {
+  ok = false;
+  cudaStream_t s = ctx->stream;
+  const uint64_t lo_bit = (m0 + hw.pos) * 8ull, hi_bit = (m0 + hw.end) * 8ull, limit_byte = m0 + hw.end;
+  const uint32_t cap = (uint32_t)std::min<uint64_t>((hw.end - hw.pos) / 64 + 1024, 1u << 24);
+  ENSURE(ctx->seg_cand, (size_t)cap * 8 + 16);
+  ENSURE(ctx->counter, 64);
+  uint32_t *d_cnt = (uint32_t *)ctx->counter.p + 8;
+  CK(zb_launch_find_blocks(d_src, lo_bit, hi_bit, limit_byte, (uint64_t *)ctx->seg_cand.p, cap, d_cnt, s));
+  uint32_t cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->timing.kernel_launches += 1;
+  if (cnt == 0 || cnt > cap) return ZB200_OK;
+  std::vector<uint64_t> cand(cnt);
+  CK(cudaMemcpyAsync(cand.data(), ctx->seg_cand.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  std::sort(cand.begin(), cand.end());
+  // boundaries: the payload start, then candidates at least min_gap apart (a segment costs a 64 KiB marker prefill)
+  const uint64_t min_gap = 16384ull * 8ull;
+  std::vector<uint64_t> bits(1, lo_bit);
+  for (uint64_t c : cand)
+    if (c >= bits.back() + min_gap && c + min_gap / 4 < hi_bit) bits.push_back(c);
+  const size_t S = bits.size();
+  if (S < 2) return ZB200_OK;
+  std::vector<uint64_t> sb(2 * S);
+  for (size_t i = 0; i < S; i++) {
+    sb[2 * i] = bits[i];
+    sb[2 * i + 1] = i + 1 < S ? bits[i + 1] : hi_bit;
+  }
+  ENSURE(ctx->seg_bits, 2 * S * 8);
+  ENSURE(ctx->seg_dst, (S + 1) * 8);
+  ENSURE(ctx->seg_len, S * 8);
+  ENSURE(ctx->seg_status, S * 4);
+  ENSURE(ctx->seg_kind, S * 4);
+  ENSURE(ctx->seg_expect, S * 4);
+  CK(cudaMemcpyAsync(ctx->seg_bits.p, sb.data(), 2 * S * 8, cudaMemcpyHostToDevice, s));
+  ZbInflateWork w;
+  memset(&w, 0, sizeof(w));
+  w.src = d_src;
+  w.seg_bits = (const uint64_t *)ctx->seg_bits.p;
+  w.seg_limit = limit_byte;
+  w.dst_off = (const uint64_t *)ctx->seg_dst.p;
+  w.out_len = (uint64_t *)ctx->seg_len.p;
+  w.status = (int *)ctx->seg_status.p;
+  w.expect = (uint32_t *)ctx->seg_expect.p;
+  w.kind = (uint32_t *)ctx->seg_kind.p;
+  w.counter = (uint32_t *)ctx->counter.p + 4;
+  w.tabs = ctx->d_tabs;
+  w.n = (uint32_t)S;
+  w.data_format = ZB200_DF_DEFLATE;
+  w.seg_mode = 1;
+  std::vector<uint64_t> sl(S);
+  std::vector<int> sst(S);
+  std::vector<uint32_t> sk(S);
+  auto fetch = [&]() -> int {
+    CK(cudaMemcpyAsync(sl.data(), ctx->seg_len.p, S * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(sst.data(), ctx->seg_status.p, S * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(sk.data(), ctx->seg_kind.p, S * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ZB200_OK;
+  };
+  // 2. the counting pass
+  w.count_only = 1;
+  CK(zb_launch_inflate(w, s));
+  int rc = fetch();
+  if (rc) return rc;
+  ctx->timing.kernel_launches += 1;
+  uint64_t total = 0, scr_elems = 0;
+  uint32_t max_n = 0;
+  for (size_t i = 0; i < S; i++) {
+    if (sst[i] != ZB200_OK || (sk[i] != 0) != (i + 1 == S) || sl[i] > 0xf0000000ull) return ZB200_OK;
+    total += sl[i];
+    scr_elems += 32768ull + sl[i];
+    max_n = std::max<uint32_t>(max_n, (uint32_t)sl[i]);
+  }
+  if (count_only) {
+    ok = true;
+    out_len = total;
+    return ZB200_OK;
+  }
+  if (total > mcap) return ZB200_OK;   // the serial decode reports it
+  // 3. uint16 symbols, markers in front of every segment
+  ENSURE(ctx->mark_scratch, (size_t)scr_elems * 2 + 64);
+  ENSURE(ctx->mark_segs, S * sizeof(ZbMarkSegHost) + 16);
+  std::vector<ZbMarkSegHost> segs(S);
+  std::vector<uint64_t> dof(S + 1);
+  uint64_t se = 0, de = dst0;
+  for (size_t i = 0; i < S; i++) {
+    se += 32768ull;
+    segs[i].scr = se;
+    segs[i].dst = de;
+    segs[i].n = (uint32_t)sl[i];
+    segs[i].pad = 0;
+    dof[i] = se;
+    se += sl[i];
+    de += sl[i];
+  }
+  dof[S] = se;
+  const std::vector<uint64_t> want = sl;
+  CK(cudaMemcpyAsync(ctx->mark_segs.p, segs.data(), S * sizeof(ZbMarkSegHost), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->seg_dst.p, dof.data(), (S + 1) * 8, cudaMemcpyHostToDevice, s));
+  int *d_bad = (int *)((uint32_t *)ctx->counter.p + 12);
+  CK(cudaMemsetAsync(d_bad, 0, 4, s));
+  CK(zb_launch_mark_prefill((uint16_t *)ctx->mark_scratch.p, ctx->mark_segs.p, (uint32_t)S, s));
+  w.count_only = 0;
+  w.mark = 1;
+  w.dst = (uint8_t *)ctx->mark_scratch.p;
+  CK(zb_launch_inflate(w, s));
+  rc = fetch();
+  if (rc) return rc;
+  ctx->timing.kernel_launches += 2;
+  for (size_t i = 0; i < S; i++)
+    if (sst[i] != ZB200_OK || sl[i] != want[i]) return ZB200_OK;
+  // 4. markers -> bytes
+  CK(zb_launch_resolve((const uint16_t *)ctx->mark_scratch.p, ctx->mark_segs.p, (uint32_t)S, max_n, d_dst, d_bad, s));
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->timing.kernel_launches += 2;
+  if (bad) return ZB200_OK;
+  ok = true;
+  out_len = total;
+  return ZB200_OK;
+}
+
 // Tries every large member; `done` gets the members that were fully decoded here (their output
 // is in place; status / length / kind / expect still have to be written to the device arrays).
 int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *src_offsets, size_t n, int data_format,
@@ -501,6 +641,29 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
     if (!host_parse_wrapper(head, hn, tail, len, data_format, raw_pos, hw)) continue;
     if (count_only && hw.fmt == ZB200_DF_GZIP) continue;  // ISIZE answers that (gzip.nim:66)
     if (hw.end <= hw.pos + 4) continue;
+    const uint64_t dst0_m = count_only ? 0 : dst_offsets[m], mcap_m = count_only ? ~0ull : dst_offsets[m + 1] - dst_offsets[m];
+    // streams without sync markers (or whose pieces are not independent): speculative segments
+    auto speculative = [&]() -> int {
+      bool sok = false;
+      uint64_t slen = 0;
+      int src_ = inflate_member_speculative(ctx, d_src, m0, hw, d_dst, dst0_m, mcap_m, count_only, sok, slen);
+      if (src_) return src_;
+      if (sok) {
+        BigResult r;
+        r.member = m;
+        r.out_len = slen;
+        r.kind = (uint32_t)hw.fmt;
+        r.expect = hw.expect;
+        done.push_back(r);
+      }
+      return ZB200_OK;
+    };
+#define ZB_TRY_SPECULATIVE()      \
+  {                               \
+    int _rc = speculative();      \
+    if (_rc) return _rc;          \
+    continue;                     \
+  }
     // 1. candidate boundaries
     const uint32_t cap = (uint32_t)std::min<uint64_t>((hw.end - hw.pos) / 32 + 64, 1u << 24);
     ENSURE(ctx->seg_cand, (size_t)cap * 8 + 16);
@@ -510,7 +673,7 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
     uint32_t cnt = 0;
     CK(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (cnt == 0 || cnt > cap) continue;
+    if (cnt == 0 || cnt > cap) ZB_TRY_SPECULATIVE();
     std::vector<uint64_t> bounds(cnt + 2);
     CK(cudaMemcpyAsync(bounds.data() + 1, ctx->seg_cand.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -519,7 +682,7 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
     size_t S = cnt + 1;
     if (bounds[cnt] >= hw.end) S = cnt;  // the payload ends with a marker: no trailing segment
     else bounds[cnt + 1] = hw.end;
-    if (S < 2) continue;
+    if (S < 2) ZB_TRY_SPECULATIVE();
     for (size_t j = 0; j <= S; j++) bounds[j] += m0;  // absolute in d_src
     ENSURE(ctx->seg_src, (S + 1) * 8);
     ENSURE(ctx->seg_dst, (S + 1) * 8);
@@ -586,7 +749,7 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
         ok = sst[j] == ZB200_OK && (sk[j] != 0) == (j + 1 == S);
         dof[j + 1] = dof[j] + sl[j];
       }
-      if (!ok || dof[S] - dst0 > mcap || dof[S] - dst0 > 0xfffffdffull) continue;
+      if (!ok || dof[S] - dst0 > mcap) ZB_TRY_SPECULATIVE();
       if (!count_only) {
         std::vector<uint64_t> want = sl;
         CK(cudaMemcpyAsync(ctx->seg_dst.p, dof.data(), (S + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -596,7 +759,7 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
         if (rc) return rc;
         ctx->timing.kernel_launches += 1;
         for (size_t j = 0; j < S && ok; j++) ok = sst[j] == ZB200_OK && sl[j] == want[j];
-        if (!ok) continue;
+        if (!ok) ZB_TRY_SPECULATIVE();
       }
     }
     BigResult r;
@@ -1038,7 +1201,7 @@ void zb200_shutdown(zb200_ctx *ctx) {
                     &ctx->cb, &ctx->chunk_off, &ctx->member_off, &ctx->member_check, &ctx->member_isize,
                     &ctx->src_off, &ctx->dst_off, &ctx->out_len, &ctx->status, &ctx->expect, &ctx->kind,
                     &ctx->counter, &ctx->ck_out, &ctx->ck_pieces, &ctx->ck_first, &ctx->ck_piece_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables,
-                    &ctx->seg_src, &ctx->seg_dst, &ctx->seg_len, &ctx->seg_status, &ctx->seg_kind, &ctx->seg_expect, &ctx->seg_cand, &ctx->skip_mask, &ctx->order};
+                    &ctx->seg_src, &ctx->seg_dst, &ctx->seg_len, &ctx->seg_status, &ctx->seg_kind, &ctx->seg_expect, &ctx->seg_cand, &ctx->skip_mask, &ctx->order, &ctx->mark_scratch, &ctx->mark_segs, &ctx->seg_bits};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_tabs) cudaFree(ctx->d_tabs);

@@ -234,8 +234,17 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
       if (warp > 0) {
         // pre-seed the private table with the positions just before this sub-chunk
         for (uint32_t s = b0 - LZ_PRESEED; s < b0; s += 32) {
-          uint32_t p = s + (uint32_t)lane;
-          if (p + 4 <= len) table[lz_hash(zb_ld32_unaligned(data, mis + p))] = (uint16_t)p;
+          const uint32_t p = s + (uint32_t)lane;
+          const bool can = p + 4 <= len;
+          const uint32_t h = lz_hash(zb_ld32_unaligned(data, mis + p));
+          if (can) table[h] = (uint16_t)p;
+          __syncwarp();
+          for (;;) {  // same-entry stores of one instruction: the highest position wins (see the main loop)
+            const bool lost = can && table[h] < (uint16_t)p;
+            if (!__any_sync(ZB_FULL, lost)) break;
+            if (lost) table[h] = (uint16_t)p;
+            __syncwarp();
+          }
         }
         __syncwarp();
       }
@@ -260,10 +269,18 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           c = table[h];
           __syncwarp();
           // Lanes of this window that share a hash store to the same entry in one instruction:
-          // exactly one of them lands (any is a valid, later-verified candidate).  Resolving the
-          // winner with __match_any_sync costs 30 % of the kernel (measured), so it is left to the
-          // hardware's fixed arbitration; output is repeatable run to run on the same GPU.
+          // exactly one of them lands, and WHICH is up to the hardware (resolving the winner with
+          // __match_any_sync costs 30 % of the kernel, measured) ...
           if (can) table[h] = (uint16_t)p;
+          __syncwarp();
+          // ... so make the outcome independent of it: the highest position wins (full-size runs were NOT
+          // identical run to run without this; every round strictly raises the entry, so it ends)
+          for (;;) {
+            const bool lost = can && table[h] < (uint16_t)p;
+            if (!__any_sync(ZB_FULL, lost)) break;
+            if (lost) table[h] = (uint16_t)p;
+            __syncwarp();
+          }
           // a match may not cross the sub-chunk end (the next warp starts its own parse there)
           const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
           if (can && c < p && p - c <= ZB_MAX_DIST && p >= entry && limit >= ZB_MIN_MATCH) {
@@ -335,22 +352,23 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 // head/chain arrays -- 256 KiB + 64 KiB per block -- do not fit next to the data).
 // Same CTA = chunk / warp = 8 KiB sub-chunk mapping as k_lz; the chunk is staged together with up
 // to 32 KiB of the member's preceding bytes so a match can reach back the full DEFLATE window across
-// chunk boundaries.  The dictionary is cut into 8 KiB SEGMENTS (= sub-chunks), one 2048-bucket x
-// 4-way table of u16 positions per segment (as many slots as positions; a bucket keeps the most
-// recent four of its hash), all in global memory / L2, one set per resident CTA:
+// chunk boundaries.  The dictionary is cut into 8 KiB SEGMENTS (= sub-chunks), 16 KiB of u16 positions
+// per segment, all in global memory / L2, one set per resident CTA:
 //  * phase 1, BUILD: the segments that lie BEFORE some sub-chunk of this chunk (the staged history
-//    and all but the last sub-chunk) get a static table, each built once by one warp inserting the
-//    segment's positions in order.  (The first version gave every warp a private table pre-seeded
-//    with its own 32 KiB of history: every position was inserted five times and the 155 MB of tables
-//    thrashed the L2 -- 80 % of that kernel was pre-seeding.)
+//    and all but the last sub-chunk) get a static, direct-mapped table: 8192 entries, entry = the
+//    most recent position of the segment with that 13-bit hash.  Plain 2-byte stores, ten
+//    instructions per 32 positions, each segment built once.  (The first version gave every warp a
+//    private table pre-seeded with its own 32 KiB of history: every position was inserted five times
+//    and the 155 MB of tables thrashed the L2 -- 80 % of that kernel was pre-seeding.)
 //  * phase 2, PARSE: a warp walks its sub-chunk 32 positions per step; a lane's candidates are the
 //    nearest same-hash position inside the window, the four ways of its bucket in the warp's own
-//    incremental table (positions of this sub-chunk seen so far) and the four ways of its bucket in
-//    each of the four preceding segments' static tables -- five independent 8-byte loads instead of
-//    a dependent chain walk (the reference follows up to `chain` links, lz77.nim:88-109).  Candidates
-//    are verified / extended against shared memory nearest first under the level's budget:
-//    at most `maxcand` verified candidates, one more once a match of `good` bytes is in hand
-//    (lz77.nim:104 quarters its budget there); the longest wins;
+//    incremental table (2048 buckets x 4 most recent positions of this sub-chunk so far) and the
+//    entry of its hash in each of the four preceding segments' static tables -- nine candidates from
+//    five independent loads instead of a dependent chain walk (the reference follows up to `chain`
+//    links, lz77.nim:88-109).  Candidates are verified / extended against shared memory nearest first
+//    under the level's budget: `nslots` candidates looked at, at most `maxcand` of them verified, one
+//    more once a match of `good` bytes is in hand (lz77.nim:104 quarters its budget there); the
+//    longest wins;
 //  * one-step lazy evaluation: a match shorter than `lazy` is dropped when the next position has a
 //    longer one (the reference is greedy; this recovers what the bounded search loses).
 #define LZ2_HIST 32768
@@ -371,7 +389,10 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 #define LZ2_SM_TOTAL (LZ2_SM_BAR + 16)
 static_assert(2 * (LZ2_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
 
-__device__ __forceinline__ uint32_t lz2_hash(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - LZ2_BUCKET_BITS); }
+#define LZ2_STATIC_BITS 13                                          // direct-mapped static tables: 8192 x u16 = one own table's size
+// own bucket = the top 11 bits of the product, static entry = the top 13
+__device__ __forceinline__ uint32_t lz2_hash_mul(uint32_t v) { return v * 0x9E3779B1u; }
+__device__ __forceinline__ uint32_t lz2_hash(uint32_t v) { return lz2_hash_mul(v) >> (32 - LZ2_BUCKET_BITS); }
 
 // shift `e` into way 0 of a bucket of four u16 entries (most recent first)
 __device__ __forceinline__ uint2 lz2_push(uint2 b, uint32_t e) {
@@ -532,8 +553,6 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     }
 
     // ---- phase 1: static tables of every segment that precedes some sub-chunk of this chunk ----
-    // Slot s of a bucket holds the most recent position whose 32-byte window index is s (mod 4): plain
-    // 2-byte stores, no read-modify-write, so a segment costs ten instructions per 32 positions.
     {
       const uint32_t nseg = (rlen + LZ2_SEG_BYTES - 1) / LZ2_SEG_BYTES;  // segments of the region; the last is never history
       for (uint32_t sg = (uint32_t)warp; sg + 1 < nseg; sg += ZB_WARPS_PER_CHUNK) {
@@ -542,12 +561,21 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
         __syncwarp();
         uint16_t *tab16 = reinterpret_cast<uint16_t *>(tab);
         const uint32_t q0 = sg * LZ2_SEG_BYTES, q1 = q0 + LZ2_SEG_BYTES;  // a full segment (only the last one can be short)
-#pragma unroll 4
         for (uint32_t s = q0; s < q1; s += 32) {
           const uint32_t q = s + (uint32_t)lane;
           const uint32_t v = zb_ld32_unaligned(data, mis + q);
-          // lanes of one window that share a hash write the same slot in one instruction: one of them lands
-          if (q + 4 <= rlen) tab16[(lz2_hash(v) << 2) + ((s >> 5) & 3u)] = (uint16_t)q;
+          const uint32_t hs = lz2_hash_mul(v) >> (32 - LZ2_STATIC_BITS);
+          const bool can = q + 4 <= rlen;
+          if (can) __stcg(&tab16[hs], (uint16_t)q);
+          __syncwarp();
+          // lanes of one window that share a hash stored to one entry in one instruction: make the highest
+          // position win whatever the hardware picked (a later window always overwrites an earlier one)
+          for (;;) {
+            const bool lost = can && (uint16_t)(__ldcg(&tab16[hs]) - (uint16_t)s) < (uint16_t)lane;
+            if (!__any_sync(ZB_FULL, lost)) break;
+            if (lost) __stcg(&tab16[hs], (uint16_t)q);
+            __syncwarp();
+          }
         }
       }
     }
@@ -570,13 +598,15 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
         const uint32_t h = lz2_hash(v);
         const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
         const bool search = entry < wb + 32 && can && p >= entry && limit >= ZB_MIN_MATCH;
-        // history buckets: four independent loads, in flight while the own table is updated
-        uint2 hbk[4];
+        // history: the entry of this hash in each of the four preceding segments' tables -- four
+        // independent 2-byte loads, in flight while the own table is updated
+        const uint32_t hs = lz2_hash_mul(v) >> (32 - LZ2_STATIC_BITS);
+        uint32_t hcand[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          hbk[j] = make_uint2(~0u, ~0u);
-          if (search && myseg > (uint32_t)j && prm.nslots > 5u + 4u * (uint32_t)j)
-            hbk[j] = __ldcg(&stat[(size_t)(myseg - 1u - (uint32_t)j) * LZ2_BUCKETS + h]);
+          hcand[j] = 0xffffu;
+          if (search && myseg > (uint32_t)j && prm.nslots > 5u + (uint32_t)j)
+            hcand[j] = __ldcg(reinterpret_cast<const uint16_t *>(stat + (size_t)(myseg - 1u - (uint32_t)j) * LZ2_BUCKETS) + hs);
         }
         uint32_t grp;
         const uint2 bucket = lz2_probe_insert(own, h, can, q - (uint32_t)lane, grp);
@@ -597,7 +627,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           // candidate slots, nearest first; the level decides how many are looked at (nslots):
           //   0      the closest same-hash position inside this window
           //   1..4   the own bucket, most recent first
-          //   5..20  the four preceding segments' buckets, each from its most recent window residue down
+          //   5..8   the entries of the four preceding segments, nearest segment first
           if (search) {
             const uint32_t lower = grp & ((1u << lane) - 1u);
             if (lower) lz2_try(P, data, q - ((uint32_t)lane - (uint32_t)(31 - __clz((int)lower))), prm.good, m, dist, budget);
@@ -608,12 +638,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            if (prm.nslots > 5u + 4u * (uint32_t)j && __any_sync(ZB_FULL, budget > 0 && m < P.stop)) {
-              lz2_try(P, data, hbk[j].y >> 16, prm.good, m, dist, budget);
-              if (prm.nslots > 6u + 4u * (uint32_t)j) lz2_try(P, data, hbk[j].y & 0xffffu, prm.good, m, dist, budget);
-              if (prm.nslots > 7u + 4u * (uint32_t)j) lz2_try(P, data, hbk[j].x >> 16, prm.good, m, dist, budget);
-              if (prm.nslots > 8u + 4u * (uint32_t)j) lz2_try(P, data, hbk[j].x & 0xffffu, prm.good, m, dist, budget);
-            }
+            if (prm.nslots > 5u + (uint32_t)j && __any_sync(ZB_FULL, budget > 0 && m < P.stop))
+              lz2_try(P, data, hcand[j], prm.good, m, dist, budget);
           }
           // one-step lazy evaluation (zlib's max_lazy idea)
           const uint32_t mnext = __shfl_down_sync(ZB_FULL, m, 1);
@@ -1063,8 +1089,8 @@ static bool zb_is_lz_level(int level) { return level == -1 || level >= 2; }
 // compressed size are monotone in the level.
 ZbLz2Params zb_lz2_params(int level) {
   //                                     nslots maxcand good lazy
-  static const ZbLz2Params table[10] = {{12, 8, 8, 16},  {12, 8, 8, 16},  {5, 2, 4, 0},    {5, 3, 4, 6},    {7, 4, 4, 8},
-                                        {9, 6, 8, 16},   {12, 8, 8, 16},  {14, 12, 8, 32}, {21, 21, 16, 32}, {21, 21, 32, 64}};
+  static const ZbLz2Params table[10] = {{9, 8, 8, 16},  {9, 8, 8, 16},  {5, 2, 4, 0},   {6, 3, 4, 6},   {7, 4, 4, 8},
+                                        {8, 6, 8, 16},  {9, 8, 8, 16},  {9, 9, 8, 32},  {9, 9, 16, 32}, {9, 9, 32, 64}};
   return table[(level >= 2 && level <= 9) ? level : 6];  // -1 (Default) = level 6
 }
 size_t zb_lz2_table_bytes(int *grid_out) {

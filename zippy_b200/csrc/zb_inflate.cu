@@ -17,6 +17,8 @@
 // the chain lane-parallel afterwards (32 raw tokens per member are validated, placed by a prefix
 // sum and copied one lane per token).  Large members are split at sync markers into segments
 // that run through the same kernel in parallel (zb_api.cu: inflate_big_members).
+#include <type_traits>
+
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 #include "zb_wrapper.h"
@@ -294,10 +296,14 @@ __device__ __forceinline__ uint32_t decode_clc(BitReader &b, const GroupSmem *gs
 // whose index is stored to bad_k; only the tokens before it are written and counted in op.
 #define INF_ROUNDS (32 / INF_G)
 #define INF_LONG_MATCH 24u
-template <bool COUNT_ONLY>
-__device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t cap, const uint32_t (&ta)[INF_ROUNDS],
-                                            const uint32_t (&tb)[INF_ROUNDS], uint32_t ntok, uint32_t len_addr,
-                                            uint32_t dist_addr, uint32_t &bad_k) {
+// OutT is uint8_t, or uint16_t when a segment of a large member is decoded without its window
+// (zb_api.cu: speculative segments): the 32768 elements in front of `out` then hold marker symbols
+// 0x8000 | k standing for "byte k of the unknown window", copies move markers like literals, and `win`
+// (0 or 32768) is how far before its own start the segment may reach.
+template <bool COUNT_ONLY, typename OutT>
+__device__ __forceinline__ int flush_tokens(OutT *out, uint32_t &op, uint32_t cap, uint32_t win,
+                                            const uint32_t (&ta)[INF_ROUNDS], const uint32_t (&tb)[INF_ROUNDS],
+                                            uint32_t ntok, uint32_t len_addr, uint32_t dist_addr, uint32_t &bad_k) {
   const int lane = g_lane();
   const uint32_t gsel = INF_G == 32 ? 0xffffffffu : ((1u << INF_G) - 1u);
   const uint32_t batch_op = op;
@@ -324,7 +330,7 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
     }
     rel[r] = base + incl - len[r];  // output offset inside the batch
     base += __shfl_sync(FULL_MASK, incl, INF_G - 1, INF_G);
-    const bool bad = is_m[r] && (lidx >= 29u || dsym >= 30u || dist[r] > batch_op + rel[r]);
+    const bool bad = is_m[r] && (lidx >= 29u || dsym >= 30u || dist[r] > batch_op + rel[r] + win);
     const bool noroom = act && rel[r] + len[r] > cap - batch_op;
     badm[r] = (__ballot_sync(FULL_MASK, bad) >> g_shift()) & gsel;
     evm[r] = (__ballot_sync(FULL_MASK, bad || noroom) >> g_shift()) & gsel;
@@ -354,26 +360,26 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
   op = batch_op + total;
   if (COUNT_ONLY) return ev;
   __syncwarp();  // stores of earlier batches are visible to every lane from here on
-  uint8_t *const bout = out + batch_op;
+  OutT *const bout = out + batch_op;
   // parallel part, 4 bytes per token and pass
   uint32_t more = 0;
 #pragma unroll
   for (int r = 0; r < INF_ROUNDS; r++) {
     dep[r] = is_m[r] && (dist[r] < rel[r] + len[r] || len[r] > INF_LONG_MATCH);
     if (len[r] != 0u && !is_m[r]) {
-      bout[rel[r]] = (uint8_t)ta[r];
-      if (len[r] == 2u) bout[rel[r] + 1u] = (uint8_t)(ta[r] >> 14);
+      bout[rel[r]] = (OutT)(uint8_t)ta[r];
+      if (len[r] == 2u) bout[rel[r] + 1u] = (OutT)(uint8_t)(ta[r] >> 14);
     }
     if (is_m[r] && !dep[r] && len[r] > 4u) more |= 1u << r;
   }
   {
-    uint8_t v[INF_ROUNDS][4];
+    OutT v[INF_ROUNDS][4];
 #pragma unroll
     for (int r = 0; r < INF_ROUNDS; r++) {
-      const uint8_t *from = bout + rel[r] - dist[r];
+      const OutT *from = bout + rel[r] - dist[r];
       const bool go = is_m[r] && !dep[r];
 #pragma unroll
-      for (int k = 0; k < 4; k++) v[r][k] = (go && (uint32_t)k < len[r]) ? from[k] : (uint8_t)0;
+      for (int k = 0; k < 4; k++) v[r][k] = (go && (uint32_t)k < len[r]) ? from[k] : (OutT)0;
     }
 #pragma unroll
     for (int r = 0; r < INF_ROUNDS; r++) {
@@ -387,11 +393,11 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
 #pragma unroll
     for (int r = 0; r < INF_ROUNDS; r++) {
       if (more & (1u << r)) {
-        uint8_t *to = bout + rel[r];
-        const uint8_t *from = to - dist[r];
+        OutT *to = bout + rel[r];
+        const OutT *from = to - dist[r];
         for (uint32_t k = 4; k < len[r]; k += 4) {
-          uint8_t c0 = from[k], c1 = k + 1 < len[r] ? from[k + 1] : (uint8_t)0, c2 = k + 2 < len[r] ? from[k + 2] : (uint8_t)0,
-                  c3 = k + 3 < len[r] ? from[k + 3] : (uint8_t)0;
+          OutT c0 = from[k], c1 = k + 1 < len[r] ? from[k + 1] : (OutT)0, c2 = k + 2 < len[r] ? from[k + 2] : (OutT)0,
+               c3 = k + 3 < len[r] ? from[k + 3] : (OutT)0;
           to[k] = c0;
           if (k + 1 < len[r]) to[k + 1] = c1;
           if (k + 2 < len[r]) to[k + 2] = c2;
@@ -410,8 +416,8 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
       const uint32_t rj = g_shfl(rel[r], j), lj = g_shfl(len[r], j);
       const uint32_t dj = g_shfl(dist[r], j);
       g_sync();
-      uint8_t *tj = bout + rj;
-      const uint8_t *fj = tj - dj;
+      OutT *tj = bout + rj;
+      const OutT *fj = tj - dj;
       if (dj >= lj) {
         for (uint32_t i = (uint32_t)lane; i < lj; i += INF_G) tj[i] = fj[i];
       } else {
@@ -424,12 +430,14 @@ __device__ __forceinline__ int flush_tokens(uint8_t *out, uint32_t &op, uint32_t
 
 // ---- per-group decoder state (identical in every lane of the group) ----
 enum { ST_FETCH = 0, ST_BLOCK = 1, ST_SYMS = 2, ST_EXIT = 3 };
+template <typename OutT>
 struct Grp {
   BitReader b;
   const uint8_t *src;   // member bytes
   uint64_t len;
-  uint8_t *out;
+  OutT *out;
   uint32_t shift0, cap, op, idx, kind, expect;
+  uint32_t win;         // elements in front of `out` a back-reference may reach (speculative segments: 32768)
   int st;
   bool final_block;
 };
@@ -438,8 +446,8 @@ struct Grp {
 // Returns BLK_SYMS when the decode tables are ready for the symbol loop, BLK_DONE when the block
 // is already complete (stored), or a (positive) ZB_ERR_*.
 enum { BLK_SYMS = -1, BLK_DONE = -2 };
-template <bool COUNT_ONLY>
-__device__ __forceinline__ int begin_block(Grp &g, GroupSmem *gs) {
+template <bool COUNT_ONLY, typename OutT>
+__device__ __forceinline__ int begin_block(Grp<OutT> &g, GroupSmem *gs) {
   const int lane = g_lane();
   const uint8_t clcl_order[19] = ZB_CLCL_ORDER;
   BitReader &b = g.b;
@@ -459,7 +467,7 @@ __device__ __forceinline__ int begin_block(Grp &g, GroupSmem *gs) {
       if (byte_pos + l > g.len) return ZB_ERR_END_OF_BUFFER;
       if (l > g.cap - g.op) return ZB_ERR_DST_TOO_SMALL;
       if (!COUNT_ONLY)
-        for (uint32_t i = (uint32_t)lane; i < l; i += INF_G) g.out[g.op + i] = g.src[byte_pos + i];
+        for (uint32_t i = (uint32_t)lane; i < l; i += INF_G) g.out[g.op + i] = (OutT)g.src[byte_pos + i];
       g.op += l;
       br_seek(b, g.shift0, byte_pos + l);
     }
@@ -542,8 +550,8 @@ __device__ __forceinline__ int begin_block(Grp &g, GroupSmem *gs) {
 // slot k / INF_G) and then flushed; a group that reaches the end of its block idles until the
 // batch ends, the loop stops, and the caller resolves the event.
 // Returns 0 (another group stopped the loop), 1 (end of block) or 100 + ZB_ERR_*.
-template <bool COUNT_ONLY>
-__device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t tab_addr) {
+template <bool COUNT_ONLY, typename OutT>
+__device__ __forceinline__ int symbol_loop(Grp<OutT> &g, const GroupSmem *gs, uint32_t tab_addr) {
   const int lane = g_lane();
   bool act = g.st == ST_SYMS;
   BitReader &b = g.b;
@@ -619,7 +627,9 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
       }
     }
     uint32_t bad_k = 0;
-    const int fev = flush_tokens<COUNT_ONLY>(g.out, op, g.cap, ta, tb, ntok, len_addr, dist_addr, bad_k);
+    // only the counting and the marker kernels ever see a segment with a window in front of it
+    const uint32_t win = (COUNT_ONLY || sizeof(OutT) == 2) ? g.win : 0u;
+    const int fev = flush_tokens<COUNT_ONLY, OutT>(g.out, op, g.cap, win, ta, tb, ntok, len_addr, dist_addr, bad_k);
     // a group that stopped: end of block (symbol 256), or a reader far past the end of its input
     ev = (act0 && !act) ? (b.overrun ? 100 + ZB_ERR_END_OF_BUFFER : 1) : 0;
     if (fev) {
@@ -643,9 +653,10 @@ __device__ __forceinline__ int symbol_loop(Grp &g, const GroupSmem *gs, uint32_t
 #ifndef INF_MIN_CTAS
 #define INF_MIN_CTAS 5   // register budget for 5 CTAs (20 warps) per SM, the shared-memory limit
 #endif
-template <bool COUNT_ONLY>
+template <bool COUNT_ONLY, bool MARK>
 __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
     k_inflate(ZbInflateWork w) {
+  typedef typename std::conditional<MARK, uint16_t, uint8_t>::type OutT;
   extern __shared__ __align__(16) unsigned char inf_smem[];
   // base | extra bits << 16 (RFC 1951 3.2.5), unused slots 0; placed after the groups' tables
   uint32_t *len_tab = reinterpret_cast<uint32_t *>(inf_smem + INF_GROUPS * sizeof(GroupSmem));
@@ -660,8 +671,9 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
     dist_tab[c] = c < 30 ? (zb_dist_base(c) | ((uint32_t)zb_dist_extra_bits(c) << 16)) : 0u;
   }
   __syncthreads();
-  Grp g;
+  Grp<OutT> g;
   g.st = ST_FETCH;
+  g.win = 0;
   g.b.gbase = nullptr;
   g.b.nwords = 0;
   g.b.cur = g.b.nxt = g.b.over_word = 0;
@@ -682,9 +694,35 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
         g.st = ST_EXIT;
       } else if (w.skip && w.skip[i]) {
         // handled elsewhere (a large member decoded as parallel segments): fetch the next one
+      } else if ((COUNT_ONLY || MARK) && w.seg_bits) {
+        // a speculative segment of one raw stream: bit-exact start and end inside w.src; bits beyond the
+        // end are the next segment's (real data), so an over-read is harmless and an over-RUN is caught
+        const uint64_t sb = w.seg_bits[2 * i], eb = w.seg_bits[2 * i + 1];
+        const uint64_t byte0 = sb >> 3;
+        g.idx = i;
+        g.src = w.src + byte0;
+        g.len = w.seg_limit - byte0;
+        g.op = 0;
+        g.final_block = false;
+        g.kind = ZB_DF_DEFLATE;
+        g.expect = 0;
+        g.win = i == 0 ? 0u : 32768u;   // segment 0 starts the stream: it has no window
+        g.out = COUNT_ONLY ? nullptr : reinterpret_cast<OutT *>(w.dst) + w.dst_off[i];
+        const uint64_t cap64 = COUNT_ONLY ? ~0ull : w.dst_off[i + 1] - w.dst_off[i];
+        g.cap = (uint32_t)min(cap64, (uint64_t)0xfffffdffu - 32768u);
+        g.shift0 = (uint32_t)((uintptr_t)g.src & 3u);
+        g.b.gbase = reinterpret_cast<const uint32_t *>(g.src - g.shift0);
+        g.b.nwords = (uint32_t)min((uint64_t)0xffffffffu, (g.shift0 + g.len + 3u) >> 2);
+        g.b.end_bit = g.shift0 * 8ull + (eb - byte0 * 8ull);
+        g.b.over_word = (uint32_t)((g.b.end_bit + 64ull) >> 5);
+        g.b.overrun = false;
+        br_seek(g.b, g.shift0, 0);
+        br_skip<false>(g.b, (uint32_t)(sb & 7ull));
+        g.st = ST_BLOCK;
       } else {
         const uint64_t s0 = w.src_off[i], s1 = w.src_off[i + 1];
         g.idx = i;
+        g.win = 0;
         g.src = w.src + s0;
         g.len = s1 - s0;
         g.op = 0;
@@ -702,7 +740,7 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
           fin = true;
           done = st;
         } else {
-          g.out = COUNT_ONLY ? nullptr : w.dst + w.dst_off[i];
+          g.out = COUNT_ONLY ? nullptr : reinterpret_cast<OutT *>(w.dst) + w.dst_off[i];
           const uint64_t cap64 = COUNT_ONLY ? ~0ull : w.dst_off[i + 1] - w.dst_off[i];
           // positions are 32-bit inside a member (a single member's output is limited to 4 GiB - 1);
           // op + tlen is computed in 32 bits: keep 512 bytes of headroom below 2^32
@@ -721,7 +759,7 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
       fin = true;  // the segment's input is used up at a block boundary
       done = ZB_OK;
     } else if (g.st == ST_BLOCK) {
-      int r = begin_block<COUNT_ONLY>(g, gs);
+      int r = begin_block<COUNT_ONLY, OutT>(g, gs);
       if (r >= 0) {
         fin = true;
         done = r;
@@ -746,7 +784,7 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
     // run the lockstep symbol loop only when no group of the warp is waiting for a header or a
     // new member: those are short, and would otherwise stall behind a whole block of symbols
     if (__any_sync(FULL_MASK, g.st == ST_FETCH || g.st == ST_BLOCK)) continue;
-    const int ev = symbol_loop<COUNT_ONLY>(g, gs, tab_addr);
+    const int ev = symbol_loop<COUNT_ONLY, OutT>(g, gs, tab_addr);
     if (g.st == ST_SYMS && ev) {
       int st = ZB_OK;
       if (ev == 1) {
@@ -968,6 +1006,236 @@ __global__ void __launch_bounds__(256) k_find_sync(const uint8_t *src, uint64_t 
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Speculative segments of ONE large raw-deflate stream (the reference decodes any stream
+// at 0.5-1.6 GB/s on a CPU core, inflate.nim:173-250 -- a single 8-lane group here is ~50x slower, so a
+// large foreign member has to be cut).  A stream can only be entered at a block boundary, and nothing
+// in it says where those are: k_find_blocks tests EVERY bit offset of the payload for a plausible
+// dynamic-block header (BTYPE = 2, HLIT/HDIST in range, a COMPLETE code-length code, code lengths that
+// parse to exactly HLIT + HDIST entries, a complete literal/length code that can encode end-of-block,
+// a distance code that is not over-subscribed).  Random data passes with vanishing probability, and a
+// false candidate is caught later anyway: the decode of the previous segment must END exactly on it.
+__device__ __forceinline__ uint64_t fb_ld64(const uint8_t *src, uint64_t byte, uint64_t limit) {
+  uint64_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if (byte + (uint64_t)k < limit) v |= (uint64_t)src[byte + (uint64_t)k] << (8 * k);
+  return v;
+}
+// up to 32 bits at absolute bit position `bit`
+__device__ __forceinline__ uint32_t fb_bits(const uint8_t *src, uint64_t bit, uint64_t limit_byte) {
+  const uint64_t w = fb_ld64(src, bit >> 3, limit_byte);
+  return (uint32_t)(w >> (bit & 7ull));
+}
+
+__device__ bool fb_full_check(const uint8_t *src, uint64_t bit, uint64_t limit_byte) {
+  const uint8_t order[19] = ZB_CLCL_ORDER;
+  uint32_t hdr = fb_bits(src, bit, limit_byte);
+  const int hlit = (int)((hdr >> 3) & 31u) + 257, hdist = (int)((hdr >> 8) & 31u) + 1, hclen = (int)((hdr >> 13) & 15u) + 4;
+  uint64_t pos = bit + 17;
+  uint8_t cl[19];
+  for (int i = 0; i < 19; i++) cl[i] = 0;
+  for (int i = 0; i < hclen; i++, pos += 3) cl[order[i]] = (uint8_t)(fb_bits(src, pos, limit_byte) & 7u);
+  // canonical code-length code -> 128-entry lookup: symbol | len << 5
+  uint8_t tab[128];
+  for (int i = 0; i < 128; i++) tab[i] = 0;
+  {
+    uint32_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8];
+    for (int i = 0; i < 19; i++) count[cl[i]]++;
+    count[0] = 0;
+    uint32_t code = 0;
+    for (int l = 1; l < 8; l++) {
+      code = (code + count[l - 1]) << 1;
+      next[l] = code;
+    }
+    for (int sy = 0; sy < 19; sy++) {
+      const int l = cl[sy];
+      if (!l) continue;
+      const uint32_t c = next[l]++;
+      const uint32_t rev = __brev(c) >> (32 - l);
+      for (uint32_t idx = rev; idx < 128u; idx += 1u << l) tab[idx] = (uint8_t)(sy | (l << 5));
+    }
+  }
+  uint8_t lens[320];
+  const int total = hlit + hdist;
+  int i = 0;
+  uint32_t prev = 0;
+  while (i < total) {
+    if ((pos >> 3) >= limit_byte) return false;
+    const uint32_t x = fb_bits(src, pos, limit_byte);
+    const uint32_t e = tab[x & 127u];
+    const uint32_t l = e >> 5, sym = e & 31u;
+    if (l == 0) return false;
+    pos += l;
+    const uint32_t y = x >> l;
+    if (sym <= 15) {
+      lens[i++] = (uint8_t)sym;
+      prev = sym;
+    } else {
+      int rep;
+      uint32_t v = 0;
+      if (sym == 16) {
+        if (i == 0) return false;
+        rep = 3 + (int)(y & 3u);
+        pos += 2;
+        v = prev;
+      } else if (sym == 17) {
+        rep = 3 + (int)(y & 7u);
+        pos += 3;
+        prev = 0;
+      } else {
+        rep = 11 + (int)(y & 127u);
+        pos += 7;
+        prev = 0;
+      }
+      if (i + rep > total) return false;
+      for (int k = 0; k < rep; k++) lens[i++] = (uint8_t)v;
+    }
+  }
+  if (lens[256] == 0) return false;  // end-of-block must have a code
+  uint32_t kl = 0, kd = 0, nd = 0;
+  for (int k = 0; k < hlit; k++)
+    if (lens[k]) kl += 32768u >> lens[k];
+  for (int k = 0; k < hdist; k++)
+    if (lens[hlit + k]) {
+      kd += 32768u >> lens[hlit + k];
+      nd++;
+    }
+  if (kl != 32768u) return false;                 // every encoder emits a complete literal/length code
+  if (kd > 32768u) return false;                  // over-subscribed
+  if (kd != 32768u && nd > 1) return false;       // incomplete only in the one-code (or no-code) case
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_find_blocks(const uint8_t *src, uint64_t lo_bit, uint64_t hi_bit, uint64_t limit_byte,
+                                                     uint64_t *out, uint32_t cap, uint32_t *count) {
+  const uint8_t order[19] = ZB_CLCL_ORDER;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t bit = lo_bit + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; bit + 80 <= hi_bit; bit += stride) {
+    // the 17 fixed header bits + 19 x 3 bits of code-length code lengths live in 74 bits
+    const uint64_t byte = bit >> 3;
+    const uint32_t sh = (uint32_t)(bit & 7ull);
+    const uint64_t w0 = fb_ld64(src, byte, limit_byte), w1 = fb_ld64(src, byte + 8, limit_byte);
+    const uint64_t a = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;   // bits 0..63 from `bit`
+    const uint32_t b = (uint32_t)(w1 >> sh);                        // bits 64..
+    if (((a >> 1) & 3ull) != 2ull) continue;          // BTYPE = dynamic
+    if (((a >> 3) & 31ull) > 29ull) continue;         // HLIT <= 286 - 257
+    if (((a >> 8) & 31ull) > 29ull) continue;         // HDIST <= 30 - 1
+    const int hclen = (int)((a >> 13) & 15ull) + 4;
+    uint32_t kraft = 0;
+    bool len_ok = true;
+#pragma unroll
+    for (int i = 0; i < 19; i++) {
+      const int p = 17 + 3 * i;
+      const uint32_t l = p + 3 <= 64 ? (uint32_t)(a >> p) & 7u : p >= 64 ? (b >> (p - 64)) & 7u
+                                     : (uint32_t)((a >> p) | ((uint64_t)b << (64 - p))) & 7u;
+      if (i < hclen && l) kraft += 128u >> l;
+      (void)order;
+    }
+    if (!len_ok || kraft != 128u) continue;           // the code-length code must be complete
+    if (!fb_full_check(src, bit, limit_byte)) continue;
+    const uint32_t k = atomicAdd(count, 1u);
+    if (k < cap) out[k] = bit;
+  }
+}
+
+cudaError_t zb_launch_find_blocks(const uint8_t *src, uint64_t lo_bit, uint64_t hi_bit, uint64_t limit_byte, uint64_t *out,
+                                  uint32_t cap, uint32_t *count, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  if (hi_bit < lo_bit + 80) return cudaSuccess;
+  uint64_t blocks = (hi_bit - lo_bit + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  k_find_blocks<<<(uint32_t)blocks, 256, 0, s>>>(src, lo_bit, hi_bit, limit_byte, out, cap, count);
+  return cudaGetLastError();
+}
+
+// ---- markers -> bytes ----
+// Segment i was decoded into scr[soff[i] ...) as uint16 symbols: < 256 a byte, 0x8000 | k byte k of the
+// 32768 bytes that precede the segment in the member's output.  (1) k_mark_prefill puts those marker
+// symbols in front of every segment before the decode, so that a copy reaching before the segment's start
+// simply copies markers.  (2) k_resolve_tails walks the segments IN ORDER with the last 32 KiB of resolved
+// output in a shared-memory ring and finalises the last min(n, 32768) bytes of every segment -- exactly
+// the bytes the following segments' markers can refer to.  (3) k_resolve_rest then resolves everything
+// else in parallel, reading windows from the finished tails in dst.
+struct ZbMarkSeg {
+  uint64_t scr;   // element offset of the segment's first output symbol in the scratch
+  uint64_t dst;   // byte offset of the segment's first output byte in dst
+  uint32_t n;     // output bytes
+  uint32_t pad;
+};
+__global__ void __launch_bounds__(256) k_mark_prefill(uint16_t *scr, const ZbMarkSeg *segs) {
+  const ZbMarkSeg sg = segs[blockIdx.y];
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  if (k < 32768u) scr[sg.scr - 32768ull + k] = (uint16_t)(0x8000u | k);
+}
+
+#define RT_THREADS 1024
+#define RT_PER (32768 / RT_THREADS)
+__global__ void __launch_bounds__(RT_THREADS, 1) k_resolve_tails(const uint16_t *scr, const ZbMarkSeg *segs, uint32_t nseg,
+                                                                 uint8_t *dst, int *bad) {
+  extern __shared__ uint8_t ring[];   // ring[p & 32767] = resolved output byte at member position p (relative to segs[0].dst)
+  const uint32_t tid = threadIdx.x;
+  const uint64_t base = segs[0].dst;
+  for (uint32_t i = 0; i < nseg; i++) {
+    const ZbMarkSeg sg = segs[i];
+    const uint32_t T = min(sg.n, 32768u), j0 = sg.n - T;
+    const uint64_t p0 = sg.dst - base;          // member position of the segment's first byte
+    uint8_t val[RT_PER];
+    bool any_bad = false;
+#pragma unroll
+    for (int r = 0; r < RT_PER; r++) {
+      const uint32_t j = j0 + tid + (uint32_t)r * RT_THREADS;
+      val[r] = 0;
+      if (j < sg.n) {
+        const uint32_t sy = scr[sg.scr + j];
+        if (sy < 256u) val[r] = (uint8_t)sy;
+        else {
+          // marker k = byte at member position p0 - 32768 + k; it must exist (a reference before the
+          // start of the whole stream is the reference's "distance > op" error, inflate.nim:224)
+          const uint32_t k = sy & 0x7fffu;
+          if (p0 + k < 32768ull) any_bad = true;
+          val[r] = ring[(uint32_t)(p0 + k) & 32767u];
+        }
+      }
+    }
+    __syncthreads();   // every read of the old window is done before it is overwritten
+#pragma unroll
+    for (int r = 0; r < RT_PER; r++) {
+      const uint32_t j = j0 + tid + (uint32_t)r * RT_THREADS;
+      if (j < sg.n) {
+        ring[(uint32_t)(p0 + j) & 32767u] = val[r];
+        dst[sg.dst + j] = val[r];
+      }
+    }
+    if (any_bad) *bad = 1;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_resolve_rest(const uint16_t *scr, const ZbMarkSeg *segs, uint8_t *dst) {
+  const ZbMarkSeg sg = segs[blockIdx.y];
+  const uint32_t T = min(sg.n, 32768u), rest = sg.n - T;
+  for (uint32_t j = blockIdx.x * 2048u + threadIdx.x; j < min(rest, blockIdx.x * 2048u + 2048u); j += 256u) {
+    const uint32_t sy = scr[sg.scr + j];
+    dst[sg.dst + j] = sy < 256u ? (uint8_t)sy : dst[sg.dst - 32768ull + (sy & 0x7fffu)];
+  }
+}
+
+cudaError_t zb_launch_mark_prefill(uint16_t *scr, const void *segs, uint32_t nseg, cudaStream_t s) {
+  if (!nseg) return cudaSuccess;
+  k_mark_prefill<<<dim3(128, nseg), 256, 0, s>>>(scr, (const ZbMarkSeg *)segs);
+  return cudaGetLastError();
+}
+cudaError_t zb_launch_resolve(const uint16_t *scr, const void *segs, uint32_t nseg, uint32_t max_n, uint8_t *dst, int *bad,
+                              cudaStream_t s) {
+  if (!nseg) return cudaSuccess;
+  k_resolve_tails<<<1, RT_THREADS, 32768, s>>>(scr, (const ZbMarkSeg *)segs, nseg, dst, bad);
+  const uint32_t slabs = (max_n + 2047u) / 2048u;
+  if (slabs) k_resolve_rest<<<dim3(slabs, nseg), 256, 0, s>>>(scr, (const ZbMarkSeg *)segs, dst);
+  return cudaGetLastError();
+}
+
 cudaError_t zb_launch_find_sync(const uint8_t *src, uint64_t lo, uint64_t hi, uint64_t *out, uint32_t cap,
                                 uint32_t *count, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
@@ -982,8 +1250,10 @@ cudaError_t zb_launch_find_sync(const uint8_t *src, uint64_t lo, uint64_t hi, ui
 // function attributes are per device: zb200_init calls this once for the ctx's device
 cudaError_t zb_setup_inflate_attrs() {
   const int smem = (int)(INF_GROUPS * sizeof(GroupSmem)) + 256;
-  cudaError_t e = cudaFuncSetAttribute(k_inflate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(k_inflate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resolve_tails, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_piece_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL);
   return e;
 }
@@ -1001,8 +1271,9 @@ cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s) {
   if (blocks > need) blocks = need;
   cudaError_t e = cudaMemsetAsync(w.counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  if (w.count_only) k_inflate<true><<<blocks, INF_THREADS, smem, s>>>(w);
-  else k_inflate<false><<<blocks, INF_THREADS, smem, s>>>(w);
+  if (w.count_only) k_inflate<true, false><<<blocks, INF_THREADS, smem, s>>>(w);
+  else if (w.mark) k_inflate<false, true><<<blocks, INF_THREADS, smem, s>>>(w);
+  else k_inflate<false, false><<<blocks, INF_THREADS, smem, s>>>(w);
   return cudaGetLastError();
 }
 

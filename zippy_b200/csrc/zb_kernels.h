@@ -44,7 +44,7 @@ struct ZbCompressWork {
   const uint64_t *out_base_ptr;// ... or, when non-null, a device word holding it (the previous group's end),
                                // so consecutive groups can be enqueued without a host round trip
   const ZbCrcTables *tabs;     // device
-  uint2 *lz2_tables;           // k_lz2 dictionaries: [grid][8 own + 12 segment tables][2048 buckets x 4 ways] (LZ levels only)
+  uint2 *lz2_tables;           // k_lz2 dictionaries: [grid][8 own tables of 2048 x 4 ways + 12 segment tables of 8192 entries], u16 positions (LZ levels only)
   uint32_t n_chunks, n_members;
   int level, data_format;
 };
@@ -53,7 +53,7 @@ struct ZbCompressWork {
 cudaError_t zb_setup_deflate_attrs();
 cudaError_t zb_setup_inflate_attrs();
 struct ZbLz2Params {
-  uint32_t nslots;   // candidate slots looked at per position (1 + 4 own ways + 4 x 4 ways of the preceding segments)
+  uint32_t nslots;   // candidate slots looked at per position (1 in-window + 4 own ways + 1 per preceding segment, <= 9)
   uint32_t maxcand;  // candidates per position that may pass the 4-byte check and be extended
   uint32_t good;     // a match this long leaves room for one more candidate only
   uint32_t lazy;     // matches shorter than this yield to a longer match at the next position (0: greedy)
@@ -82,6 +82,12 @@ struct ZbInflateWork {
   int count_only;
   const uint32_t *order;       // device [n] or null: the work queue hands out members in this order (longest first)
   const uint8_t *skip;         // device [n] or null: members with skip[i] != 0 are left alone
+  const uint64_t *seg_bits;    // device [2n] or null (seg_mode only): bit-exact (start, end) of segment i inside src --
+                               //   speculative segments found by zb_launch_find_blocks; segment i > 0 may reference
+                               //   32768 bytes before its own start (its unknown window)
+  uint64_t seg_limit;          // with seg_bits: byte offset in src where the stream's payload ends
+  int mark;                    // with seg_bits: dst holds uint16 elements (dst_off in elements), 32768 marker
+                               //   symbols sit in front of every segment's output
   int seg_mode;                // members are independently decodable SEGMENTS of one raw deflate stream:
                                // a segment also ends, successfully, when its input is used up at a block
                                // boundary; kind[i] reports whether a final block was seen
@@ -92,6 +98,21 @@ cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s);
 // src[lo, hi): unordered, *count may exceed cap (then the list is incomplete)
 cudaError_t zb_launch_find_sync(const uint8_t *src, uint64_t lo, uint64_t hi, uint64_t *out, uint32_t cap,
                                 uint32_t *count, cudaStream_t s);
+
+// candidate starts (bit positions) of dynamic deflate blocks inside src bits [lo_bit, hi_bit): unordered,
+// *count may exceed cap; bytes at and beyond limit_byte read as zero
+cudaError_t zb_launch_find_blocks(const uint8_t *src, uint64_t lo_bit, uint64_t hi_bit, uint64_t limit_byte, uint64_t *out,
+                                  uint32_t cap, uint32_t *count, cudaStream_t s);
+// speculative segments decoded as uint16 symbols (ZbInflateWork::mark): marker prefill and resolution
+struct ZbMarkSegHost {
+  uint64_t scr;   // element offset of the segment's first output symbol in the scratch
+  uint64_t dst;   // byte offset of the segment's first output byte in dst
+  uint32_t n;     // output bytes
+  uint32_t pad;
+};
+cudaError_t zb_launch_mark_prefill(uint16_t *scr, const void *segs, uint32_t nseg, cudaStream_t s);
+cudaError_t zb_launch_resolve(const uint16_t *scr, const void *segs, uint32_t nseg, uint32_t max_n, uint8_t *dst, int *bad,
+                              cudaStream_t s);
 
 // ---- checksums over a batch of buffers (standalone crc32/adler32, and the trailer
 // verification after inflate) ----
