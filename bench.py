@@ -985,6 +985,64 @@ def run_c5(e, args, steps, warmup):
     return out
 
 
+def run_large_member(e, args):
+    """ONE large input.  (a) 1 GiB of text as a single gzip member of this library (64 KiB chunks
+    joined by sync markers): compress and uncompress, device-resident.  (b) a FOREIGN member -- 64 MiB of text
+    through system zlib level 6, no sync markers -- inflated as speculative segments, device-resident and through
+    the single drop-in call; beside the oracle's single-thread inflate of the same member."""
+    import zlib
+    from oracle import oracle as o
+    t, z, ctx = e.torch, e.z, e.ctx
+    T = text_corpus()
+    out = {}
+    n_bytes = 1 << 30
+    reps = n_bytes // len(T) + 1
+    d_src = t.frombuffer(bytearray(T), dtype=t.uint8).to(e.dev).repeat(reps)[:n_bytes].contiguous()
+    offs = np.array([0, n_bytes], dtype=np.uint64)
+    cap = n_bytes + n_bytes // 8 + (1 << 20)
+    d_dst = t.empty(cap, dtype=t.uint8, device=e.dev)
+    d_back = t.empty(n_bytes, dtype=t.uint8, device=e.dev)
+    oo = [None]
+
+    def comp():
+        oo[0] = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfGzip, d_dst.data_ptr(), cap)
+
+    comp()
+    c_ms = timed(e, comp, 2)
+    lens, st = ctx.uncompress_batch_device(d_dst.data_ptr(), oo[0], z.dfDetect, d_back.data_ptr(), offs)
+    assert not st.any() and int(lens[0]) == n_bytes and t.equal(d_back, d_src)
+    u_ms = timed(e, lambda: ctx.uncompress_batch_device(d_dst.data_ptr(), oo[0], z.dfDetect, d_back.data_ptr(), offs), 2)
+    out["own_1GiB_member"] = {"compress_gibs": n_bytes / GIB / (c_ms / 1e3), "uncompress_out_gibs": n_bytes / GIB / (u_ms / 1e3),
+                              "member_bytes": int(oo[0][1]), "kernel_launches_uncompress": int(ctx.timing()["kernel_launches"])}
+    del d_src, d_dst, d_back
+    raw = (T * (1 + (64 << 20) // len(T)))[:64 << 20]
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    blob = c.compress(raw) + c.flush()
+    d_blob = t.frombuffer(bytearray(blob), dtype=t.uint8).to(e.dev)
+    bo = np.array([0, len(blob)], dtype=np.uint64)
+    do = np.array([0, len(raw)], dtype=np.uint64)
+    d_out = t.empty(len(raw) + 64, dtype=t.uint8, device=e.dev)
+    lens, st = ctx.uncompress_batch_device(d_blob.data_ptr(), bo, z.dfDetect, d_out.data_ptr(), do)
+    assert not st.any() and int(lens[0]) == len(raw)
+    assert d_out[:len(raw)].cpu().numpy().tobytes() == raw, "speculative inflate differs from the input"
+    f_ms = timed(e, lambda: ctx.uncompress_batch_device(d_blob.data_ptr(), bo, z.dfDetect, d_out.data_ptr(), do), 3)
+    launches = int(ctx.timing()["kernel_launches"])
+    t0 = time.perf_counter()
+    got = z.uncompress(blob)
+    call_ms = (time.perf_counter() - t0) * 1e3
+    assert got == raw
+    t0 = time.perf_counter()
+    o.uncompress(blob)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    out["foreign_zlib6_64MiB_member"] = {"in_bytes": len(blob), "out_bytes": len(raw), "uncompress_ms": f_ms,
+                                         "uncompress_out_gibs": len(raw) / GIB / (f_ms / 1e3), "kernel_launches": launches,
+                                         "single_call_ms": call_ms, "single_call_out_gibs": len(raw) / GIB / (call_ms / 1e3),
+                                         "cpu_baseline": {"value": len(raw) / GIB / (cpu_ms / 1e3), "unit": "GiB/s out", "cores": 1,
+                                                          "kind": "port", "sample": "oracle inflate of the same member, one call"},
+                                         "parity": "byte-exact vs the input; CRC-32 + ISIZE verified on the device"}
+    return out
+
+
 # ======================================================================================
 def run_reference(args, rank, world):
     """--impl reference: the CPU arm (oracle port on all host threads).  Rank 0 only."""
@@ -1113,7 +1171,8 @@ def main():
                 if not args.no_e2e:
                     extras["pcie"] = pcie_peaks(e)
                 for name, fn in (("c1", lambda: run_c1(e, args)), ("c3", lambda: run_c3(e, args, xs, 3)),
-                                 ("c4", lambda: run_c4(e, args, xs, 3)), ("c5", lambda: run_c5(e, args, xs, 3))):
+                                 ("c4", lambda: run_c4(e, args, xs, 3)), ("c5", lambda: run_c5(e, args, xs, 3)),
+                                 ("large_member", lambda: run_large_member(e, args))):
                     e.torch.cuda.empty_cache()
                     try:
                         extras[name] = strip(fn())

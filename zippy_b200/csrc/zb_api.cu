@@ -472,6 +472,7 @@ struct BigResult {
   size_t member;
   uint64_t out_len;
   uint32_t kind, expect;
+  int status = ZB200_OK;
 };
 
 // ---- a large member WITHOUT sync markers (any foreign gzip / zlib / raw stream) ----
@@ -487,8 +488,9 @@ struct BigResult {
 //    decode, which also produces the reference's verdict for it.  The trailer check runs on the output
 //    either way.
 int inflate_member_speculative(zb200_ctx *ctx, const uint8_t *d_src, uint64_t m0, const HostWrapper &hw, uint8_t *d_dst,
-                               uint64_t dst0, uint64_t mcap, bool count_only, bool &ok, uint64_t &out_len) {
+                               uint64_t dst0, uint64_t mcap, bool count_only, bool &ok, uint64_t &out_len, bool &too_small) {
   ok = false;
+  too_small = false;
   cudaStream_t s = ctx->stream;
   const uint64_t lo_bit = (m0 + hw.pos) * 8ull, hi_bit = (m0 + hw.end) * 8ull, limit_byte = m0 + hw.end;
   const uint32_t cap = (uint32_t)std::min<uint64_t>((hw.end - hw.pos) / 64 + 1024, 1u << 24);
@@ -506,7 +508,8 @@ int inflate_member_speculative(zb200_ctx *ctx, const uint8_t *d_src, uint64_t m0
   CK(cudaStreamSynchronize(s));
   std::sort(cand.begin(), cand.end());
   // boundaries: the payload start, then candidates at least min_gap apart (a segment costs a 64 KiB marker prefill)
-  const uint64_t min_gap = 16384ull * 8ull;
+  // (at most 60000 segments: the resolve kernels index them with a grid dimension)
+  const uint64_t min_gap = std::max<uint64_t>(16384ull * 8ull, (hi_bit - lo_bit) / 60000ull);
   std::vector<uint64_t> bits(1, lo_bit);
   for (uint64_t c : cand)
     if (c >= bits.back() + min_gap && c + min_gap / 4 < hi_bit) bits.push_back(c);
@@ -568,7 +571,10 @@ int inflate_member_speculative(zb200_ctx *ctx, const uint8_t *d_src, uint64_t m0
     out_len = total;
     return ZB200_OK;
   }
-  if (total > mcap) return ZB200_OK;   // the serial decode reports it
+  if (total > mcap) {   // the whole stream decodes, so the serial decode could only run out of room: say so now
+    too_small = true;
+    return ZB200_OK;
+  }
   // 3. uint16 symbols, markers in front of every segment
   ENSURE(ctx->mark_scratch, (size_t)scr_elems * 2 + 64);
   ENSURE(ctx->mark_segs, S * sizeof(ZbMarkSegHost) + 16);
@@ -644,16 +650,17 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
     const uint64_t dst0_m = count_only ? 0 : dst_offsets[m], mcap_m = count_only ? ~0ull : dst_offsets[m + 1] - dst_offsets[m];
     // streams without sync markers (or whose pieces are not independent): speculative segments
     auto speculative = [&]() -> int {
-      bool sok = false;
+      bool sok = false, small = false;
       uint64_t slen = 0;
-      int src_ = inflate_member_speculative(ctx, d_src, m0, hw, d_dst, dst0_m, mcap_m, count_only, sok, slen);
+      int src_ = inflate_member_speculative(ctx, d_src, m0, hw, d_dst, dst0_m, mcap_m, count_only, sok, slen, small);
       if (src_) return src_;
-      if (sok) {
+      if (sok || small) {
         BigResult r;
         r.member = m;
-        r.out_len = slen;
+        r.out_len = sok ? slen : 0;
         r.kind = (uint32_t)hw.fmt;
         r.expect = hw.expect;
+        r.status = small ? ZB200_ERR_DST_TOO_SMALL : ZB200_OK;
         done.push_back(r);
       }
       return ZB200_OK;
@@ -860,8 +867,7 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
       ENSURE(ctx->skip_mask, n);
       for (const BigResult &r : big) {
         skip_host[r.member] = 1;
-        const int ok = ZB200_OK;
-        CK(cudaMemcpyAsync((int *)ctx->status.p + r.member, &ok, 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync((int *)ctx->status.p + r.member, &r.status, 4, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync((uint64_t *)ctx->out_len.p + r.member, &r.out_len, 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync((uint32_t *)ctx->kind.p + r.member, &r.kind, 4, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync((uint32_t *)ctx->expect.p + r.member, &r.expect, 4, cudaMemcpyHostToDevice, s));

@@ -1213,12 +1213,23 @@ __global__ void __launch_bounds__(RT_THREADS, 1) k_resolve_tails(const uint16_t 
   }
 }
 
-__global__ void __launch_bounds__(256) k_resolve_rest(const uint16_t *scr, const ZbMarkSeg *segs, uint8_t *dst) {
+__global__ void __launch_bounds__(256) k_resolve_rest(const uint16_t *scr, const ZbMarkSeg *segs, uint8_t *dst, int *bad) {
   const ZbMarkSeg sg = segs[blockIdx.y];
+  const uint64_t p0 = sg.dst - segs[0].dst;   // member position of the segment's first byte
   const uint32_t T = min(sg.n, 32768u), rest = sg.n - T;
   for (uint32_t j = blockIdx.x * 2048u + threadIdx.x; j < min(rest, blockIdx.x * 2048u + 2048u); j += 256u) {
     const uint32_t sy = scr[sg.scr + j];
-    dst[sg.dst + j] = sy < 256u ? (uint8_t)sy : dst[sg.dst - 32768ull + (sy & 0x7fffu)];
+    uint8_t v = (uint8_t)sy;
+    if (sy >= 256u) {
+      const uint32_t k = sy & 0x7fffu;
+      if (p0 + k < 32768ull) {   // before the start of the stream: the member goes to the serial decode
+        *bad = 1;
+        v = 0;
+      } else {
+        v = dst[sg.dst - 32768ull + k];
+      }
+    }
+    dst[sg.dst + j] = v;
   }
 }
 
@@ -1232,7 +1243,7 @@ cudaError_t zb_launch_resolve(const uint16_t *scr, const void *segs, uint32_t ns
   if (!nseg) return cudaSuccess;
   k_resolve_tails<<<1, RT_THREADS, 32768, s>>>(scr, (const ZbMarkSeg *)segs, nseg, dst, bad);
   const uint32_t slabs = (max_n + 2047u) / 2048u;
-  if (slabs) k_resolve_rest<<<dim3(slabs, nseg), 256, 0, s>>>(scr, (const ZbMarkSeg *)segs, dst);
+  if (slabs) k_resolve_rest<<<dim3(slabs, nseg), 256, 0, s>>>(scr, (const ZbMarkSeg *)segs, dst, bad);
   return cudaGetLastError();
 }
 
