@@ -367,7 +367,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   return ZB200_OK;
 }
 
-// 64 KiB pieces covering the capacity [offs[i], offs[i+1]) of every buffer (at least one per buffer)
+// ZB_CK_PIECE_BYTES pieces covering the capacity [offs[i], offs[i+1]) of every buffer (at least one per buffer)
 int upload_pieces(zb200_ctx *ctx, const uint64_t *offs, size_t n, ZbChecksumWork &w) {
   std::vector<ZbPiece> pieces;
   std::vector<uint32_t> first(n + 1);
@@ -381,7 +381,7 @@ int upload_pieces(zb200_ctx *ctx, const uint64_t *offs, size_t n, ZbChecksumWork
       p.buf = (uint32_t)i;
       p.pad = 0;
       pieces.push_back(p);
-      rel += ZB_CHUNK_BYTES;
+      rel += ZB_CK_PIECE_BYTES;
     } while (rel < cap);
   }
   first[n] = (uint32_t)pieces.size();
@@ -822,6 +822,7 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
   if (!count_only)
     CK(cudaMemcpyAsync(ctx->dst_off.p, dst_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
   ZbInflateWork w;
+  memset(&w, 0, sizeof(w));
   w.src = d_src;
   w.src_off = (const uint64_t *)ctx->src_off.p;
   w.dst = d_dst;
@@ -948,7 +949,7 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
         pc.buf = (uint32_t)(i - m0);
         pc.pad = 0;
         pieces.push_back(pc);
-        rel += ZB_CHUNK_BYTES;
+        rel += ZB_CK_PIECE_BYTES;
       } while (rel < cap);
     }
     first.push_back((uint32_t)(pieces.size() - piece0[gi]));

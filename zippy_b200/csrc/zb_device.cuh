@@ -92,8 +92,10 @@ __device__ __forceinline__ uint64_t zb_warp_sum64(uint64_t v) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t zb_mul1024(const uint32_t *tab /*[4][256] in smem*/, uint32_t r) {
-  return tab[r & 255u] ^ tab[256 + ((r >> 8) & 255u)] ^ tab[512 + ((r >> 16) & 255u)] ^ tab[768 + (r >> 24)];
+// `ts` = distance (in words) between consecutive table entries: 1 for the plain [4][256] table, 32 for the
+// per-lane copies the checksum kernel keeps (pass tab + lane there)
+__device__ __forceinline__ uint32_t zb_mul1024(const uint32_t *tab /*[4][256] in smem*/, uint32_t r, uint32_t ts = 1u) {
+  return tab[(r & 255u) * ts] ^ tab[(256 + ((r >> 8) & 255u)) * ts] ^ tab[(512 + ((r >> 16) & 255u)) * ts] ^ tab[(768 + (r >> 24)) * ts];
 }
 
 // Raw (init-0) CRC-32 and Adler sums of bytes [off, off+n) of a shared-memory buffer,
@@ -106,9 +108,10 @@ struct ZbCheck {
   uint64_t a_sum, b_sum;
 };
 __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32_t off, uint32_t n,
-                                                     const uint32_t *tab, const uint32_t *lane_mul) {
+                                                     const uint32_t *tab, const uint32_t *lane_mul, uint32_t ts = 1u) {
   const int lane = zb_lane();
-  if (n == (uint32_t)ZB_SUB_BYTES) {
+  if (ts != 1u) tab += lane;
+  if (n == (uint32_t)ZB_SUB_BYTES && ts == 1u) {
     // Full 8 KiB piece (the common case): four independent Horner chains of 16 rows each, so the
     // table-lookup latency of one chain hides behind the other three; they are joined with the
     // quarter shifts lane_mul[41 + k] = x^(8 * 2048 * k).
@@ -156,7 +159,7 @@ __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32
   uint32_t rel = 4u * (uint32_t)lane;      // offset relative to the piece start
   for (uint32_t k = 0; k < rows; k++) {
     uint32_t w = zb_ld32_unaligned(base, o);
-    if (k) r = zb_mul1024(tab, r);
+    if (k) r = zb_mul1024(tab, r, ts);
     r ^= w;
     uint32_t s = __dp4a(w, 0x01010101u, 0u);
     uint32_t ws = __dp4a(w, 0x03020100u, 0u);

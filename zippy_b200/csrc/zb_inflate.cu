@@ -814,57 +814,140 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
 // to one CTA (TMA-staged, 8 warps x 8 KiB, lane-strided CRC stepping + dp4a Adler sums, see
 // zb_device.cuh), k_buffer_combine folds a buffer's pieces with x^(8*len) multiplications /
 // the closed-form Adler merge, and in verify mode compares with the trailer.
-#define CK_PIECE ZB_CHUNK_BYTES
-#define CK_THREADS (ZB_WARPS_PER_CHUNK * 32)
-#define CK_STAGES 3
+#define CK_PIECE ZB_CK_PIECE_BYTES
+#define CK_THREADS 256
+#define CK_WARPS (CK_THREADS / 32)
+#define CK_WARP_BYTES (CK_PIECE / CK_WARPS)          // 4 KiB per warp and piece
+#define CK_STAGES 2
 #define CK_STAGE_BYTES (CK_PIECE + 128)
-#define CK_SM_CRC (CK_STAGES * CK_STAGE_BYTES)
-#define CK_SM_LMUL (CK_SM_CRC + 4096)
+#define CK_SM_REP (CK_STAGES * CK_STAGE_BYTES)        // x^1024 step tables, one copy per lane (bank): 4 x 256 x 32 words
+#define CK_SM_QT (CK_SM_REP + 4 * 256 * 32 * 4)       // multiply-by-x^(8*1024*k) tables, k = 1..3
+#define CK_SM_LMUL (CK_SM_QT + 3 * 4 * 256 * 4)
 #define CK_SM_PART (CK_SM_LMUL + 48 * 4)
-#define CK_SM_BAR (CK_SM_PART + ZB_WARPS_PER_CHUNK * 24)
+#define CK_SM_BAR (CK_SM_PART + CK_WARPS * 24)
 #define CK_SM_TOTAL (CK_SM_BAR + 8 * CK_STAGES + 8)
+static_assert(CK_SM_TOTAL <= 232448, "one CTA per SM");
 
 __device__ __forceinline__ uint32_t piece_len(uint64_t buflen, uint64_t rel) {
   return rel < buflen ? (uint32_t)min((uint64_t)CK_PIECE, buflen - rel) : 0u;
 }
-__device__ __forceinline__ uint32_t ck_piece_info(const ZbChecksumWork &w, uint32_t pid, const uint8_t *&src) {
+__device__ __forceinline__ uint32_t ck_piece_info(const ZbChecksumWork &w, uint32_t pid, const uint8_t *&src, uint32_t &kind) {
   const ZbPiece pc = w.pieces[pid];
   uint64_t buflen = w.lens ? w.lens[pc.buf] : w.off[pc.buf + 1] - w.off[pc.buf];
   if (w.status && w.status[pc.buf] != ZB_OK) buflen = 0;
+  kind = (uint32_t)w.kind;
+  if (w.kinds) {
+    const uint32_t kd = w.kinds[pc.buf];
+    kind = kd == ZB_DF_ZLIB ? 1u : 0u;
+    if (kd != ZB_DF_GZIP && kd != ZB_DF_ZLIB) buflen = 0;   // raw deflate: nothing to verify
+  }
   src = w.src + w.off[pc.buf] + pc.rel;
   return piece_len(buflen, pc.rel);
 }
 
-// Persistent CTAs (one per SM), a 3-stage ring of 64 KiB shared-memory buffers filled by TMA
-// bulk copies: while the 8 warps checksum stage k, the copies for k+1 and k+2 are in flight.
-// Piece descriptors (source pointer, length: two dependent global loads) are fetched 16..32
-// pieces ahead into a small shared ring so they never sit on the critical path.
-// This is the one kernel on the path that is genuinely memory-bound (0.12 instructions per byte).
+// x^1024 step with the lane's own copy of the tables: entry (j, b) of lane l at rep[((j * 256 + b) * 32) + l],
+// i.e. always in bank l -- four conflict-free lookups (the shared 4 KiB table cost ~3.5 wavefronts per lookup)
+__device__ __forceinline__ uint32_t ck_mul1024(const uint32_t *rep_lane, uint32_t r) {
+  return rep_lane[(r & 255u) * 32u] ^ rep_lane[(256u + ((r >> 8) & 255u)) * 32u] ^ rep_lane[(512u + ((r >> 16) & 255u)) * 32u] ^
+         rep_lane[(768u + (r >> 24)) * 32u];
+}
+__device__ __forceinline__ uint32_t ck_mul_tab(const uint32_t *t /*[4][256]*/, uint32_t r) {
+  return t[r & 255u] ^ t[256 + ((r >> 8) & 255u)] ^ t[512 + ((r >> 16) & 255u)] ^ t[768 + (r >> 24)];
+}
+
+// Raw CRC-32 (KIND 0) or the Adler sums (KIND 1) of one warp's 4 KiB of a staged piece: lane i takes word i
+// of every 128-byte row; four independent chains (1 KiB each) hide the lookup latency and are joined with
+// table multiplications; one generic GF(2) multiplication per warp shifts the lanes into place.
+template <int KIND>
+__device__ __forceinline__ ZbCheck ck_warp_full(const uint8_t *base, uint32_t off, const uint32_t *rep_lane, const uint32_t *qt,
+                                                const uint32_t *lane_mul) {
+  const int lane = zb_lane();
+  constexpr uint32_t QR = CK_WARP_BYTES / 512;   // rows per chain (8)
+  constexpr uint32_t QB = CK_WARP_BYTES / 4;     // bytes per chain (1024)
+  const uint32_t o = off + 4u * (uint32_t)lane, rel0 = 4u * (uint32_t)lane;
+  ZbCheck out;
+  out.crc_raw = 0;
+  out.a_sum = out.b_sum = 0;
+  if (KIND == 0) {
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+#pragma unroll 2
+    for (uint32_t k = 0; k < QR; k++) {
+      const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (QR + k));
+      const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (2u * QR + k)), w3 = zb_ld32_unaligned(base, o + 128u * (3u * QR + k));
+      if (k) {
+        r0 = ck_mul1024(rep_lane, r0);
+        r1 = ck_mul1024(rep_lane, r1);
+        r2 = ck_mul1024(rep_lane, r2);
+        r3 = ck_mul1024(rep_lane, r3);
+      }
+      r0 ^= w0;
+      r1 ^= w1;
+      r2 ^= w2;
+      r3 ^= w3;
+    }
+    uint32_t r = ck_mul_tab(qt + 2 * 1024, r0) ^ ck_mul_tab(qt + 1024, r1) ^ ck_mul_tab(qt, r2) ^ r3;
+    r = zb_gf2_mul(r, lane_mul[32 - lane]);
+    out.crc_raw = zb_warp_xor(r);
+  } else {
+    uint32_t a = 0;
+    uint64_t b = 0;
+#pragma unroll 2
+    for (uint32_t k = 0; k < QR; k++) {
+      const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (QR + k));
+      const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (2u * QR + k)), w3 = zb_ld32_unaligned(base, o + 128u * (3u * QR + k));
+      const uint32_t s0 = __dp4a(w0, 0x01010101u, 0u), s1 = __dp4a(w1, 0x01010101u, 0u);
+      const uint32_t s2 = __dp4a(w2, 0x01010101u, 0u), s3 = __dp4a(w3, 0x01010101u, 0u);
+      a += s0 + s1 + s2 + s3;
+      const uint32_t rel = rel0 + 128u * k;
+      // (4 KiB - position) * byte sums fit in 32 bits per row: 4096 * 4 * 1020 < 2^32
+      b += (uint64_t)((4u * QB - rel) * s0 + (3u * QB - rel) * s1) + (uint64_t)((2u * QB - rel) * s2 + (QB - rel) * s3);
+      b -= (uint64_t)(__dp4a(w0, 0x03020100u, 0u) + __dp4a(w1, 0x03020100u, 0u) + __dp4a(w2, 0x03020100u, 0u) +
+                      __dp4a(w3, 0x03020100u, 0u));
+    }
+    out.a_sum = zb_warp_sum64((uint64_t)a);
+    out.b_sum = zb_warp_sum64(b);
+  }
+  return out;
+}
+
+// Persistent CTAs (one per SM), a ring of 32 KiB shared-memory stages filled by TMA bulk copies: while the
+// 8 warps checksum stage k, the copy for k+1 is in flight.  Piece descriptors (source pointer, length, kind:
+// dependent global loads) are fetched 16..32 pieces ahead into a small shared ring so they never sit on the
+// critical path.  CRC-32 and Adler-32 are separate paths (a piece needs one of them): Adler is two dp4a per
+// word and runs at the copy rate; CRC-32 without a carry-less multiply is one table lookup per byte, which
+// is why the step tables are replicated per bank.
 #define CK_INFO 32
 __global__ void __launch_bounds__(CK_THREADS, 1)
     k_piece_checksum(ZbChecksumWork w) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint32_t *crc_tab = reinterpret_cast<uint32_t *>(smem + CK_SM_CRC);
+  uint32_t *rep = reinterpret_cast<uint32_t *>(smem + CK_SM_REP);
+  uint32_t *qt = reinterpret_cast<uint32_t *>(smem + CK_SM_QT);
   uint32_t *lane_mul = reinterpret_cast<uint32_t *>(smem + CK_SM_LMUL);
   uint64_t *part = reinterpret_cast<uint64_t *>(smem + CK_SM_PART);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CK_SM_BAR);
   __shared__ const uint8_t *info_src[CK_INFO];
   __shared__ uint32_t info_len[CK_INFO];
+  __shared__ uint32_t info_kind[CK_INFO];
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t stride = gridDim.x;
   if (tid == 0) {
     for (int i = 0; i < CK_STAGES; i++) zb_mbar_init(&bars[i], 1);
     zb_fence_mbar_init();
   }
-  for (int i = tid; i < 1024; i += CK_THREADS) crc_tab[i] = (&w.tabs->mul1024[0][0])[i];
+  {
+    const uint32_t *t = &w.tabs->mul1024[0][0];
+    for (int i = tid; i < 1024 * 32; i += CK_THREADS) rep[i] = t[i >> 5];   // entry e, lane l at rep[e * 32 + l]
+    const uint32_t *q = &w.tabs->ck_quart[0][0][0];
+    for (int i = tid; i < 3 * 1024; i += CK_THREADS) qt[i] = q[i];
+  }
   if (tid < 33) lane_mul[tid] = w.tabs->lane_mul[tid];
-  if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = w.tabs->sub_mul[tid - 64];
-  if (tid >= 96 && tid < 100) lane_mul[41 + tid - 96] = w.tabs->quart_mul[tid - 96];
   if (tid >= 128 && tid < 128 + CK_INFO) {  // descriptors of this CTA's first 32 pieces
     const uint32_t j = (uint32_t)tid - 128u, pid = blockIdx.x + j * stride;
     const uint8_t *src = nullptr;
-    info_len[j] = pid < w.n_pieces ? ck_piece_info(w, pid, src) : 0u;
+    uint32_t kd = 0;
+    info_len[j] = pid < w.n_pieces ? ck_piece_info(w, pid, src, kd) : 0u;
     info_src[j] = src;
+    info_kind[j] = kd;
   }
   __syncthreads();
   if (tid == 0) {  // prologue: fill the ring
@@ -873,10 +956,11 @@ __global__ void __launch_bounds__(CK_THREADS, 1)
       if (info_len[k]) zb_stage_chunk(smem + k * CK_STAGE_BYTES, info_src[k], info_len[k], &bars[k]);
     }
   }
+  const uint32_t *rep_lane = rep + lane;
   uint32_t k = 0, phases = 0;  // bit s of `phases` = parity of the next completion of stage s
   for (uint32_t pid = blockIdx.x; pid < w.n_pieces; pid += stride, k++) {
     const uint32_t stage = k % CK_STAGES;
-    const uint32_t len = info_len[k % CK_INFO];
+    const uint32_t len = info_len[k % CK_INFO], kind = info_kind[k % CK_INFO];
     const uint8_t *src = info_src[k % CK_INFO];
     const uint8_t *data = smem + stage * CK_STAGE_BYTES;
     const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
@@ -884,17 +968,18 @@ __global__ void __launch_bounds__(CK_THREADS, 1)
       zb_mbar_wait(&bars[stage], (phases >> stage) & 1u);
       phases ^= 1u << stage;
     }
-    const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES, b1 = min(b0 + ZB_SUB_BYTES, len);
+    const uint32_t b0 = (uint32_t)warp * CK_WARP_BYTES, b1 = min(b0 + CK_WARP_BYTES, len);
     ZbCheck c;
     c.crc_raw = 0;
     c.a_sum = c.b_sum = 0;
     if (b0 < len) {
-      c = zb_warp_checksums(data, mis + b0, b1 - b0, crc_tab, lane_mul);
+      const uint32_t n = b1 - b0;
+      if (n == CK_WARP_BYTES) c = kind ? ck_warp_full<1>(data, mis + b0, rep_lane, qt, lane_mul) : ck_warp_full<0>(data, mis + b0, rep_lane, qt, lane_mul);
+      else c = zb_warp_checksums(data, mis + b0, n, rep, lane_mul, 32u);   // a buffer's ragged last piece
       const uint32_t after = len - b1;
       if (after) {
-        const uint32_t shift = ((after & (ZB_SUB_BYTES - 1)) == 0) ? lane_mul[33 + after / ZB_SUB_BYTES] : zb_xpow8(after);
-        c.crc_raw = zb_gf2_mul(c.crc_raw, shift);
-        c.b_sum += (uint64_t)after * c.a_sum;
+        if (kind == 0) c.crc_raw = zb_gf2_mul(c.crc_raw, zb_xpow8(after));
+        else c.b_sum += (uint64_t)after * c.a_sum;
       }
     }
     if (lane == 0) {
@@ -904,13 +989,13 @@ __global__ void __launch_bounds__(CK_THREADS, 1)
     }
     __syncthreads();  // every warp is done with this stage (and with info slot k)
     if (tid == 0) {
-      // refill this stage with the piece three iterations ahead
+      // refill this stage with the piece CK_STAGES iterations ahead
       const uint32_t nk = k + CK_STAGES;
       if (pid + CK_STAGES * stride < w.n_pieces && info_len[nk % CK_INFO])
         zb_stage_chunk(smem + stage * CK_STAGE_BYTES, info_src[nk % CK_INFO], info_len[nk % CK_INFO], &bars[stage]);
       uint32_t raw = 0;
       uint64_t a = 0, b = 0;
-      for (int j = 0; j < ZB_WARPS_PER_CHUNK; j++) {
+      for (int j = 0; j < CK_WARPS; j++) {
         raw ^= (uint32_t)part[j * 3 + 0];
         a += part[j * 3 + 1];
         b += part[j * 3 + 2];
@@ -923,8 +1008,10 @@ __global__ void __launch_bounds__(CK_THREADS, 1)
       // descriptors for pieces k+17 .. k+32 go into the half of the ring that has just been used up
       const uint32_t j = k + 17u + (uint32_t)lane, npid = blockIdx.x + j * stride;
       const uint8_t *nsrc = nullptr;
-      info_len[j % CK_INFO] = npid < w.n_pieces ? ck_piece_info(w, npid, nsrc) : 0u;
+      uint32_t kd = 0;
+      info_len[j % CK_INFO] = npid < w.n_pieces ? ck_piece_info(w, npid, nsrc, kd) : 0u;
       info_src[j % CK_INFO] = nsrc;
+      info_kind[j % CK_INFO] = kd;
     }
     __syncthreads();  // part[] and the descriptor ring are consistent for the next piece
   }
@@ -981,7 +1068,7 @@ __global__ void __launch_bounds__(128)
     b = zb_warp_sum64(b);
   }
   if (lane != 0) return;
-  const uint32_t v = kind == 0 ? ~(zb_gf2_mul(buflen == CK_PIECE ? w.tabs->sub_mul[0] : zb_xpow8(buflen), 0xffffffffu) ^ r)
+  const uint32_t v = kind == 0 ? ~(zb_gf2_mul(buflen == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8(buflen), 0xffffffffu) ^ r)
                                : zb_adler_from_sums(a % ZB_ADLER_MOD, b % ZB_ADLER_MOD, buflen);
   if (w.out) w.out[i] = v;
   if (w.expect) {

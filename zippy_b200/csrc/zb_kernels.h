@@ -116,6 +116,7 @@ cudaError_t zb_launch_resolve(const uint16_t *scr, const void *segs, uint32_t ns
 
 // ---- checksums over a batch of buffers (standalone crc32/adler32, and the trailer
 // verification after inflate) ----
+#define ZB_CK_PIECE_BYTES 32768   // the checksum kernels cut every buffer into pieces of this size
 struct ZbPiece {
   uint64_t rel;   // start of the piece relative to its buffer
   uint32_t buf;   // buffer index
@@ -125,7 +126,7 @@ struct ZbChecksumWork {
   const uint8_t *src;          // device: base of the buffers
   const uint64_t *off;         // device [n+1]: buffer i starts at src + off[i]
   const uint64_t *lens;        // device [n] actual lengths, or null (= off[i+1]-off[i])
-  const ZbPiece *pieces;       // device [n_pieces]: 64 KiB pieces covering every buffer's capacity
+  const ZbPiece *pieces;       // device [n_pieces]: ZB_CK_PIECE_BYTES pieces covering every buffer's capacity
   const uint32_t *first;       // device [n+1]: first piece of each buffer
   ZbChunkCheck *piece_out;     // device [n_pieces] scratch
   uint32_t *out;               // device [n] checksums, or null
