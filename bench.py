@@ -358,7 +358,7 @@ def make_env(args):
     e.torch, e.dist, e.z, e.sharding = torch, dist, z, sharding
     e.ctx = z.Context(e.local_rank)
     e.stream = torch.cuda.current_stream()
-    e.ctx.set_stream(e.stream.cuda_stream)
+    e.ctx.set_stream(e.stream.cuda_stream or e.ctx.LEGACY_DEFAULT_STREAM)   # same stream as torch's work: ordered
     e.ev0 = torch.cuda.Event(enable_timing=True)
     e.ev1 = torch.cuda.Event(enable_timing=True)
     try:
@@ -459,6 +459,7 @@ def gen_c2(e, n, first):
     for s in range(0, n, 4096):
         k = min(n, s + 4096)
         d_src[s * BLOCK:k * BLOCK] = t.index_select(windows, 0, offs[s:k]).reshape(-1)
+    t.cuda.synchronize()   # the ctx runs on its own stream: inputs are complete before the first call
     return d_src, T
 
 
@@ -495,6 +496,7 @@ def gen_c5(e, nb, first):
         blob = t.repeat_interleave(vals, runs)[:need]
         assert blob.numel() == need
         view[idx] = blob.view(len(idx), BLOCK)
+    t.cuda.synchronize()
     return d_src, cls
 
 
@@ -786,7 +788,7 @@ def run_c2(e, args, steps, warmup, full=True):
     os.environ["ZB200_DEV_GROUP_CHUNKS"] = str(max(n, 1))   # one launch group per step: per-launch = per-step figures
     e.ctx.close()
     e.ctx = e.z.Context(e.local_rank)
-    e.ctx.set_stream(e.stream.cuda_stream)
+    e.ctx.set_stream(e.stream.cuda_stream or e.ctx.LEGACY_DEFAULT_STREAM)   # same stream as torch's work: ordered
     d_src, T = gen_c2(e, n, e.rank * n)
     src_offs = np.arange(n + 1, dtype=np.uint64) * BLOCK
     r = measure_compress(e, d_src, src_offs, args.level, steps, warmup, e.world * n, e.rank * n, do_e2e=not args.no_e2e,

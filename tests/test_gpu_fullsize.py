@@ -34,7 +34,7 @@ def env():
         pytest.skip("needs 40 GiB of free device memory")
     ctx = z.Context(0)
     stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
+    ctx.set_stream(stream.cuda_stream or ctx.LEGACY_DEFAULT_STREAM)   # same stream as torch's work: ordered
     yield torch, z, o, ctx
     ctx.close()
 
@@ -50,6 +50,7 @@ def _c2_batch(torch, n):
     for s in range(0, n, 4096):
         e = min(n, s + 4096)
         d_src[s * BLOCK:e * BLOCK] = torch.index_select(windows, 0, offs_d[s:e]).reshape(-1)
+    torch.cuda.synchronize()   # the ctx runs on its own stream: the input must be complete before it is read
     return T, offs, d_src
 
 
@@ -64,6 +65,7 @@ def test_c2_full_size_properties(env):
     assert (np.diff(oo.astype(np.int64)) > 18).all()
     # determinism at full size: a second run into a dirty buffer yields the same bytes and offsets
     d_dst2 = torch.full((cap,), 0x5A, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     oo2 = ctx.compress_batch_device(d_src.data_ptr(), src_offsets, 1, z.dfGzip, d_dst2.data_ptr(), cap)
     assert (oo2 == oo).all() and torch.equal(d_dst[:int(oo[n])], d_dst2[:int(oo[n])]), "level-1 output differs run to run"
     del d_dst2

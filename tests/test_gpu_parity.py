@@ -283,6 +283,7 @@ def test_device_resident_batch(z, o, corpus):
     cap = n * 70000
     d_dst = torch.zeros(cap, dtype=torch.uint8, device="cuda")
     ctx = z.Context()
+    ctx.set_stream(ctx.LEGACY_DEFAULT_STREAM)   # ordered with torch's default-stream work on the same buffers
     oo = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfGzip, d_dst.data_ptr(), cap)
     comp = d_dst.cpu().numpy()
     for i in range(n):
@@ -321,6 +322,7 @@ def test_launch_groups_and_tight_capacity(z, o, corpus, monkeypatch):
     total = int(oo[-1])
     cap = (total + 64 + 3) & ~3
     d_dst = torch.full((cap,), 0xAB, dtype=torch.uint8, device="cuda")   # dirty buffer: the call writes every output byte itself
+    torch.cuda.synchronize()   # ctx runs on its own stream
     o2 = ctx.compress_batch_device(d_src.data_ptr(), offs, 1, z.dfZlib, d_dst.data_ptr(), cap)
     host = d_dst.cpu().numpy()
     for i, x in enumerate(items):
@@ -661,6 +663,7 @@ def test_device_pointers_of_any_alignment(z, o, corpus):
     variants a source pointer that is off by 1..15 bytes and members of odd sizes."""
     torch = pytest.importorskip("torch")
     ctx = z.Context()
+    ctx.set_stream(ctx.LEGACY_DEFAULT_STREAM)   # ordered with torch's default-stream work on the same buffers
     items = [corpus["alice29.txt"][:70001], corpus["html"][:12345], b"", corpus["urls.10K"][:65537], b"q" * 31]
     blob = b"".join(items)
     offs = np.zeros(len(items) + 1, dtype=np.uint64)

@@ -32,7 +32,7 @@ def main():
     dev = torch.device("cuda", 0)
     ctx = z.Context(0)
     stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
+    ctx.set_stream(stream.cuda_stream or ctx.LEGACY_DEFAULT_STREAM)   # same stream as torch's work: ordered
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     if "c3" in args.what:

@@ -72,8 +72,13 @@ class Context:
             raise ZippyError(rc, "zb200_init failed: %s (zippy_b200 needs a CUDA device; there is no CPU fallback)"
                              % L.zb200_strerror(rc).decode())
 
+    LEGACY_DEFAULT_STREAM = 1   # cudaStreamLegacy: the handle that names the default stream explicitly
+
     def set_stream(self, cuda_stream):
-        """Run on a caller-owned cudaStream_t (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        """Run on a caller-owned cudaStream_t (int handle).  0 / None restores the ctx's own (non-blocking)
+        stream, which is NOT ordered against work the caller queued elsewhere: a caller that fills device
+        buffers on its default stream and wants ordering without synchronising passes LEGACY_DEFAULT_STREAM
+        (torch: `ctx.set_stream(torch.cuda.current_stream().cuda_stream or ctx.LEGACY_DEFAULT_STREAM)`)."""
         _check(self._h, _native.lib().zb200_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
 
     def close(self):

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 //    entry of its hash in each of the four preceding segments' static tables -- nine candidates from
 //    five independent loads instead of a dependent chain walk (the reference follows up to `chain`
 //    links, lz77.nim:88-109).  Candidates are verified / extended against shared memory nearest first
-//    under the level's budget: `nslots` candidates looked at, at most `maxcand` of them verified, one
+//    under the level's budget: a level-dependent number of them looked at, at most `maxcand` verified, one
 //    more once a match of `good` bytes is in hand (lz77.nim:104 quarters its budget there); the
 //    longest wins;
 //  * one-step lazy evaluation: a match shorter than `lazy` is dropped when the next position has a
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           hcand[j] = 0xffffu;
-          if (search && myseg > (uint32_t)j && prm.nslots > 5u + (uint32_t)j)
+          if (search && myseg > (uint32_t)j && prm.hist_segs > (uint32_t)j)
             hcand[j] = __ldcg(reinterpret_cast<const uint16_t *>(stat + (size_t)(myseg - 1u - (uint32_t)j) * LZ2_BUCKETS) + hs);
         }
         uint32_t grp;
@@ -624,21 +624,21 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           P.lim = min(q, (uint32_t)ZB_MAX_DIST);
           P.limit = limit;
           P.stop = min(limit, (uint32_t)LZ_LANE_CAP);
-          // candidate slots, nearest first; the level decides how many are looked at (nslots):
-          //   0      the closest same-hash position inside this window
-          //   1..4   the own bucket, most recent first
-          //   5..8   the entries of the four preceding segments, nearest segment first
+          // candidates, nearest first; the level decides how many are looked at:
+          //   the closest same-hash position inside this window
+          //   own_ways entries of the own bucket, most recent first
+          //   the entries of hist_segs preceding segments, nearest segment first
           if (search) {
             const uint32_t lower = grp & ((1u << lane) - 1u);
             if (lower) lz2_try(P, data, q - ((uint32_t)lane - (uint32_t)(31 - __clz((int)lower))), prm.good, m, dist, budget);
             lz2_try(P, data, bucket.x & 0xffffu, prm.good, m, dist, budget);
-            if (prm.nslots > 2) lz2_try(P, data, bucket.x >> 16, prm.good, m, dist, budget);
-            if (prm.nslots > 3) lz2_try(P, data, bucket.y & 0xffffu, prm.good, m, dist, budget);
-            if (prm.nslots > 4) lz2_try(P, data, bucket.y >> 16, prm.good, m, dist, budget);
+            if (prm.own_ways > 1) lz2_try(P, data, bucket.x >> 16, prm.good, m, dist, budget);
+            if (prm.own_ways > 2) lz2_try(P, data, bucket.y & 0xffffu, prm.good, m, dist, budget);
+            if (prm.own_ways > 3) lz2_try(P, data, bucket.y >> 16, prm.good, m, dist, budget);
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            if (prm.nslots > 5u + (uint32_t)j && __any_sync(ZB_FULL, budget > 0 && m < P.stop))
+            if (prm.hist_segs > (uint32_t)j && __any_sync(ZB_FULL, budget > 0 && m < P.stop))
               lz2_try(P, data, hcand[j], prm.good, m, dist, budget);
           }
           // one-step lazy evaluation (zlib's max_lazy idea)
@@ -1083,14 +1083,14 @@ __global__ void __launch_bounds__(LZ_THREADS)
 static bool zb_is_lz_level(int level) { return level == -1 || level >= 2; }
 // Search effort per level, after the reference's configurationTable (internal.nim:177-189: good / lazy / nice /
 // chain per level; lz77.nim:97-109 walks `chain` links and quarters the rest at `good`).  Here the candidates
-// come from 4-way buckets instead of a chain, so the budget is how many candidate slots are looked at
-// (nslots: own window, own bucket, then the preceding segments' buckets) and how many of them may pass the
-// 4-byte check (maxcand); `good` keeps its meaning and `lazy` is the one-step lazy threshold.  Effort and
-// compressed size are monotone in the level.
+// come from tables instead of a chain, so the budget is how many candidates are looked at (own_ways of the
+// own bucket, the entries of hist_segs preceding segments) and how many of them may pass the 4-byte check
+// (maxcand); `good` keeps its meaning and `lazy` is the one-step lazy threshold.  Effort and compressed
+// size are monotone in the level.
 ZbLz2Params zb_lz2_params(int level) {
-  //                                     nslots maxcand good lazy
-  static const ZbLz2Params table[10] = {{9, 8, 8, 16},  {9, 8, 8, 16},  {5, 2, 4, 0},   {6, 3, 4, 6},   {7, 4, 4, 8},
-                                        {8, 6, 8, 16},  {9, 8, 8, 16},  {9, 9, 8, 32},  {9, 9, 16, 32}, {9, 9, 32, 64}};
+  //                                     own hist maxcand good lazy
+  static const ZbLz2Params table[10] = {{4, 4, 8, 8, 16}, {4, 4, 8, 8, 16}, {2, 4, 2, 4, 0},  {2, 4, 3, 4, 6},   {3, 4, 4, 4, 8},
+                                        {4, 4, 6, 8, 16}, {4, 4, 8, 8, 16}, {4, 4, 9, 8, 32}, {4, 4, 9, 16, 32}, {4, 4, 9, 32, 64}};
   return table[(level >= 2 && level <= 9) ? level : 6];  // -1 (Default) = level 6
 }
 size_t zb_lz2_table_bytes(int *grid_out) {

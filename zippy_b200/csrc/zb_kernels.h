@@ -53,10 +53,11 @@ struct ZbCompressWork {
 cudaError_t zb_setup_deflate_attrs();
 cudaError_t zb_setup_inflate_attrs();
 struct ZbLz2Params {
-  uint32_t nslots;   // candidate slots looked at per position (1 in-window + 4 own ways + 1 per preceding segment, <= 9)
-  uint32_t maxcand;  // candidates per position that may pass the 4-byte check and be extended
-  uint32_t good;     // a match this long leaves room for one more candidate only
-  uint32_t lazy;     // matches shorter than this yield to a longer match at the next position (0: greedy)
+  uint32_t own_ways;   // ways of the own bucket looked at (1..4), after the closest same-hash position of the window
+  uint32_t hist_segs;  // preceding segments whose entry is looked at (0..4), nearest first
+  uint32_t maxcand;    // candidates per position that may pass the 4-byte check and be extended
+  uint32_t good;       // a match this long leaves room for one more candidate only
+  uint32_t lazy;       // matches shorter than this yield to a longer match at the next position (0: greedy)
 };
 ZbLz2Params zb_lz2_params(int level);
 size_t zb_lz2_table_bytes(int *grid_out);
