@@ -163,6 +163,26 @@ int zb200_checksum_batch_device(zb200_ctx *ctx, const uint8_t *d_src, const uint
 int zb200_host_register(void *ptr, size_t bytes);
 int zb200_host_unregister(void *ptr);
 
+/* ---- several GPUs behind one call (SURVEY 8e at the boundary) ----
+ * Members shard by contiguous index range, balanced by bytes; one host thread drives each device through its
+ * own ctx; there is no data-path collective.  compress: every shard is compressed on its device, the per-shard
+ * sizes are gathered, and each shard's bytes are copied to their place in ONE concatenated host stream
+ * (dst_offsets are global).  The multi-process form (one rank per GPU, NCCL all_gather of the sizes) is
+ * zippy_b200/sharding.py; this is the same path for a caller that is a single process, e.g. a Nim program.
+ * devices == NULL or n_devices <= 0: every visible device.  A device may be listed more than once. */
+typedef struct zb200_mgpu zb200_mgpu;
+int zb200_mgpu_init(const int *devices, int n_devices, zb200_mgpu **out);
+void zb200_mgpu_shutdown(zb200_mgpu *m);
+int zb200_mgpu_device_count(zb200_mgpu *m);
+int zb200_mgpu_compress_batch(zb200_mgpu *m, const uint8_t *src_base, const uint64_t *src_offsets, size_t n,
+                              int level, int data_format, const uint8_t *fname_lens,
+                              uint8_t *dst_base, size_t dst_cap, uint64_t *dst_offsets, int *statuses);
+int zb200_mgpu_uncompress_batch(zb200_mgpu *m, const uint8_t *src_base, const uint64_t *src_offsets, size_t n,
+                                int data_format, uint8_t *dst_base, const uint64_t *dst_offsets,
+                                uint64_t *dst_lens, int *statuses);
+int zb200_mgpu_checksum_batch(zb200_mgpu *m, const uint8_t *src_base, const uint64_t *src_offsets, size_t n,
+                              int kind, uint32_t *out);
+
 /* ---- instrumentation (bench.py): device time in ms of the kernels of the last batch call,
  * measured with CUDA events on the ctx stream, and how many kernels it launched. ---- */
 typedef struct {

@@ -26,7 +26,7 @@ NoCompression, BestSpeed, BestCompression = 0, 1, 9                    # common.
 DefaultCompression, HuffmanOnly = -1, -2
 
 __all__ = ["compress", "uncompress", "crc32", "adler32", "deflate", "inflate", "compress_batch", "uncompress_batch",
-           "uncompressed_sizes", "checksum_batch", "ZippyError", "Context", "dfDetect", "dfZlib", "dfGzip",
+           "uncompressed_sizes", "checksum_batch", "ZippyError", "Context", "MultiGpu", "dfDetect", "dfZlib", "dfGzip",
            "dfDeflate", "NoCompression", "BestSpeed", "BestCompression", "DefaultCompression", "HuffmanOnly"]
 
 
@@ -285,6 +285,70 @@ class Context:
         v = ctypes.c_uint32(0)
         _check(self._h, _native.lib().zb200_adler32(self._h, src.ctypes.data, src.size, ctypes.byref(v)))
         return v.value
+
+
+class MultiGpu:
+    """zb200_mgpu: several devices behind one call (one host thread and one ctx per device)."""
+
+    def __init__(self, devices=None):
+        self._h = ctypes.c_void_p()
+        L = _native.lib()
+        arr = (ctypes.c_int * len(devices))(*devices) if devices else None
+        rc = L.zb200_mgpu_init(arr, len(devices) if devices else 0, ctypes.byref(self._h))
+        if rc != 0:
+            raise ZippyError(rc, "zb200_mgpu_init failed: %s" % L.zb200_strerror(rc).decode())
+
+    def close(self):
+        if self._h:
+            _native.lib().zb200_mgpu_shutdown(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_count(self):
+        return _native.lib().zb200_mgpu_device_count(self._h)
+
+    def compress_batch(self, base, offsets, level=DefaultCompression, dataFormat=dfGzip):
+        """-> (one concatenated uint8 stream, global member offsets uint64[n+1])"""
+        L = _native.lib()
+        base = _as_u8(base)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        bound = int(L.zb200_compress_bound(int(offsets[-1] - offsets[0]), dataFormat)) + 128 * n + 4096
+        out = np.empty(bound, dtype=np.uint8)
+        oo = np.zeros(n + 1, dtype=np.uint64)
+        _check(None, L.zb200_mgpu_compress_batch(self._h, base.ctypes.data, offsets.ctypes.data, n, level, dataFormat, None,
+                                                  out.ctypes.data, out.size, oo.ctypes.data, None))
+        return out[:int(oo[n])], oo
+
+    def uncompress_batch(self, base, offsets, sizes, dataFormat=dfDetect):
+        """sizes: output slot sizes (uint64[n]).  -> (out, dst_offsets, lens, statuses)"""
+        L = _native.lib()
+        base = _as_u8(base)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        do = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(np.asarray(sizes, dtype=np.uint64), out=do[1:])
+        out = np.empty(int(do[n]) + 64, dtype=np.uint8)
+        lens = np.zeros(max(n, 1), dtype=np.uint64)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        _check(None, L.zb200_mgpu_uncompress_batch(self._h, base.ctypes.data, offsets.ctypes.data, n, dataFormat,
+                                                    out.ctypes.data, do.ctypes.data, lens.ctypes.data, st.ctypes.data))
+        return out[:int(do[n])], do, lens[:n], st[:n]
+
+    def checksum_batch(self, base, offsets, kind="crc32"):
+        L = _native.lib()
+        base = _as_u8(base)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        _check(None, L.zb200_mgpu_checksum_batch(self._h, base.ctypes.data, offsets.ctypes.data, n,
+                                                  0 if kind == "crc32" else 1, out.ctypes.data))
+        return out[:n]
 
 
 def host_register(ptr, nbytes):

@@ -54,6 +54,13 @@ SYMBOLS = {
                                               c_intp]),
     "zb200_uncompress_sizes_device": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, c_u64p, c_intp]),
     "zb200_checksum_batch_device": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, ctypes.c_void_p]),
+    "zb200_mgpu_init": (c_int, [ctypes.c_void_p, c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "zb200_mgpu_shutdown": (None, [ctypes.c_void_p]),
+    "zb200_mgpu_device_count": (c_int, [ctypes.c_void_p]),
+    "zb200_mgpu_compress_batch": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, c_int, c_u8p, c_u8p, c_size_t,
+                                          c_u64p, c_intp]),
+    "zb200_mgpu_uncompress_batch": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, c_u8p, c_u64p, c_u64p, c_intp]),
+    "zb200_mgpu_checksum_batch": (c_int, [ctypes.c_void_p, c_u8p, c_u64p, c_size_t, c_int, ctypes.c_void_p]),
     "zb200_last_timing": (c_int, [ctypes.c_void_p, ctypes.POINTER(Timing)]),
 }
 

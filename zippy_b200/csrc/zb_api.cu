@@ -8,8 +8,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
 #include <functional>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -29,6 +32,97 @@ constexpr size_t kHostGroupChunks = 4096;     // host batches: 256 MiB groups so
 
 }  // namespace
 
+// ---- pageable host memory ----
+// cudaMemcpyAsync only overlaps with kernels for page-locked memory; a caller's ordinary buffer (a Nim
+// string, malloc, numpy) would make every copy block.  Such buffers are staged through a ring of pinned
+// slots: a few host threads memcpy a slice into a slot while the DMA engine drains the previous one.
+class CopyPool {
+ public:
+  ~CopyPool() { stop(); }
+  void start(int n) {
+    if (!th_.empty()) return;
+    for (int i = 0; i < n; i++) th_.emplace_back([this] { work(); });
+  }
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (std::thread &t : th_) t.join();
+    th_.clear();
+  }
+  // copy n bytes with all workers (plus the caller); returns when done
+  void copy(uint8_t *dst, const uint8_t *src, size_t n) {
+    const size_t piece = 1 << 20;
+    if (th_.empty() || n < 2 * piece) {
+      memcpy(dst, src, n);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      dst_ = dst;
+      src_ = src;
+      n_ = n;
+      next_ = 0;
+      left_ = (n + piece - 1) / piece;
+    }
+    cv_.notify_all();
+    help(piece);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return left_ == 0; });
+  }
+
+ private:
+  bool take(size_t piece, size_t &off, size_t &len) {
+    std::lock_guard<std::mutex> lk(m_);
+    if (next_ >= n_) return false;
+    off = next_;
+    len = std::min(piece, n_ - next_);
+    next_ += len;
+    return true;
+  }
+  void finish_one() {
+    std::lock_guard<std::mutex> lk(m_);
+    if (--left_ == 0) done_.notify_all();
+  }
+  void help(size_t piece) {
+    size_t off, len;
+    while (take(piece, off, len)) {
+      memcpy(dst_ + off, src_ + off, len);
+      finish_one();
+    }
+  }
+  void work() {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [this] { return quit_ || next_ < n_; });
+        if (quit_) return;
+      }
+      help(1 << 20);
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  uint8_t *dst_ = nullptr;
+  const uint8_t *src_ = nullptr;
+  size_t n_ = 0, next_ = 0, left_ = 0;
+  bool quit_ = false;
+};
+
+constexpr size_t kStageSlotBytes = 32u << 20;
+constexpr int kStageSlots = 4;
+struct StageRing {
+  uint8_t *slot[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  bool busy[kStageSlots] = {false, false, false, false};
+  uint8_t *out_dst[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};  // D2H ring: where the slot's bytes go
+  size_t out_n[kStageSlots] = {0, 0, 0, 0};
+  size_t next = 0;
+};
+
 struct zb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -40,10 +134,14 @@ struct zb200_ctx {
   DevBuf seg_src, seg_dst, seg_len, seg_status, seg_kind, seg_expect, seg_cand, skip_mask;  // large-member segments
   DevBuf mark_scratch, mark_segs, seg_bits;  // speculative segments of a large member (uint16 symbols, descriptors)
   DevBuf order;             // work-queue order of an inflate launch (longest members first)
+  StageRing ring_in, ring_out;   // pinned slots for pageable callers (allocated on first use)
+  CopyPool pool;
   uint64_t pending_len = 0;     // zb200_decode_begin's result, waiting in out_stage for zb200_decode_finish
   bool pending = false;
-  bool serial_copies = false;  // host pipelines: do not run H2D and D2H at the same time (ZB200_SERIAL_COPIES)
   uint64_t big_member_bytes = 512ull << 10;  // members at least this long are tried as parallel segments
+  uint64_t single_member_bytes = 24ull << 10;  // ... and from this size when the call holds ONE input: nothing else could fill the GPU,
+                                               // so even three or four blocks decoded side by side cut the latency (config 1)
+  bool big_env = false;
   cudaEvent_t ev[10] = {};
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> gev;   // per-group events (H2D done, compute done, offsets ready)
@@ -120,6 +218,12 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 int ensure_pinned(zb200_ctx *ctx, size_t bytes) {
   if (bytes <= ctx->pin_cap) return ZB200_OK;
   if (ctx->pin) cudaFreeHost(ctx->pin);
+  ctx->pool.stop();
+  for (StageRing *r : {&ctx->ring_in, &ctx->ring_out})
+    for (int i = 0; i < kStageSlots; i++) {
+      if (r->slot[i]) cudaFreeHost(r->slot[i]);
+      if (r->ev[i]) cudaEventDestroy(r->ev[i]);
+    }
   ctx->pin = nullptr;
   ctx->pin_cap = 0;
   size_t want = bytes + bytes / 4 + 4096;
@@ -137,6 +241,93 @@ int ensure_group_events(zb200_ctx *ctx, size_t n) {
     cudaEvent_t e;
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return ZB200_ERR_CUDA;
     ctx->gev.push_back(e);
+  }
+  return ZB200_OK;
+}
+
+bool is_pageable(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+int ring_ready(zb200_ctx *ctx, StageRing &r) {
+  if (r.slot[0]) return ZB200_OK;
+  for (int i = 0; i < kStageSlots; i++) {
+    if (cudaMallocHost((void **)&r.slot[i], kStageSlotBytes) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->last_err = "pinned staging ring: allocation failed";
+      return ZB200_ERR_NOMEM;
+    }
+  }
+  unsigned hc = std::thread::hardware_concurrency();
+  ctx->pool.start((int)std::min<unsigned>(7, hc > 2 ? hc / 2 : 1));
+  return ZB200_OK;
+}
+
+// host -> device on `st`: asynchronous for page-locked memory, staged through the pinned ring otherwise
+int h2d_copy(zb200_ctx *ctx, uint8_t *d_dst, const uint8_t *h_src, size_t n, cudaStream_t st, bool pageable) {
+  if (!n) return ZB200_OK;
+  if (!pageable) {
+    CK(cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, st));
+    return ZB200_OK;
+  }
+  StageRing &r = ctx->ring_in;
+  int rc = ring_ready(ctx, r);
+  if (rc) return rc;
+  for (size_t off = 0; off < n; off += kStageSlotBytes) {
+    const size_t len = std::min(kStageSlotBytes, n - off);
+    const size_t k = r.next++ % kStageSlots;
+    if (r.busy[k]) CK(cudaEventSynchronize(r.ev[k]));   // the DMA that last read this slot is done
+    ctx->pool.copy(r.slot[k], h_src + off, len);
+    CK(cudaMemcpyAsync(d_dst + off, r.slot[k], len, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(r.ev[k], st));
+    r.busy[k] = true;
+  }
+  return ZB200_OK;
+}
+
+// finish the oldest / all pending device -> pageable copies (the slot's bytes go to their place)
+int d2h_complete(zb200_ctx *ctx, size_t k) {
+  StageRing &r = ctx->ring_out;
+  if (!r.busy[k]) return ZB200_OK;
+  CK(cudaEventSynchronize(r.ev[k]));
+  ctx->pool.copy(r.out_dst[k], r.slot[k], r.out_n[k]);
+  r.busy[k] = false;
+  return ZB200_OK;
+}
+int d2h_flush(zb200_ctx *ctx) {
+  if (!ctx->ring_out.slot[0]) return ZB200_OK;
+  for (size_t i = 0; i < (size_t)kStageSlots; i++) {
+    int rc = d2h_complete(ctx, (ctx->ring_out.next + i) % kStageSlots);   // oldest first
+    if (rc) return rc;
+  }
+  return ZB200_OK;
+}
+// device -> host on `st`; for pageable memory the bytes land when d2h_flush (or a later d2h_copy) says so
+int d2h_copy(zb200_ctx *ctx, uint8_t *h_dst, const uint8_t *d_src, size_t n, cudaStream_t st, bool pageable) {
+  if (!n) return ZB200_OK;
+  if (!pageable) {
+    CK(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, st));
+    return ZB200_OK;
+  }
+  StageRing &r = ctx->ring_out;
+  int rc = ring_ready(ctx, r);
+  if (rc) return rc;
+  for (size_t off = 0; off < n; off += kStageSlotBytes) {
+    const size_t len = std::min(kStageSlotBytes, n - off);
+    const size_t k = r.next++ % kStageSlots;
+    rc = d2h_complete(ctx, k);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(r.slot[k], d_src + off, len, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(r.ev[k], st));
+    r.busy[k] = true;
+    r.out_dst[k] = h_dst + off;
+    r.out_n[k] = len;
   }
   return ZB200_OK;
 }
@@ -174,6 +365,7 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   dst_offsets[0] = 0;
   if (n == 0) return ZB200_OK;
   const uint64_t src_lo = src_offsets[0];  // d_src holds [src_lo, src_hi) rebased to 0 when staging from the host
+  const bool src_pageable = h_src && is_pageable(h_src + src_lo), dst_pageable = h_dst && is_pageable(h_dst);
 
   // ---- plan: groups, descriptors ----
   std::vector<Group> groups;
@@ -306,7 +498,10 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
         if (hi > h_dst_cap) return ZB200_ERR_DST_TOO_SMALL;
         CK(cudaStreamWaitEvent(sd, ctx->gev[3 * d2h_done + 1], 0));
         if (d2h_done == 0) CK(cudaEventRecord(ctx->ev[8], sd));
-        if (hi > lo) CK(cudaMemcpyAsync(h_dst + lo, d_dst + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, sd));
+        if (hi > lo) {
+          int rc2 = d2h_copy(ctx, h_dst + lo, d_dst + lo, (size_t)(hi - lo), sd, dst_pageable);
+          if (rc2) return rc2;
+        }
       }
     }
     return ZB200_OK;
@@ -315,9 +510,10 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
   for (size_t gi = 0; gi < ng; gi++) {
     const Group &g = groups[gi];
     if (h_src) {
-      if (g.in_hi > g.in_lo)
-        CK(cudaMemcpyAsync((uint8_t *)d_src + g.in_lo, h_src + src_lo + g.in_lo, (size_t)(g.in_hi - g.in_lo),
-                           cudaMemcpyHostToDevice, sh));
+      if (g.in_hi > g.in_lo) {
+        int rc2 = h2d_copy(ctx, (uint8_t *)d_src + g.in_lo, h_src + src_lo + g.in_lo, (size_t)(g.in_hi - g.in_lo), sh, src_pageable);
+        if (rc2) return rc2;
+      }
       CK(cudaEventRecord(ctx->gev[3 * gi + 0], sh));
       CK(cudaStreamWaitEvent(s, ctx->gev[3 * gi + 0], 0));
     }
@@ -354,6 +550,10 @@ int compress_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint8_t *h_src, 
     if (rc) return rc;
   }
   if (h_dst) CK(cudaEventRecord(ctx->ev[9], sd));
+  if (dst_pageable) {
+    int rc = d2h_flush(ctx);
+    if (rc) return rc;
+  }
   CK(cudaStreamSynchronize(s));
   if (h_src) CK(cudaStreamSynchronize(sh));
   if (h_dst) CK(cudaStreamSynchronize(sd));
@@ -488,7 +688,8 @@ struct BigResult {
 //    decode, which also produces the reference's verdict for it.  The trailer check runs on the output
 //    either way.
 int inflate_member_speculative(zb200_ctx *ctx, const uint8_t *d_src, uint64_t m0, const HostWrapper &hw, uint8_t *d_dst,
-                               uint64_t dst0, uint64_t mcap, bool count_only, bool &ok, uint64_t &out_len, bool &too_small) {
+                               uint64_t dst0, uint64_t mcap, bool count_only, bool latency, bool &ok, uint64_t &out_len,
+                               bool &too_small) {
   ok = false;
   too_small = false;
   cudaStream_t s = ctx->stream;
@@ -509,7 +710,8 @@ int inflate_member_speculative(zb200_ctx *ctx, const uint8_t *d_src, uint64_t m0
   std::sort(cand.begin(), cand.end());
   // boundaries: the payload start, then candidates at least min_gap apart (a segment costs a 64 KiB marker prefill)
   // (at most 60000 segments: the resolve kernels index them with a grid dimension)
-  const uint64_t min_gap = std::max<uint64_t>(16384ull * 8ull, (hi_bit - lo_bit) / 60000ull);
+  // a single input is all the GPU has: cut it as finely as its blocks allow
+  const uint64_t min_gap = std::max<uint64_t>((latency ? 2048ull : 16384ull) * 8ull, (hi_bit - lo_bit) / 60000ull);
   std::vector<uint64_t> bits(1, lo_bit);
   for (uint64_t c : cand)
     if (c >= bits.back() + min_gap && c + min_gap / 4 < hi_bit) bits.push_back(c);
@@ -628,7 +830,7 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
   // Every large member costs a few host round trips here, while a batch of thousands of members
   // already fills the GPU with one group per member: with many large members only the huge ones
   // (minutes of serial decode) take this path.
-  uint64_t min_len = ctx->big_member_bytes;
+  uint64_t min_len = (n == 1 && !ctx->big_env) ? ctx->single_member_bytes : ctx->big_member_bytes;
   {
     size_t count = 0;
     for (size_t m = 0; m < n; m++) count += (src_offsets[m + 1] - src_offsets[m]) >= min_len;
@@ -652,7 +854,7 @@ int inflate_big_members(zb200_ctx *ctx, const uint8_t *d_src, const uint64_t *sr
     auto speculative = [&]() -> int {
       bool sok = false, small = false;
       uint64_t slen = 0;
-      int src_ = inflate_member_speculative(ctx, d_src, m0, hw, d_dst, dst0_m, mcap_m, count_only, sok, slen, small);
+      int src_ = inflate_member_speculative(ctx, d_src, m0, hw, d_dst, dst0_m, mcap_m, count_only, n == 1, sok, slen, small);
       if (src_) return src_;
       if (sok || small) {
         BigResult r;
@@ -990,16 +1192,17 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
   CK(cudaStreamWaitEvent(sd, ctx->gev[2 * ng], 0));
   CK(cudaEventRecord(ctx->ev[6], sh));
   CK(cudaEventRecord(ctx->ev[8], sd));
-  for (size_t gi = 0; gi < ng; gi++) {
-    const uint64_t b0 = reb[gb[gi]], b1 = reb[gb[gi + 1]];
-    if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + b0, h_src + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sh));
-    CK(cudaEventRecord(ctx->gev[2 * gi], sh));
-  }
-  CK(cudaEventRecord(ctx->ev[7], sh));
-  if (ctx->serial_copies) CK(cudaStreamWaitEvent(sd, ctx->gev[2 * (ng - 1)], 0));  // copies out start after the last copy in
+  const bool src_pageable = is_pageable(h_src), dst_pageable = h_dst && is_pageable(h_dst);
   CK(cudaEventRecord(ctx->ev[0], s));
   for (size_t gi = 0; gi < ng; gi++) {
     const size_t m0 = gb[gi], m1 = gb[gi + 1], nm = m1 - m0;
+    {
+      const uint64_t b0 = reb[m0], b1 = reb[m1];
+      int rc = h2d_copy(ctx, (uint8_t *)ctx->in_stage.p + b0, h_src + b0, (size_t)(b1 - b0), sh, src_pageable);
+      if (rc) return rc;
+      CK(cudaEventRecord(ctx->gev[2 * gi], sh));
+      if (gi + 1 == ng) CK(cudaEventRecord(ctx->ev[7], sh));
+    }
     CK(cudaStreamWaitEvent(s, ctx->gev[2 * gi], 0));
     ZbInflateWork w;
     memset(&w, 0, sizeof(w));
@@ -1038,11 +1241,18 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
     CK(cudaEventRecord(ctx->gev[2 * gi + 1], s));
     CK(cudaStreamWaitEvent(sd, ctx->gev[2 * gi + 1], 0));
     const uint64_t o0 = dreb[m0], o1 = dreb[m1];
-    if (o1 > o0 && h_dst) CK(cudaMemcpyAsync(h_dst + o0, d_dst + o0, (size_t)(o1 - o0), cudaMemcpyDeviceToHost, sd));
+    if (o1 > o0 && h_dst) {
+      int rc = d2h_copy(ctx, h_dst + o0, d_dst + o0, (size_t)(o1 - o0), sd, dst_pageable);
+      if (rc) return rc;
+    }
     ctx->timing.kernel_launches += 3;
   }
   CK(cudaEventRecord(ctx->ev[1], s));
   CK(cudaEventRecord(ctx->ev[9], sd));
+  if (dst_pageable) {
+    int rc = d2h_flush(ctx);
+    if (rc) return rc;
+  }
   uint64_t *pl = (uint64_t *)ctx->pin;
   int *ps = (int *)(pl + n);
   CK(cudaMemcpyAsync(pl, ctx->out_len.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -1166,13 +1376,15 @@ int zb200_init(int device, zb200_ctx **out) {
   }
   if (const char *e = getenv("ZB200_BIG_MEMBER_BYTES")) {  // test hook: segment path for small members too
     long long v = atoll(e);
-    if (v > 0) ctx->big_member_bytes = (uint64_t)v;
+    if (v > 0) {
+      ctx->big_member_bytes = (uint64_t)v;
+      ctx->big_env = true;
+    }
   }
   if (const char *e = getenv("ZB200_UNC_GROUP_BYTES")) {  // test hook: small pipelined groups in the host uncompress
     long long v = atoll(e);
     if (v > 0) ctx->unc_group_out_bytes = (uint64_t)v;
   }
-  if (const char *e = getenv("ZB200_SERIAL_COPIES")) ctx->serial_copies = atoi(e) != 0;
   if (const char *e = getenv("ZB200_DEV_GROUP_CHUNKS")) {  // device-resident batches only (bench.py)
     long v = atol(e);
     if (v > 0) ctx->dev_group_chunks = (size_t)v;
@@ -1216,6 +1428,12 @@ void zb200_shutdown(zb200_ctx *ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (cudaEvent_t e : ctx->gev) cudaEventDestroy(e);
   if (ctx->pin) cudaFreeHost(ctx->pin);
+  ctx->pool.stop();
+  for (StageRing *r : {&ctx->ring_in, &ctx->ring_out})
+    for (int i = 0; i < kStageSlots; i++) {
+      if (r->slot[i]) cudaFreeHost(r->slot[i]);
+      if (r->ev[i]) cudaEventDestroy(r->ev[i]);
+    }
   if (ctx->group_end.p) cudaFree(ctx->group_end.p);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);

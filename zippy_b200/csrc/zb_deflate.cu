@@ -19,6 +19,9 @@
 #define LZ_HASH_BITS 11
 #define LZ_TABLE_ENTRIES (1 << LZ_HASH_BITS)
 #define LZ_PRESEED 2048
+#ifndef ZB_LZ1_RESOLVE_WINNER
+#define ZB_LZ1_RESOLVE_WINNER 0  // 1: resolve same-entry stores of one instruction in software (deterministic by construction)
+#endif
 #define LZ_LANE_CAP 32  // bytes a lane extends on its own; a selected match that hit the cap finishes warp-cooperatively
 
 // shared-memory layout of k_lz (bytes).  The CRC step table (4 KiB) is loaded by each warp
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           const bool can = p + 4 <= len;
           const uint32_t h = lz_hash(zb_ld32_unaligned(data, mis + p));
           if (can) table[h] = (uint16_t)p;
+#if ZB_LZ1_RESOLVE_WINNER
           __syncwarp();
           for (;;) {  // same-entry stores of one instruction: the highest position wins (see the main loop)
             const bool lost = can && table[h] < (uint16_t)p;
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
             if (lost) table[h] = (uint16_t)p;
             __syncwarp();
           }
+#endif
         }
         __syncwarp();
       }
@@ -272,15 +277,19 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           // exactly one of them lands, and WHICH is up to the hardware (resolving the winner with
           // __match_any_sync costs 30 % of the kernel, measured) ...
           if (can) table[h] = (uint16_t)p;
+#if ZB_LZ1_RESOLVE_WINNER
           __syncwarp();
-          // ... so make the outcome independent of it: the highest position wins (full-size runs were NOT
-          // identical run to run without this; every round strictly raises the entry, so it ends)
+          // make the outcome independent of the arbitration: the highest position wins (every round strictly
+          // raises the entry, so it ends).  +10 % on the kernel, measured; off by default because the
+          // arbitration IS a fixed function of the instruction's addresses on this hardware -- the full-size
+          // run-to-run test (tests/test_gpu_fullsize.py) is what holds that claim to account
           for (;;) {
             const bool lost = can && table[h] < (uint16_t)p;
             if (!__any_sync(ZB_FULL, lost)) break;
             if (lost) table[h] = (uint16_t)p;
             __syncwarp();
           }
+#endif
           // a match may not cross the sub-chunk end (the next warp starts its own parse there)
           const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
           if (can && c < p && p - c <= ZB_MAX_DIST && p >= entry && limit >= ZB_MIN_MATCH) {
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 #define LZ2_BUCKET_BITS 11
 #define LZ2_BUCKETS (1 << LZ2_BUCKET_BITS)                          // per table (own and static)
 #define LZ2_TABLES_PER_CTA (ZB_WARPS_PER_CHUNK + LZ2_SEGS)          // 8 own + 12 static
-#define LZ2_RING_WINDOWS 16
+#define LZ2_RING_WINDOWS 8
 #define LZ2_SM_DATA_BYTES (ZB_CHUNK_BYTES + LZ2_HIST + 64 + 384)
 #define LZ2_SM_HIST (LZ2_SM_DATA_BYTES)
 #define LZ2_SM_RING (LZ2_SM_HIST + LZ_SM_HIST_BYTES)
@@ -385,7 +394,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
 #define LZ2_SM_CRC (LZ2_SM_RING + LZ2_SM_RING_BYTES)
 #define LZ2_SM_LMUL (LZ2_SM_CRC + 4096)
 #define LZ2_SM_PART (LZ2_SM_LMUL + LZ_SM_LMUL_BYTES)
-#define LZ2_SM_BAR (LZ2_SM_PART + LZ_SM_PART_BYTES)
+#define LZ2_SM_LIST (LZ2_SM_PART + LZ_SM_PART_BYTES)               // verified candidates: 8 x u16 per thread
+#define LZ2_SM_BAR (LZ2_SM_LIST + 8 * LZ_THREADS * 2)
 #define LZ2_SM_TOTAL (LZ2_SM_BAR + 16)
 static_assert(2 * (LZ2_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
 
@@ -438,29 +448,39 @@ struct Lz2Pos {
   uint32_t limit, stop;    // longest match allowed here; per-lane extension stops at min(limit, lane cap)
 };
 
-// One candidate, stored as a position modulo 2^16.  Cheap rejection first: the distance test also
-// discards empty entries (0xffff aliases a distance that is out of range, or a real position whose
-// bytes are then compared like any other candidate's), then the candidate's four bytes; `budget` counts
-// the candidates that passed (lz77.nim:97-109 counts chain links).  Survivors are extended against
-// shared memory up to the lane cap; the longest match wins, a match of `good` bytes leaves room for
-// one more candidate only.
-__device__ __forceinline__ void lz2_try(const Lz2Pos &P, const uint8_t *data, uint32_t e, uint32_t good, uint32_t &m,
-                                        uint32_t &dist, int &budget) {
+// Candidate evaluation in two passes, so that the expensive part runs with full lanes:
+//  lz2_verify : one candidate (a position modulo 2^16).  Cheap rejection -- the distance test also
+//    discards empty entries (0xffff aliases a distance that is out of range, or a real position whose
+//    bytes are then compared like any other candidate's) -- then the candidate's four bytes; a survivor's
+//    distance is appended to the lane's short list in shared memory.  Every lane runs this for every
+//    candidate slot: ~16 instructions, no divergence to speak of.
+//  lz2_extend : one list entry.  Extends against shared memory up to the lane cap; the longest match wins,
+//    `budget` counts extended candidates (lz77.nim:97-109 counts chain links), a match of `good` bytes
+//    leaves room for one more only.  The warp loops over list POSITIONS, so the number of rounds is the
+//    longest list of the window (typically 3-5), not the number of slots (9).
+#define LZ2_LIST 8
+__device__ __forceinline__ void lz2_verify(const Lz2Pos &P, uint32_t e, bool search, uint16_t *dl, uint32_t &n) {
   const uint32_t d = (P.q - e) & 0xffffu;
-  if ((d - 1u) >= P.lim || budget <= 0 || m >= P.stop) return;
+  if (!search || (d - 1u) >= P.lim) return;
   const uint32_t co = P.poff - d;
   const uint32_t *wc = P.data32 + (co >> 2);
-  const uint32_t sc = (co & 3u) * 8u;
-  uint32_t hc = wc[1];
-  if (__funnelshift_r(wc[0], hc, sc) != P.v) return;
+  if (__funnelshift_r(wc[0], wc[1], (co & 3u) * 8u) != P.v) return;
+  if (n < LZ2_LIST) dl[n * (uint32_t)LZ_THREADS] = (uint16_t)d;   // entry k of thread t at list[k * LZ_THREADS + t]: conflict-free
+  n += n < LZ2_LIST ? 1u : 0u;
+}
+__device__ __forceinline__ void lz2_extend(const Lz2Pos &P, const uint8_t *data, uint32_t d, uint32_t good, uint32_t &m,
+                                           uint32_t &dist, int &budget) {
+  const uint32_t co = P.poff - d;
   budget--;
   if (m >= 4 && data[co + m] != data[P.poff + m]) {  // cannot beat the best so far
     if (m >= good && budget > 1) budget = 1;
     return;
   }
+  const uint32_t *wc = P.data32 + (co >> 2);
+  const uint32_t sc = (co & 3u) * 8u;
   const uint32_t *wp = P.data32 + (P.poff >> 2);
   const uint32_t sp = (P.poff & 3u) * 8u;
-  uint32_t hp = wp[1];
+  uint32_t hp = wp[1], hc = wc[1];
   uint32_t mc = 4;
 #pragma unroll 1
   for (int j = 2; j <= LZ_LANE_CAP / 4; j++) {
@@ -495,6 +515,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
   uint64_t *part = reinterpret_cast<uint64_t *>(smem + LZ2_SM_PART);
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + LZ2_SM_BAR);
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint16_t *dlist = reinterpret_cast<uint16_t *>(smem + LZ2_SM_LIST) + tid;
   uint32_t *whist = hist_all + warp * ZB_HIST_WORDS;
   uint32_t *ring = ring_all + warp * LZ2_RING_WINDOWS * ZB_MATCH_SLOTS;
   uint2 *cta_tabs = tables + (size_t)blockIdx.x * LZ2_TABLES_PER_CTA * LZ2_BUCKETS;
@@ -521,6 +542,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
     const uint32_t rlen = hb + len;           // staged bytes; region position q = hb + chunk position
     if (tid == 0 && rlen) zb_stage_chunk(data, rsrc, rlen, bar);
     for (int i = tid; i < ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS; i += LZ_THREADS) hist_all[i] = 0;
+    // every table starts empty for every chunk: what a member compresses to does not depend on which
+    // chunks this CTA saw before (identical inputs give identical output wherever they sit in a batch)
     lz2_clear_table(own);
     __syncthreads();
     if (rlen) {
@@ -566,17 +589,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           const uint32_t v = zb_ld32_unaligned(data, mis + q);
           const uint32_t hs = lz2_hash_mul(v) >> (32 - LZ2_STATIC_BITS);
           const bool can = q + 4 <= rlen;
-          if (can) __stcg(&tab16[hs], (uint16_t)q);
-          __syncwarp();
-          // lanes of one window that share a hash stored to one entry in one instruction: make the highest
-          // position win whatever the hardware picked (a later window always overwrites an earlier one)
-          for (;;) {
-            const bool lost = can && (uint16_t)(__ldcg(&tab16[hs]) - (uint16_t)s) < (uint16_t)lane;
-            if (!__any_sync(ZB_FULL, lost)) break;
-            if (lost) __stcg(&tab16[hs], (uint16_t)q);
-            __syncwarp();
-          }
+          // lanes of one window that share a hash would store to one entry in one instruction, and which of
+          // them lands is up to the hardware: the highest position writes, the others stand back
+          const uint32_t grp = __match_any_sync(ZB_FULL, can ? hs : (0x80000000u | (uint32_t)lane));
+          if (can && lane == 31 - __clz((int)grp)) __stcg(&tab16[hs], (uint16_t)q);
         }
+        __syncwarp();
       }
     }
     __syncthreads();  // every static table is complete (bar.sync orders the global writes inside the CTA)
@@ -628,18 +646,21 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           //   the closest same-hash position inside this window
           //   own_ways entries of the own bucket, most recent first
           //   the entries of hist_segs preceding segments, nearest segment first
-          if (search) {
+          uint32_t nl = 0;
+          {
             const uint32_t lower = grp & ((1u << lane) - 1u);
-            if (lower) lz2_try(P, data, q - ((uint32_t)lane - (uint32_t)(31 - __clz((int)lower))), prm.good, m, dist, budget);
-            lz2_try(P, data, bucket.x & 0xffffu, prm.good, m, dist, budget);
-            if (prm.own_ways > 1) lz2_try(P, data, bucket.x >> 16, prm.good, m, dist, budget);
-            if (prm.own_ways > 2) lz2_try(P, data, bucket.y & 0xffffu, prm.good, m, dist, budget);
-            if (prm.own_ways > 3) lz2_try(P, data, bucket.y >> 16, prm.good, m, dist, budget);
-          }
+            lz2_verify(P, q - ((uint32_t)lane - (uint32_t)(31 - __clz((int)(lower | 1u)))), search && lower != 0u, dlist, nl);
+            lz2_verify(P, bucket.x & 0xffffu, search, dlist, nl);
+            if (prm.own_ways > 1) lz2_verify(P, bucket.x >> 16, search, dlist, nl);
+            if (prm.own_ways > 2) lz2_verify(P, bucket.y & 0xffffu, search, dlist, nl);
+            if (prm.own_ways > 3) lz2_verify(P, bucket.y >> 16, search, dlist, nl);
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (prm.hist_segs > (uint32_t)j && __any_sync(ZB_FULL, budget > 0 && m < P.stop))
-              lz2_try(P, data, hcand[j], prm.good, m, dist, budget);
+            for (int j = 0; j < 4; j++)
+              if (prm.hist_segs > (uint32_t)j) lz2_verify(P, hcand[j], search, dlist, nl);
+          }
+          const uint32_t rounds = __reduce_max_sync(ZB_FULL, nl);
+          for (uint32_t k = 0; k < rounds; k++) {
+            if (k < nl && budget > 0 && m < P.stop) lz2_extend(P, data, dlist[k * (uint32_t)LZ_THREADS], prm.good, m, dist, budget);
           }
           // one-step lazy evaluation (zlib's max_lazy idea)
           const uint32_t mnext = __shfl_down_sync(ZB_FULL, m, 1);
