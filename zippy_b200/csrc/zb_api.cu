@@ -3,7 +3,10 @@
 // back to the CPU: every data byte is produced by the kernels in zb_deflate.cu /
 // zb_inflate.cu.
 #include <cuda_runtime.h>
+#include <execinfo.h>
+#include <signal.h>
 #include <stdio.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -218,12 +221,6 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 int ensure_pinned(zb200_ctx *ctx, size_t bytes) {
   if (bytes <= ctx->pin_cap) return ZB200_OK;
   if (ctx->pin) cudaFreeHost(ctx->pin);
-  ctx->pool.stop();
-  for (StageRing *r : {&ctx->ring_in, &ctx->ring_out})
-    for (int i = 0; i < kStageSlots; i++) {
-      if (r->slot[i]) cudaFreeHost(r->slot[i]);
-      if (r->ev[i]) cudaEventDestroy(r->ev[i]);
-    }
   ctx->pin = nullptr;
   ctx->pin_cap = 0;
   size_t want = bytes + bytes / 4 + 4096;
@@ -1322,6 +1319,9 @@ void quiesce(zb200_ctx *ctx) {
   if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
   cudaGetLastError();
+  // copies that were still waiting in the pinned ring belong to the failed call: their destinations are
+  // the caller's buffers, which it may free now -- forget them
+  for (int i = 0; i < kStageSlots; i++) ctx->ring_out.busy[i] = false;
 }
 
 // No C++ exception crosses the C ABI (std::vector growth on attacker-sized inputs, ...).
@@ -1355,8 +1355,18 @@ int zb200_device_count(void) {
   return n;
 }
 
+static void zb_segv_handler(int sig) {
+  void *frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "zippy_b200: fatal signal, backtrace (resolve with addr2line -e libzippy_b200.so):\n";
+  if (write(2, msg, sizeof(msg) - 1) < 0) _exit(128 + sig);
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(128 + sig);
+}
+
 int zb200_init(int device, zb200_ctx **out) {
   if (!out) return ZB200_ERR_ARG;
+  if (getenv("ZB200_DEBUG_SEGV")) signal(SIGSEGV, zb_segv_handler);  // debugging aid: where did a host fault happen
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -1694,7 +1704,8 @@ int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64
   const size_t ng = gb.size() - 1;
   {
     bool any_big = false;
-    for (size_t i = 0; i < n && !any_big; i++) any_big = reb[i + 1] - reb[i] >= ctx->big_member_bytes;
+    const uint64_t big_thr = (n == 1 && !ctx->big_env) ? ctx->single_member_bytes : ctx->big_member_bytes;
+    for (size_t i = 0; i < n && !any_big; i++) any_big = reb[i + 1] - reb[i] >= big_thr;
     if (!any_big) {
       int rc = uncompress_host_pipelined(ctx, src_base + slo, reb, n, data_format, dst_base ? dst_base + lo : nullptr, dreb,
                                          dst_lens, statuses, gb);

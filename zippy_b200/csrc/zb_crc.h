@@ -85,6 +85,7 @@ struct ZbCrcTables {
   uint32_t sub_mul[8];  // [k] = x^(8 * 8192 * k) mod P, k = 1..7: shifts a sub-chunk's CRC to the chunk end;
                         // [0] = x^(8 * 65536) mod P: shifts by one whole chunk
   uint32_t quart_mul[4];  // [k] = x^(8 * 2048 * k) mod P: shifts a quarter of a sub-chunk (16 rows of 128 B)
+  uint32_t ck_sub[8];     // [k] = x^(8 * 4096 * k) mod P: shifts a warp's 4 KiB of a checksum piece to the piece end
   uint32_t ck_quart[3][4][256];  // multiply-by-constant tables: [k-1][j][b] = (b << 8j) * x^(8 * 1024 * k), k = 1..3:
                                  // joins the four 1 KiB chains of the checksum kernel's 4 KiB warp pieces with lookups
 };
@@ -97,6 +98,7 @@ inline void zb_crc_build_tables(ZbCrcTables *t) {
   for (int k = 1; k < 8; k++) t->sub_mul[k] = zb_xpow8((uint64_t)ZB_SUB_BYTES * (uint64_t)k);
   t->sub_mul[0] = zb_xpow8((uint64_t)ZB_CHUNK_BYTES);
   for (int k = 0; k < 4; k++) t->quart_mul[k] = zb_xpow8((uint64_t)(ZB_SUB_BYTES / 4) * (uint64_t)k);
+  for (int k = 0; k < 8; k++) t->ck_sub[k] = zb_xpow8(4096ull * (uint64_t)k);
   for (int k = 1; k <= 3; k++) {
     const uint32_t c = zb_xpow8(1024ull * (uint64_t)k);
     for (int j = 0; j < 4; j++)

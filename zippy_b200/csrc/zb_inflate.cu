@@ -941,6 +941,7 @@ __global__ void __launch_bounds__(CK_THREADS, 1)
     for (int i = tid; i < 3 * 1024; i += CK_THREADS) qt[i] = q[i];
   }
   if (tid < 33) lane_mul[tid] = w.tabs->lane_mul[tid];
+  if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = w.tabs->ck_sub[tid - 64];
   if (tid >= 128 && tid < 128 + CK_INFO) {  // descriptors of this CTA's first 32 pieces
     const uint32_t j = (uint32_t)tid - 128u, pid = blockIdx.x + j * stride;
     const uint8_t *src = nullptr;
@@ -978,7 +979,8 @@ __global__ void __launch_bounds__(CK_THREADS, 1)
       else c = zb_warp_checksums(data, mis + b0, n, rep, lane_mul, 32u);   // a buffer's ragged last piece
       const uint32_t after = len - b1;
       if (after) {
-        if (kind == 0) c.crc_raw = zb_gf2_mul(c.crc_raw, zb_xpow8(after));
+        if (kind == 0)
+          c.crc_raw = zb_gf2_mul(c.crc_raw, (after & (CK_WARP_BYTES - 1u)) == 0u ? lane_mul[33 + after / CK_WARP_BYTES] : zb_xpow8(after));
         else c.b_sum += (uint64_t)after * c.a_sum;
       }
     }
