@@ -452,7 +452,7 @@ def test_foreign_members_decode_as_speculative_segments(z, o, corpus, monkeypatc
         fmt = z.dfDeflate if name == "raw6" else z.dfDetect
         got, st, launches = one(blob, fmt)
         assert st == 0 and got == raw, name
-        if name != "oracle6":
+        if name in ("gzip6", "zlib6", "raw6"):
             assert launches >= 9, (name, launches)   # block search, count, prefill + marker decode, 2 resolves, verify
     # sizes without decoding twice, single call
     assert ctx.decode_one(streams["zlib6"]) == raw and ctx.inflate(streams["raw6"]) == raw

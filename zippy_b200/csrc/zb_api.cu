@@ -142,8 +142,8 @@ struct zb200_ctx {
   uint64_t pending_len = 0;     // zb200_decode_begin's result, waiting in out_stage for zb200_decode_finish
   bool pending = false;
   uint64_t big_member_bytes = 512ull << 10;  // members at least this long are tried as parallel segments
-  uint64_t single_member_bytes = 24ull << 10;  // ... and from this size when the call holds ONE input: nothing else could fill the GPU,
-                                               // so even three or four blocks decoded side by side cut the latency (config 1)
+  uint64_t single_member_bytes = 512ull << 10; // threshold when the call holds ONE input.  (24 KiB was measured: alice29.txt.gz has three blocks,
+                                               // two decode passes over three segments cost what one serial pass costs -- 10.5 vs 9.4 ms -- so no gain)
   bool big_env = false;
   cudaEvent_t ev[10] = {};
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -1704,7 +1704,13 @@ int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64
   const size_t ng = gb.size() - 1;
   {
     bool any_big = false;
-    const uint64_t big_thr = (n == 1 && !ctx->big_env) ? ctx->single_member_bytes : ctx->big_member_bytes;
+    uint64_t big_thr = (n == 1 && !ctx->big_env) ? ctx->single_member_bytes : ctx->big_member_bytes;
+    {
+      // the same rule as inflate_big_members: with hundreds of large members the batch fills the GPU by itself
+      size_t count = 0;
+      for (size_t i = 0; i < n; i++) count += reb[i + 1] - reb[i] >= big_thr;
+      if (count > 256) big_thr = std::max<uint64_t>(big_thr, 64ull << 20);
+    }
     for (size_t i = 0; i < n && !any_big; i++) any_big = reb[i + 1] - reb[i] >= big_thr;
     if (!any_big) {
       int rc = uncompress_host_pipelined(ctx, src_base + slo, reb, n, data_format, dst_base ? dst_base + lo : nullptr, dreb,

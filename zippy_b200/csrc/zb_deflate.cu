@@ -1110,8 +1110,8 @@ static bool zb_is_lz_level(int level) { return level == -1 || level >= 2; }
 // size are monotone in the level.
 ZbLz2Params zb_lz2_params(int level) {
   //                                     own hist maxcand good lazy
-  static const ZbLz2Params table[10] = {{4, 4, 8, 8, 16}, {4, 4, 8, 8, 16}, {2, 4, 2, 4, 0},  {2, 4, 3, 4, 6},   {3, 4, 4, 4, 8},
-                                        {4, 4, 6, 8, 16}, {4, 4, 8, 8, 16}, {4, 4, 9, 8, 32}, {4, 4, 9, 16, 32}, {4, 4, 9, 32, 64}};
+  static const ZbLz2Params table[10] = {{4, 4, 4, 8, 16}, {4, 4, 4, 8, 16}, {2, 4, 2, 4, 0},  {2, 4, 3, 4, 6},   {3, 4, 3, 4, 8},
+                                        {3, 4, 4, 8, 16}, {4, 4, 4, 8, 16}, {4, 4, 6, 8, 32}, {4, 4, 8, 16, 32}, {4, 4, 8, 32, 64}};
   return table[(level >= 2 && level <= 9) ? level : 6];  // -1 (Default) = level 6
 }
 size_t zb_lz2_table_bytes(int *grid_out) {
