@@ -1692,7 +1692,14 @@ int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64
   std::vector<size_t> gb(1, 0);
   {
     uint64_t out_cap = ctx->unc_group_out_bytes;
-    if (!out_cap) out_cap = std::min<uint64_t>(std::max<uint64_t>((hi - lo) / 8, 64ull << 20), 1ull << 30);
+    if (!out_cap) {
+      // a member is decoded by ONE 8-lane group at ~9 MB/s, so every group's launch ends with the tail of its
+      // longest member: a group must be worth several such tails (8192 x the largest output slot matches the
+      // measured optimum of 512 MiB groups for 64 KiB members); otherwise an eighth of the batch
+      uint64_t max_out = 0;
+      for (size_t i = 0; i < n; i++) max_out = std::max<uint64_t>(max_out, dreb[i + 1] - dreb[i]);
+      out_cap = std::max<uint64_t>(std::max<uint64_t>((hi - lo) / 8, 8192ull * max_out), 64ull << 20);
+    }
     const uint64_t in_cap = out_cap;
     size_t a = 0;
     for (size_t i = 1; i <= n; i++)
