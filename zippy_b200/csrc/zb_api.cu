@@ -147,7 +147,6 @@ struct zb200_ctx {
   bool big_env = false;
   cudaEvent_t ev[10] = {};
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  cudaStream_t alt_stream = nullptr;  // second compute stream: consecutive member groups of the host uncompress overlap their tails
   std::vector<cudaEvent_t> gev;   // per-group events (H2D done, compute done, offsets ready)
   void *pin = nullptr;            // pinned host scratch for descriptors / offsets
   size_t pin_cap = 0;
@@ -1117,11 +1116,9 @@ int uncompress_device_locked(zb200_ctx *ctx, const uint8_t *d_src, const uint64_
 // ---- uncompress, host buffers, fully asynchronous ----
 // Everything the device needs for the WHOLE batch (offsets, verification pieces, work-queue orders) is
 // built and uploaded once; then every member group is enqueued without a host wait in between:
-//   H2D stream      : copy-in of group 0, 1, 2, ...
-//   compute streams : wait copy-in(g) -> inflate(g), groups alternating between two streams: a launch ends
-//                     with the tail of its longest members (one 8-lane group each, SMs emptying), and the
-//                     next group's CTAs move in as the previous group's exit
-//   D2H stream      : wait inflate(g) -> verify(g) -> copy-out(g)
+//   H2D stream : copy-in of group 0, 1, 2, ... back to back
+//   main stream: wait copy-in(g) -> inflate(g) -> verify(g)
+//   D2H stream : wait verify(g) -> copy-out(g)
 // and the host synchronises once at the end.  (The first version waited for every group's kernels on the
 // host before it built and launched the next group, and each launch carried its own tail of long members.)
 int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::vector<uint64_t> &reb, size_t n,
@@ -1190,7 +1187,6 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
   CK(cudaEventRecord(ctx->gev[2 * ng], s));
   CK(cudaStreamWaitEvent(sh, ctx->gev[2 * ng], 0));
   CK(cudaStreamWaitEvent(sd, ctx->gev[2 * ng], 0));
-  CK(cudaStreamWaitEvent(ctx->alt_stream, ctx->gev[2 * ng], 0));
   CK(cudaEventRecord(ctx->ev[6], sh));
   CK(cudaEventRecord(ctx->ev[8], sd));
   const bool src_pageable = is_pageable(h_src), dst_pageable = h_dst && is_pageable(h_dst);
@@ -1204,8 +1200,7 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
       CK(cudaEventRecord(ctx->gev[2 * gi], sh));
       if (gi + 1 == ng) CK(cudaEventRecord(ctx->ev[7], sh));
     }
-    cudaStream_t sc = (gi & 1) ? ctx->alt_stream : s;   // this group's compute stream
-    CK(cudaStreamWaitEvent(sc, ctx->gev[2 * gi], 0));
+    CK(cudaStreamWaitEvent(s, ctx->gev[2 * gi], 0));
     ZbInflateWork w;
     memset(&w, 0, sizeof(w));
     w.src = d_src;
@@ -1221,9 +1216,7 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
     w.n = (uint32_t)nm;
     w.data_format = data_format;
     w.order = has_order[gi] ? (const uint32_t *)ctx->order.p + m0 : nullptr;
-    CK(zb_launch_inflate(w, sc));
-    CK(cudaEventRecord(ctx->gev[2 * gi + 1], sc));
-    CK(cudaStreamWaitEvent(sd, ctx->gev[2 * gi + 1], 0));
+    CK(zb_launch_inflate(w, s));
     // gzip.nim:80-88 / zippy.nim:154-162: checksum, then size, of every member that inflated
     ZbChecksumWork cw;
     memset(&cw, 0, sizeof(cw));
@@ -1241,7 +1234,9 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
     cw.tabs = ctx->d_tabs;
     cw.n = (uint32_t)nm;
     cw.n_pieces = (uint32_t)(piece0[gi + 1] - piece0[gi]);
-    CK(zb_launch_checksum(cw, sd));
+    CK(zb_launch_checksum(cw, s));
+    CK(cudaEventRecord(ctx->gev[2 * gi + 1], s));
+    CK(cudaStreamWaitEvent(sd, ctx->gev[2 * gi + 1], 0));
     const uint64_t o0 = dreb[m0], o1 = dreb[m1];
     if (o1 > o0 && h_dst) {
       int rc = d2h_copy(ctx, h_dst + o0, d_dst + o0, (size_t)(o1 - o0), sd, dst_pageable);
@@ -1249,19 +1244,19 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
     }
     ctx->timing.kernel_launches += 3;
   }
+  CK(cudaEventRecord(ctx->ev[1], s));
   CK(cudaEventRecord(ctx->ev[9], sd));
   if (dst_pageable) {
     int rc = d2h_flush(ctx);
     if (rc) return rc;
   }
-  // the caller's stream ends after the last verification and copy out (all of them are on the D2H stream, in order)
-  CK(cudaEventRecord(ctx->gev[2 * ng + 1], sd));
-  CK(cudaStreamWaitEvent(s, ctx->gev[2 * ng + 1], 0));
-  CK(cudaEventRecord(ctx->ev[1], s));
   uint64_t *pl = (uint64_t *)ctx->pin;
   int *ps = (int *)(pl + n);
   CK(cudaMemcpyAsync(pl, ctx->out_len.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(ps, ctx->status.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  // the caller's stream ends after the last copy out
+  CK(cudaEventRecord(ctx->gev[2 * ng + 1], sd));
+  CK(cudaStreamWaitEvent(s, ctx->gev[2 * ng + 1], 0));
   CK(cudaStreamSynchronize(s));  // also: the planning vectors above stay alive until their uploads are done
   CK(cudaStreamSynchronize(sh));
   for (size_t i = 0; i < n; i++) {
@@ -1323,7 +1318,6 @@ void quiesce(zb200_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
-  if (ctx->alt_stream) cudaStreamSynchronize(ctx->alt_stream);
   cudaGetLastError();
   // copies that were still waiting in the pinned ring belong to the failed call: their destinations are
   // the caller's buffers, which it may free now -- forget them
@@ -1410,7 +1404,6 @@ int zb200_init(int device, zb200_ctx **out) {
   ctx->stream = ctx->own_stream;
   if (ok) ok = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) == cudaSuccess;
   if (ok) ok = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
-  if (ok) ok = cudaStreamCreateWithFlags(&ctx->alt_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; ok && i < 10; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   if (ok) ok = cudaMalloc((void **)&ctx->d_tabs, sizeof(ZbCrcTables)) == cudaSuccess;
   // kernel attributes are per device (and cheap to set again): every ctx sets them for its own
@@ -1455,7 +1448,6 @@ void zb200_shutdown(zb200_ctx *ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
-  if (ctx->alt_stream) cudaStreamDestroy(ctx->alt_stream);
   cudaGetLastError();
   delete ctx;
 }
