@@ -525,7 +525,8 @@ def measure_compress(e, d_src, src_offs, level, steps, warmup, n_total_members, 
     def step_device():
         oo = ctx.compress_batch_device(d_src.data_ptr(), src_offs, level, z.dfGzip, d_dst.data_ptr(), cap)
         if e.world > 1:   # the path's one exchange: every rank learns every member's compressed size
-            sizes, goffs = e.sharding.gather_sizes((oo[1:] - oo[:-1]).astype(np.int64), n_total_members, device=e.dev)
+            sizes, goffs = e.sharding.gather_sizes((oo[1:] - oo[:-1]).astype(np.int64), n_total_members, device=e.dev,
+                                                   on_device=True)   # global concatenation offsets, left on the device
             state["goffs"] = goffs
         state["oo"] = oo
 
@@ -584,7 +585,8 @@ def measure_compress(e, d_src, src_offs, level, steps, warmup, n_total_members, 
                                             None, h_dst.data_ptr(), hcap, out_offs.ctypes.data, stat.ctypes.data)
                 assert rc == 0, rc
                 if e.world > 1:
-                    e.sharding.gather_sizes((out_offs[1:] - out_offs[:-1]).astype(np.int64), n_total_members, device=e.dev)
+                    e.sharding.gather_sizes((out_offs[1:] - out_offs[:-1]).astype(np.int64), n_total_members, device=e.dev,
+                                            on_device=True)
 
             for _ in range(2):
                 step_host()

@@ -30,6 +30,9 @@ def _worker(rank, world, port, n, out_dir):
     lo, hi = sharding.shard_range(n, rank, world)
     members = [o.compress(util.c2_block(T, i, 4096 + 37 * i), 1, o.dfGzip) for i in range(lo, hi)]
     sizes, offs = sharding.gather_sizes([len(m) for m in members], n)
+    # the no-host-sync form (tensors stay where the collective put them) must agree
+    t_sizes, t_offs = sharding.gather_sizes([len(m) for m in members], n, on_device=True)
+    assert t_sizes.numpy().tolist() == list(sizes) and t_offs.numpy().tolist() == list(offs)
     # every rank writes its members at the global offsets into a shared file
     path = os.path.join(out_dir, "concat.bin")
     if rank == 0:

@@ -27,24 +27,41 @@ def shard_range_by_bytes(lens, rank, world):
     return cuts[rank], cuts[rank + 1]
 
 
-def gather_sizes(local_sizes, n_total, device=None, group=None):
-    """all_gather the per-member output sizes of every rank.
+def gather_sizes(local_sizes, n_total, device=None, group=None, on_device=False):
+    """all_gather the per-member output sizes of every rank: the path's one exchange.
 
-    local_sizes: int64 array for this rank's shard (shard_range order).  Returns
-    (all_sizes int64[n_total], global_offsets int64[n_total + 1]).  Shards may differ in
-    length by one, so sizes are padded to the longest shard for the collective."""
+    local_sizes: int64 array (or tensor on `device`) for this rank's shard (shard_range order).  Returns
+    (all_sizes int64[n_total], global_offsets int64[n_total + 1]) as numpy arrays, or -- on_device=True -- as
+    tensors on `device` without a host synchronisation (a rank that only needs to know where its shard lands
+    reads two elements later).  Shards may differ in length by one, so sizes are padded to the longest shard
+    for the collective; equal shards (n_total divisible by the world size) skip the padding."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
+        if on_device:
+            ls = torch.as_tensor(np.asarray(local_sizes, dtype=np.int64) if not torch.is_tensor(local_sizes) else local_sizes,
+                                 device=device)
+            return ls, torch.cat([ls.new_zeros(1), torch.cumsum(ls, 0)])
         sizes = np.asarray(local_sizes, dtype=np.int64)
         return sizes, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     longest = (n_total + world - 1) // world
-    pad = torch.full((longest,), -1, dtype=torch.int64, device=device)
-    ls = torch.as_tensor(np.asarray(local_sizes, dtype=np.int64), device=device)
-    pad[:ls.numel()] = ls
+    ls = local_sizes if torch.is_tensor(local_sizes) else torch.as_tensor(np.asarray(local_sizes, dtype=np.int64), device=device)
+    ls = ls.to(device=device, dtype=torch.int64)
+    even = n_total % world == 0
+    if even:
+        pad = ls
+    else:
+        pad = torch.full((longest,), -1, dtype=torch.int64, device=device)
+        pad[:ls.numel()] = ls
     out = torch.empty(world * longest, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(out, pad, group=group)
+    if on_device:
+        if not even:
+            keep = torch.cat([torch.arange(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0], device=device)
+                              + r * longest for r in range(world)])
+            out = out[keep]
+        return out, torch.cat([out.new_zeros(1), torch.cumsum(out, 0)])
     out = out.cpu().numpy().reshape(world, longest)
     parts = []
     for r in range(world):
