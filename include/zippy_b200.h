@@ -121,11 +121,16 @@ int zb200_uncompress_sizes(zb200_ctx *ctx, const uint8_t *src_base, const uint64
 /* zippy.uncompress(src, dataFormat) per input (zippy.nim:100-165).  dst_offsets (n+1, in)
  * gives each output's slot; slot capacity is dst_offsets[i+1]-dst_offsets[i]; dst_lens[i]
  * receives the produced size.  A failing input sets statuses[i] and produces no output.
- * Members are independent and decoded in parallel; ONE member is a serial stream, except that
- * members of 512 KiB or more are first tried as parallel segments split at every byte-aligning
- * empty stored block 00 00 ff ff (this library's own multi-chunk output, zlib full-flush
- * streams), with the serial decode as the fallback -- results are identical either way.
- * With page-locked host buffers the copies in and out overlap the kernels (member groups). */
+ * Members are independent and decoded in parallel; ONE member is a serial stream (one 8-lane group, ~10 MB/s),
+ * so members of 512 KiB or more are first cut into parallel segments: at every byte-aligning empty stored
+ * block 00 00 ff ff when the stream has them (this library's own multi-chunk output, zlib full-flush streams),
+ * otherwise at dynamic-block starts found by testing every bit offset, each segment decoded with marker symbols
+ * for its unknown 32 KiB window and resolved afterwards (any gzip / zlib output).  The serial decode is the
+ * fallback for anything irregular -- results, including the error reported, are identical either way.
+ * Limits: on the serial path one member's output is at most 4 GiB - 33 KiB (32-bit positions inside a member);
+ * members decoded as segments have no such limit.
+ * With page-locked host buffers the copies in and out overlap the kernels (member groups); pageable buffers
+ * are staged through an internal pinned ring. */
 int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64_t *src_offsets, size_t n,
                            int data_format, uint8_t *dst_base, const uint64_t *dst_offsets,
                            uint64_t *dst_lens, int *statuses);
