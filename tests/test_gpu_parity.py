@@ -489,6 +489,49 @@ def test_foreign_members_decode_as_speculative_segments(z, o, corpus, monkeypatc
     ctx.close()
 
 
+def test_speculative_segments_reject_false_block_starts(z, o, corpus, monkeypatch):
+    """Adversarial input for the block search: the DATA is itself a deflate stream, carried in stored blocks (or
+    barely compressible), so every dynamic-block header of the inner stream is a plausible -- and false -- block
+    start of the outer stream.  The counting pass must notice (a segment does not end on the next boundary, or
+    fails to decode) and the member must come out right through the serial decode, with the oracle's verdict for
+    corrupted variants too."""
+    monkeypatch.setenv("ZB200_BIG_MEMBER_BYTES", "60000")
+    ctx = z.Context()
+    monkeypatch.delenv("ZB200_BIG_MEMBER_BYTES")
+    T = util.text_corpus(corpus)
+    inner = zlib.compress(T[:1500000], 6)            # ~600 KB of compressed bytes with ~40 dynamic-block headers
+    streams = {
+        "stored": o.compress(inner, 0, o.dfGzip),    # level 0: stored blocks only
+        "zlib6_of_compressed": zlib.compress(inner, 6),
+        "mixed": zlib.compress(T[:400000] + inner + T[400000:900000] + inner[:200000], 6),
+    }
+    c = zlib.compressobj(1, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)   # fixed-Huffman blocks only: nothing to find
+    streams["fixed_only"] = c.compress(T[:700000]) + c.flush()
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    tiny = b"".join(c.compress(T[i:i + 1500]) + c.flush(zlib.Z_FULL_FLUSH) for i in range(0, 300000, 1500)) + c.flush()
+    streams["many_tiny_blocks"] = tiny
+    want = {"stored": inner, "zlib6_of_compressed": inner, "mixed": T[:400000] + inner + T[400000:900000] + inner[:200000],
+            "fixed_only": T[:700000], "many_tiny_blocks": T[:300000]}
+    rng = random.Random(11)
+    for name, blob in streams.items():
+        base = np.frombuffer(blob, dtype=np.uint8)
+        offs = np.array([0, len(blob)], dtype=np.uint64)
+        out, do, lens, st = ctx.uncompress_batch(base, offs)
+        assert st[0] == 0 and out[int(do[0]):int(do[0]) + int(lens[0])].tobytes() == want[name], name
+        for _ in range(4):
+            bad = bytearray(blob)
+            pos = rng.randrange(12, len(bad) - 8)
+            bad[pos] ^= 1 << rng.randrange(8)
+            out, do, lens, st = ctx.uncompress_batch(np.frombuffer(bytes(bad), dtype=np.uint8), offs)
+            try:
+                ref = o.uncompress(bytes(bad))
+            except o.ZippyError as e:
+                assert st[0] == e.code, (name, pos, int(st[0]), e.code)
+                continue
+            assert st[0] == 0 and out[int(do[0]):int(do[0]) + int(lens[0])].tobytes() == ref, (name, pos)
+    ctx.close()
+
+
 def test_default_level_ratio_vs_reference(z, o, corpus):
     """BASELINE config 4: at level=Default the total compressed size on the urls.10K corpus must
     stay within 3 % of the reference's (oracle port, hash-chain level 6, deflate.nim:262-272)."""

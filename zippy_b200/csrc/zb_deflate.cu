@@ -1022,27 +1022,18 @@ __global__ void __launch_bounds__(LZ_THREADS)
         while (s) {
           const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
           s &= s - 1;
-          uint32_t v1, n1;
-          if ((im >> bit) & 1u) {
-            const uint32_t rec = wrec[mcnt++];
-            const uint32_t lc = rec & 31u, dc = (rec >> 10) & 31u;
-            const uint32_t e1 = codes[257 + lc], e2 = codes[288 + dc];
-            v1 = (e1 & 0xffffu) | (((rec >> 5) & 31u) << (e1 >> 16));
-            n1 = (e1 >> 16) + (uint32_t)zb_len_extra_bits((int)lc);
-            acc |= (uint64_t)v1 << accn;
-            accn += n1;
-            if (accn >= 32) {
-              rows[nw * 32 + lane] = (uint32_t)acc;
-              nw++;
-              acc >>= 32;
-              accn -= 32;
-            }
-            v1 = (e2 & 0xffffu) | ((rec >> 15) << (e2 >> 16));
-            n1 = (e2 >> 16) + (uint32_t)zb_dist_extra_bits((int)dc);
-          } else {
-            const uint32_t e = codes[wdata[bit]];
-            v1 = e & 0xffffu;
-            n1 = e >> 16;
+          // literal and match tokens share the first code (literal / length symbol): one lookup, one append,
+          // whatever mix of tokens the 32 lanes hold in this iteration; only the distance part is a branch
+          const bool is_m = (im >> bit) & 1u;
+          const uint32_t rec = is_m ? wrec[mcnt] : 0u;
+          mcnt += is_m ? 1u : 0u;
+          const uint32_t lc = rec & 31u;
+          const uint32_t sym = is_m ? 257u + lc : (uint32_t)wdata[bit];
+          const uint32_t e1 = codes[sym];
+          uint32_t v1 = e1 & 0xffffu, n1 = e1 >> 16;
+          if (is_m) {
+            v1 |= ((rec >> 5) & 31u) << n1;
+            n1 += (uint32_t)zb_len_extra_bits((int)lc);
           }
           acc |= (uint64_t)v1 << accn;
           accn += n1;
@@ -1051,6 +1042,18 @@ __global__ void __launch_bounds__(LZ_THREADS)
             nw++;
             acc >>= 32;
             accn -= 32;
+          }
+          if (is_m) {
+            const uint32_t dc = (rec >> 10) & 31u;
+            const uint32_t e2 = codes[288 + dc];
+            acc |= (uint64_t)((e2 & 0xffffu) | ((rec >> 15) << (e2 >> 16))) << accn;
+            accn += (e2 >> 16) + (uint32_t)zb_dist_extra_bits((int)dc);
+            if (accn >= 32) {
+              rows[nw * 32 + lane] = (uint32_t)acc;
+              nw++;
+              acc >>= 32;
+              accn -= 32;
+            }
           }
         }
         if (accn) rows[nw * 32 + lane] = (uint32_t)acc;
