@@ -1034,6 +1034,16 @@ __global__ void __launch_bounds__(LZ_THREADS)
           if (is_m) {
             v1 |= ((rec >> 5) & 31u) << n1;
             n1 += (uint32_t)zb_len_extra_bits((int)lc);
+          } else if (s) {
+            // two literals in a row leave as one append (<= 30 bits): the all-literal windows are the ones that
+            // set the iteration count of the warp
+            const uint32_t bit2 = (uint32_t)(__ffs((int)s) - 1);
+            if (!((im >> bit2) & 1u)) {
+              const uint32_t e = codes[wdata[bit2]];
+              v1 |= (e & 0xffffu) << n1;
+              n1 += e >> 16;
+              s &= s - 1;
+            }
           }
           acc |= (uint64_t)v1 << accn;
           accn += n1;
