@@ -21,7 +21,9 @@
 #define ZB_WINDOWS_PER_CHUNK (ZB_CHUNK_BYTES / ZB_WINDOW)   // 2048
 #define ZB_WINDOWS_PER_SUB (ZB_SUB_BYTES / ZB_WINDOW)       // 256
 #define ZB_MATCH_SLOTS 8          // a 32-byte window starts at most 8 matches (min length 4)
-#define ZB_RECS_PER_SUB (ZB_SUB_BYTES / 4)    // match records a sub-chunk can hold (matches are >= 4 bytes), dense
+#define ZB_RECS_PER_SUB (ZB_SUB_BYTES / 4)    // match records a sub-chunk can hold (matches are >= 4 bytes)
+#define ZB_REC_PIECE_BYTES 4096               // the records of each 4 KiB piece form one dense stream at recs[chunk][piece start / 4]
+#define ZB_REC_PIECE_WINDOWS (ZB_REC_PIECE_BYTES / ZB_WINDOW)
 #define ZB_RECS_PER_CHUNK (ZB_WARPS_PER_CHUNK * ZB_RECS_PER_SUB)
 
 #define ZB_NUM_LITLEN 286

@@ -86,6 +86,8 @@ struct ZbCrcTables {
                         // [0] = x^(8 * 65536) mod P: shifts by one whole chunk
   uint32_t quart_mul[4];  // [k] = x^(8 * 2048 * k) mod P: shifts a quarter of a sub-chunk (16 rows of 128 B)
   uint32_t ck_sub[8];     // [k] = x^(8 * 4096 * k) mod P: shifts a warp's 4 KiB of a checksum piece to the piece end
+  uint32_t piece_mul[16]; // [k] = x^(8 * 4096 * k) mod P: shifts the CRC of one of k_lz's 4 KiB pieces to the chunk end
+  uint32_t pq_mul[4];     // [k] = x^(8 * 1024 * k) mod P: joins the four 1 KiB chains of such a piece
   uint32_t ck_quart[3][4][256];  // multiply-by-constant tables: [k-1][j][b] = (b << 8j) * x^(8 * 1024 * k), k = 1..3:
                                  // joins the four 1 KiB chains of the checksum kernel's 4 KiB warp pieces with lookups
 };
@@ -99,6 +101,8 @@ inline void zb_crc_build_tables(ZbCrcTables *t) {
   t->sub_mul[0] = zb_xpow8((uint64_t)ZB_CHUNK_BYTES);
   for (int k = 0; k < 4; k++) t->quart_mul[k] = zb_xpow8((uint64_t)(ZB_SUB_BYTES / 4) * (uint64_t)k);
   for (int k = 0; k < 8; k++) t->ck_sub[k] = zb_xpow8(4096ull * (uint64_t)k);
+  for (int k = 0; k < 16; k++) t->piece_mul[k] = zb_xpow8(4096ull * (uint64_t)k);
+  for (int k = 0; k < 4; k++) t->pq_mul[k] = zb_xpow8(1024ull * (uint64_t)k);
   for (int k = 1; k <= 3; k++) {
     const uint32_t c = zb_xpow8(1024ull * (uint64_t)k);
     for (int j = 0; j < 4; j++)

@@ -24,26 +24,43 @@
 #endif
 #define LZ_LANE_CAP 32  // bytes a lane extends on its own; a selected match that hit the cap finishes warp-cooperatively
 
+// k_lz walks the chunk in LZ_PHASES phases of 32 KiB: in each phase a warp parses one 4 KiB PIECE with a fresh
+// hash table (pre-seeded with the 2 KiB before the piece), so only half the chunk sits in shared memory at a time
+// and three CTAs (24 warps) fit on an SM instead of two.  (A full 64 KiB stage + one 8 KiB piece per warp was
+// 112 KiB per CTA: 16 warps per SM, 58 % issue-active on latency.  tools/lzsim.c prices the shorter pieces at
+// +0.3 % of compressed size.)
+#define LZ_PIECE_BYTES ZB_REC_PIECE_BYTES
+#define LZ_PHASES (ZB_SUB_BYTES / LZ_PIECE_BYTES)
+#define LZ_PHASE_BYTES (ZB_CHUNK_BYTES / LZ_PHASES)
+#define LZ_PHASE_HIST 1024  // bytes of the previous phase staged again in front: the pre-seed of the phase's first piece
+#define LZ_BATCH_LPW 2      // lanes per window in the batch pass
+#define LZ_BATCH_WINDOWS (32 / LZ_BATCH_LPW)
+static_assert(LZ_PIECE_BYTES * ZB_WARPS_PER_CHUNK == LZ_PHASE_BYTES, "one piece per warp and phase");
+static_assert(LZ_PIECE_BYTES / ZB_WINDOW % LZ_BATCH_WINDOWS == 0, "a batch of windows never straddles two pieces");
+
 // shared-memory layout of k_lz (bytes).  The CRC step table (4 KiB) is loaded by each warp
-// into its own hash-table region for the checksum phase and overwritten afterwards.
+// into its own hash-table region for the checksum of a piece and overwritten afterwards.
 #define LZ_SM_DATA 0
-// + 384: match extension reads up to 296 bytes past a sub-chunk's end before clamping the length;
+// + 384: match extension reads up to 296 bytes past a piece's end before clamping the length;
 // keep those reads inside the data region (they would otherwise race with another warp's table)
-#define LZ_SM_DATA_BYTES (ZB_CHUNK_BYTES + 64 + 384)
+#define LZ_SM_DATA_BYTES (LZ_PHASE_BYTES + LZ_PHASE_HIST + 64 + 384)
 #define LZ_SM_TABLE (LZ_SM_DATA + LZ_SM_DATA_BYTES)
 #define LZ_SM_TABLE_BYTES (ZB_WARPS_PER_CHUNK * LZ_TABLE_ENTRIES * 2)
 #define LZ_SM_HIST (LZ_SM_TABLE + LZ_SM_TABLE_BYTES)
 #define LZ_SM_HIST_BYTES (ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS * 4)
 #define LZ_SM_RING (LZ_SM_HIST + LZ_SM_HIST_BYTES)
-#define LZ_SM_RING_BYTES (ZB_WARPS_PER_CHUNK * 32 * ZB_MATCH_SLOTS * 4)
+#define LZ_SM_RING_BYTES (ZB_WARPS_PER_CHUNK * LZ_BATCH_WINDOWS * ZB_MATCH_SLOTS * 4)
 #define LZ_SM_LMUL (LZ_SM_RING + LZ_SM_RING_BYTES)
-#define LZ_SM_LMUL_BYTES (48 * 4)
+#define LZ_LMUL_PIECE 33    // lane_mul[33 + k] = x^(8 * 4096 * k), k = 0..15
+#define LZ_LMUL_PQ 49       // lane_mul[49 + k] = x^(8 * 1024 * k), k = 0..3
+#define LZ_SM_LMUL_BYTES (56 * 4)
 #define LZ_SM_PART (LZ_SM_LMUL + LZ_SM_LMUL_BYTES)
 #define LZ_SM_PART_BYTES (ZB_WARPS_PER_CHUNK * 24)
 #define LZ_SM_BAR (LZ_SM_PART + LZ_SM_PART_BYTES)
 #define LZ_SM_TOTAL (LZ_SM_BAR + 16)
 static_assert(LZ_TABLE_ENTRIES * 2 >= 4096, "a warp's table region must hold the CRC step table");
-static_assert(2 * (LZ_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
+static_assert(3 * (LZ_SM_TOTAL + 1024) <= 233472, "three CTAs per SM");
+static_assert(LZ_SM_PART % 8 == 0 && LZ_SM_TABLE % 16 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t lz_hash(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
 // PTX shifts clamp (a shift by >= 32 gives 0), unlike C++ shifts
@@ -121,18 +138,22 @@ __device__ __forceinline__ void lz_select(const uint8_t *data, uint32_t off0, ui
   }
 }
 
-// One lane per window: publish the window's masks, turn its raw match records into the
-// packer's records and count every token in the sub-chunk histogram.  The records of a
-// sub-chunk form one DENSE stream in window order (grecs_sub[rec_base ...]): a warp prefix sum
-// of the windows' match counts places them, and the packer recomputes the same prefix from
-// the masks.  (Eight fixed slots per window made every record a 4-byte write into its own
-// 32-byte sector: 2.3x the algorithmic DRAM traffic.)
+// LPW lanes per window (lane l: window l % (32 / LPW), part l / (32 / LPW)): publish the window's masks, turn
+// its raw match records into the packer's records and count every token in the sub-chunk histogram.  The
+// records of a 4 KiB piece form one DENSE stream in window order (grecs_piece[rec_base ...]): a prefix sum
+// of the windows' match counts places them, and the packer recomputes the same prefix from the masks.
+// (Eight fixed slots per window made every record a 4-byte write into its own 32-byte sector: 2.3x the
+// algorithmic DRAM traffic.)  The parts of a window split its literals by position and its matches round-robin.
+template <int LPW>
 __device__ __forceinline__ void lz_batch_pass(const uint8_t *wdata, bool active, uint32_t ksel, uint32_t kism,
-                                              const uint32_t *ring_lane, uint32_t *whist, uint2 *gmask_w,
-                                              uint32_t *grecs_sub, uint32_t &rec_base) {
-  if (active) *gmask_w = make_uint2(ksel, kism);
+                                              const uint32_t *ring_win, uint32_t *whist, uint2 *gmask_w,
+                                              uint32_t *grecs_piece, uint32_t &rec_base) {
+  constexpr int NW = 32 / LPW;
+  const uint32_t part = (uint32_t)zb_lane() / NW, wi = (uint32_t)zb_lane() % NW;
+  if (active && part == 0) *gmask_w = make_uint2(ksel, kism);
   const uint32_t im = active ? kism : 0u;
-  uint32_t s = active ? (ksel & ~kism) : 0u;  // literal tokens
+  const uint32_t pm = (0xffffffffu >> (32 - 32 / LPW)) << (part * (32 / LPW));
+  uint32_t s = active ? (ksel & ~kism & pm) : 0u;  // this part's literal tokens
   while (s) {
     const uint32_t bit = (uint32_t)(__ffs((int)s) - 1);
     s &= s - 1;
@@ -142,14 +163,14 @@ __device__ __forceinline__ void lz_batch_pass(const uint8_t *wdata, bool active,
   const uint32_t nmatch = (uint32_t)__popc(im);
   uint32_t incl = nmatch;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(ZB_FULL, incl, o);
-    if (zb_lane() >= o) incl += t;
+  for (int o = 1; o < NW; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(ZB_FULL, incl, o, NW);
+    if (wi >= (uint32_t)o) incl += t;
   }
-  uint32_t *grecs_w = grecs_sub + rec_base + incl - nmatch;
-  rec_base += __shfl_sync(ZB_FULL, incl, 31);
-  for (uint32_t k = 0; k < nmatch; k++) {
-    const uint32_t raw = ring_lane[k];
+  uint32_t *grecs_w = grecs_piece + rec_base + incl - nmatch;
+  rec_base += __shfl_sync(ZB_FULL, incl, NW - 1);
+  for (uint32_t k = part; k < nmatch; k += LPW) {
+    const uint32_t raw = ring_win[k];
     int lc, dc;
     const uint32_t fin = lz_final_rec((raw & 511u) + 3u, (raw >> 9) + 1u, lc, dc);
     grecs_w[k] = fin;
@@ -160,7 +181,7 @@ __device__ __forceinline__ void lz_batch_pass(const uint8_t *wdata, bool active,
 }
 
 template <int MODE>  // 1: single-probe hash matcher (level 1); 0: literals only (levels 0, -2)
-__global__ void __launch_bounds__(LZ_THREADS, 2)
+__global__ void __launch_bounds__(LZ_THREADS, 3)
     k_lz(const uint8_t *__restrict__ src, const ZbChunkDesc *__restrict__ desc, uint2 *__restrict__ masks,
          uint32_t *__restrict__ recs, uint16_t *__restrict__ hist, ZbChunkCheck *__restrict__ chk,
          const ZbCrcTables *__restrict__ tabs) {
@@ -184,83 +205,95 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
   }
   __syncthreads();
   const uint32_t mis = (uint32_t)((uintptr_t)(src + d.src_off) & 15u);
-  if (tid == 0 && len) zb_stage_chunk(data, src + d.src_off, len, bar);
 
   uint16_t *table = table_all + warp * LZ_TABLE_ENTRIES;
-  uint32_t *whist = hist_all + warp * ZB_HIST_WORDS;
-  uint32_t *ring = ring_all + warp * 32 * ZB_MATCH_SLOTS;
-  // while the bulk copy is in flight: clear histograms, load the CRC tables
-  for (int i = tid; i < ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS; i += LZ_THREADS) hist_all[i] = 0;
-  {
-    uint32_t *crc_tab = reinterpret_cast<uint32_t *>(table);
-    for (int i = lane; i < 1024; i += 32) crc_tab[i] = (&tabs->mul1024[0][0])[i];
-  }
-  if (tid < 33) lane_mul[tid] = tabs->lane_mul[tid];
-  if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = tabs->sub_mul[tid - 64];
-  if (tid >= 96 && tid < 100) lane_mul[41 + tid - 96] = tabs->quart_mul[tid - 96];
-  __syncthreads();
-  if (len) zb_mbar_wait(bar, 0);
+  uint32_t *ring = ring_all + warp * LZ_BATCH_WINDOWS * ZB_MATCH_SLOTS;
+  uint2 *gmask = masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
+  // checksums of this warp's pieces, each already shifted to the end of the chunk (uniform across the warp)
+  uint32_t acc_crc = 0;
+  uint64_t acc_a = 0, acc_b = 0;
 
-  const uint32_t b0 = (uint32_t)warp * ZB_SUB_BYTES;
-  const uint32_t b1 = min(b0 + ZB_SUB_BYTES, len);
+  for (uint32_t ph = 0; ph < LZ_PHASES; ph++) {
+    const uint32_t pbase = ph * LZ_PHASE_BYTES;               // first byte parsed in this phase
+    if (ph && pbase >= len) break;
+    const uint32_t sbase = ph ? pbase - LZ_PHASE_HIST : 0u;   // first byte staged (a multiple of 16: same misalignment)
+    if (ph) __syncthreads();                                  // every warp is done with the previous phase's bytes
+    if (tid == 0 && len) {
+      zb_fence_proxy_async();
+      zb_stage_chunk(data, src + d.src_off + sbase, min(len, pbase + LZ_PHASE_BYTES + 384u) - sbase, bar);
+    }
+    // while the bulk copy is in flight: clear histograms (once), load the CRC tables
+    {
+      uint32_t *crc_tab = reinterpret_cast<uint32_t *>(table);
+      for (int i = lane; i < 1024; i += 32) crc_tab[i] = (&tabs->mul1024[0][0])[i];
+    }
+    if (ph == 0) {
+      for (int i = tid; i < ZB_WARPS_PER_CHUNK * ZB_HIST_WORDS; i += LZ_THREADS) hist_all[i] = 0;
+      if (tid < 33) lane_mul[tid] = tabs->lane_mul[tid];
+      if (tid >= 64 && tid < 80) lane_mul[LZ_LMUL_PIECE + tid - 64] = tabs->piece_mul[tid - 64];
+      if (tid >= 96 && tid < 100) lane_mul[LZ_LMUL_PQ + tid - 96] = tabs->pq_mul[tid - 96];
+      __syncthreads();
+    } else {
+      __syncwarp();
+    }
+    if (len) zb_mbar_wait(bar, ph & 1u);
 
-  // ---- checksums of this warp's piece, already shifted to the end of the chunk ----
-  {
-    ZbCheck c;
-    c.crc_raw = 0;
-    c.a_sum = c.b_sum = 0;
-    uint32_t n = b0 < len ? b1 - b0 : 0;
-    if (n) {
-      c = zb_warp_checksums(data, mis + b0, n, reinterpret_cast<const uint32_t *>(table), lane_mul);
+    const uint32_t b0 = pbase + (uint32_t)warp * LZ_PIECE_BYTES;
+    if (b0 >= len) continue;
+    const uint32_t b1 = min(b0 + LZ_PIECE_BYTES, len);
+    const uint32_t doff = mis - sbase;  // chunk position x lives at data[doff + x] (modular: x >= sbase)
+    // histograms stay per 8 KiB sub-chunk (k_huff derives the packer warps' bit ranges from them): the two warps
+    // whose pieces make up a sub-chunk count into the same one
+    uint32_t *whist = hist_all + (b0 / ZB_SUB_BYTES) * ZB_HIST_WORDS;
+
+    // ---- checksums of this piece, shifted to the end of the chunk ----
+    {
+      ZbCheck c = zb_warp_checksums<LZ_PIECE_BYTES, LZ_LMUL_PQ>(data, doff + b0, b1 - b0,
+                                                                reinterpret_cast<const uint32_t *>(table), lane_mul);
       const uint32_t after = len - b1;
       if (after) {
-        const uint32_t shift = ((after & (ZB_SUB_BYTES - 1)) == 0) ? lane_mul[33 + after / ZB_SUB_BYTES] : zb_xpow8(after);
+        const uint32_t shift =
+            ((after & (LZ_PIECE_BYTES - 1)) == 0) ? lane_mul[LZ_LMUL_PIECE + after / LZ_PIECE_BYTES] : zb_xpow8(after);
         c.crc_raw = zb_gf2_mul(c.crc_raw, shift);
         c.b_sum += (uint64_t)after * c.a_sum;
       }
+      acc_crc ^= c.crc_raw;
+      acc_a += c.a_sum;
+      acc_b += c.b_sum;
+      __syncwarp();
     }
-    if (lane == 0) {
-      part[warp * 3 + 0] = c.crc_raw;
-      part[warp * 3 + 1] = c.a_sum;
-      part[warp * 3 + 2] = c.b_sum;
-    }
-    __syncwarp();
-  }
 
-  if (b0 < len) {
     if (MODE == 1) {
       // the table region held the CRC step table until now: empty it
       uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u);
       uint4 *t4 = reinterpret_cast<uint4 *>(table);
       for (int i = lane; i < LZ_TABLE_ENTRIES * 2 / 16; i += 32) t4[i] = ff;
       __syncwarp();
-      if (warp > 0) {
-        // pre-seed the private table with the positions just before this sub-chunk
-        for (uint32_t s = b0 - LZ_PRESEED; s < b0; s += 32) {
-          const uint32_t p = s + (uint32_t)lane;
-          const bool can = p + 4 <= len;
-          const uint32_t h = lz_hash(zb_ld32_unaligned(data, mis + p));
-          if (can) table[h] = (uint16_t)p;
+      // pre-seed the private table with the positions just before this piece (what of them is staged)
+      for (uint32_t s = b0 - min((uint32_t)LZ_PRESEED, b0 - sbase); s < b0; s += 32) {
+        const uint32_t p = s + (uint32_t)lane;
+        const bool can = p + 4 <= len;
+        const uint32_t h = lz_hash(zb_ld32_unaligned(data, doff + p));
+        if (can) table[h] = (uint16_t)p;
 #if ZB_LZ1_RESOLVE_WINNER
-          __syncwarp();
-          for (;;) {  // same-entry stores of one instruction: the highest position wins (see the main loop)
-            const bool lost = can && table[h] < (uint16_t)p;
-            if (!__any_sync(ZB_FULL, lost)) break;
-            if (lost) table[h] = (uint16_t)p;
-            __syncwarp();
-          }
-#endif
-        }
         __syncwarp();
+        for (;;) {  // same-entry stores of one instruction: the highest position wins (see the main loop)
+          const bool lost = can && table[h] < (uint16_t)p;
+          if (!__any_sync(ZB_FULL, lost)) break;
+          if (lost) table[h] = (uint16_t)p;
+          __syncwarp();
+        }
+#endif
       }
+      __syncwarp();
     }
     uint32_t entry = b0;
-    uint32_t ksel = 0, kism = 0;  // lane i keeps the masks of window i of the current batch of 32
-    uint2 *gmask = masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
-    uint32_t *grecs = recs + (size_t)chunk * ZB_RECS_PER_CHUNK + (size_t)warp * ZB_RECS_PER_SUB;
+    uint32_t ksel = 0, kism = 0;  // lanes i and i + 16 keep the masks of window i of the current batch of 16
+    uint32_t *grecs = recs + (size_t)chunk * ZB_RECS_PER_CHUNK + (b0 >> 2);  // this piece's record stream
     uint32_t rec_base = 0;
+    const uint32_t bl = (uint32_t)lane & (LZ_BATCH_WINDOWS - 1u);
     for (uint32_t wb = b0; wb < b1; wb += 32) {
-      const uint32_t win = wb >> 5, slot = win & 31u;
+      const uint32_t win = wb >> 5, slot = win & (LZ_BATCH_WINDOWS - 1u);
       uint32_t sel = 0, ism = 0;
       if (entry < wb + 32) {
         const uint32_t p = wb + (uint32_t)lane;
@@ -268,7 +301,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
         const uint32_t cur = entry - wb;
         uint32_t m = 0, c = 0;
         if (MODE == 1) {
-          const uint32_t v = zb_ld32_unaligned(data, mis + p);
+          const uint32_t v = zb_ld32_unaligned(data, doff + p);
           const bool can = (p + 4 <= len);
           const uint32_t h = lz_hash(v);
           c = table[h];
@@ -290,13 +323,13 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
             __syncwarp();
           }
 #endif
-          // a match may not cross the sub-chunk end (the next warp starts its own parse there)
+          // a match may not cross the piece end (another warp starts its own parse there)
           const uint32_t limit = p < b1 ? min((uint32_t)ZB_MAX_MATCH, b1 - p) : 0u;
           if (can && c < p && p - c <= ZB_MAX_DIST && p >= entry && limit >= ZB_MIN_MATCH) {
             // unaligned compare, 4 bytes per step, carrying the upper word of each side
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(data) + ((mis + p) >> 2);
-            const uint32_t *wc = reinterpret_cast<const uint32_t *>(data) + ((mis + c) >> 2);
-            const uint32_t sp = ((mis + p) & 3u) * 8u, sc = ((mis + c) & 3u) * 8u;
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(data) + ((doff + p) >> 2);
+            const uint32_t *wc = reinterpret_cast<const uint32_t *>(data) + ((doff + c) >> 2);
+            const uint32_t sp = ((doff + p) & 3u) * 8u, sc = ((doff + c) & 3u) * 8u;
             uint32_t hp = wp[1], hc = wc[1];
             if (__funnelshift_r(wc[0], hc, sc) == v) {
               m = 4;
@@ -317,23 +350,28 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           }
         }
         uint32_t endw;
-        lz_select(data, mis, wb, b1, cur, nvalid, m, p - c, ring + slot * ZB_MATCH_SLOTS, sel, ism, endw);
+        lz_select(data, doff, wb, b1, cur, nvalid, m, p - c, ring + slot * ZB_MATCH_SLOTS, sel, ism, endw);
         entry = wb + max(endw, nvalid);
       }
-      if ((uint32_t)lane == slot) {
+      if (bl == slot) {
         ksel = sel;
         kism = ism;
       }
-      // ---- every 32 windows (or at the end): one lane per window walks its tokens ----
-      if (slot == 31u || wb + 32 >= b1) {
+      // ---- every 16 windows (or at the end): two lanes per window walk its tokens ----
+      if (slot == LZ_BATCH_WINDOWS - 1u || wb + 32 >= b1) {
         __syncwarp();
-        const uint32_t bwin = win - slot + (uint32_t)lane;  // this lane's window
-        lz_batch_pass(data + mis + (bwin << 5), (uint32_t)lane <= slot, ksel, kism, ring + (uint32_t)lane * ZB_MATCH_SLOTS,
-                      whist, gmask + bwin, grecs, rec_base);
+        const uint32_t bwin = win - slot + bl;  // this lane's window
+        lz_batch_pass<LZ_BATCH_LPW>(data + (uint32_t)(doff + (bwin << 5)), bl <= slot, ksel, kism, ring + bl * ZB_MATCH_SLOTS,
+                                    whist, gmask + bwin, grecs, rec_base);
         ksel = kism = 0;
         __syncwarp();
       }
     }
+  }
+  if (lane == 0) {
+    part[warp * 3 + 0] = acc_crc;
+    part[warp * 3 + 1] = acc_a;
+    part[warp * 3 + 2] = acc_b;
   }
   __syncthreads();
   // ---- publish histograms (packed u16 pairs == the global u16 layout) and chunk checksums ----
@@ -605,10 +643,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
       uint32_t entry = b0;
       uint32_t ksel = 0, kism = 0;
       uint2 *gmask = masks + (size_t)chunk * ZB_WINDOWS_PER_CHUNK;
-      uint32_t *grecs = recs + (size_t)chunk * ZB_RECS_PER_CHUNK + (size_t)warp * ZB_RECS_PER_SUB;
+      uint32_t *grecs = recs + (size_t)chunk * ZB_RECS_PER_CHUNK;
       uint32_t rec_base = 0;
       for (uint32_t wb = b0; wb < b1; wb += 32) {
         const uint32_t win = wb >> 5, slot = win & (LZ2_RING_WINDOWS - 1u);
+        if ((wb & (ZB_REC_PIECE_BYTES - 1u)) == 0u) rec_base = 0;  // a new 4 KiB piece: its own dense record stream
         const uint32_t p = wb + (uint32_t)lane;
         const uint32_t q = hb + p;               // region position of this lane
         const uint32_t v = zb_ld32_unaligned(data, off0 + p);
@@ -669,16 +708,17 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
           lz_select(data, off0, wb, b1, cur, nvalid, m, dist, ring + slot * ZB_MATCH_SLOTS, sel, ism, endw);
           entry = wb + max(endw, nvalid);
         }
-        if ((uint32_t)lane == slot) {
+        const uint32_t bl = (uint32_t)lane & (LZ2_RING_WINDOWS - 1u);
+        if (bl == slot) {
           ksel = sel;
           kism = ism;
         }
         if (slot == LZ2_RING_WINDOWS - 1u || wb + 32 >= b1) {
           __syncwarp();
-          const uint32_t bwin = win - slot + (uint32_t)lane;
-          lz_batch_pass(data + off0 + (bwin << 5), (uint32_t)lane <= slot, ksel, kism,
-                        ring + ((uint32_t)lane & (LZ2_RING_WINDOWS - 1u)) * ZB_MATCH_SLOTS, whist, gmask + bwin,
-                        grecs, rec_base);
+          const uint32_t bwin = win - slot + bl;  // four lanes per window
+          lz_batch_pass<32 / LZ2_RING_WINDOWS>(data + off0 + (bwin << 5), bl <= slot, ksel, kism, ring + bl * ZB_MATCH_SLOTS,
+                                               whist, gmask + bwin,
+                                               grecs + ((wb & ~(uint32_t)(ZB_REC_PIECE_BYTES - 1u)) >> 2), rec_base);
           ksel = kism = 0;
           __syncwarp();
         }
@@ -1000,6 +1040,10 @@ __global__ void __launch_bounds__(LZ_THREADS)
       const uint32_t nwin = (b1 - b0 + 31u) >> 5;
       uint32_t rec_base = 0;
       for (uint32_t wbase = 0; wbase < nwin; wbase += 32) {
+        if (wbase && (wbase & (ZB_REC_PIECE_WINDOWS - 1u)) == 0u) {  // the next 4 KiB piece: its own dense record stream
+          grecs += ZB_REC_PIECE_BYTES / 4;
+          rec_base = 0;
+        }
         const uint32_t widx = wbase + (uint32_t)lane;      // window within the sub-chunk
         const uint32_t win = (b0 >> 5) + widx;              // window within the chunk
         uint2 mk = make_uint2(0u, 0u);
@@ -1139,6 +1183,9 @@ size_t zb_lz2_table_bytes(int *grid_out) {
 cudaError_t zb_setup_deflate_attrs() {
   cudaError_t e = cudaFuncSetAttribute(k_lz<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_TOTAL);
+  // three CTAs of 75 KiB: ask for the largest shared-memory carve-out
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz2, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ2_SM_TOTAL);
   return e;
 }

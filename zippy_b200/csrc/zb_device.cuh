@@ -20,6 +20,8 @@ __device__ __forceinline__ int zb_lane() { return (int)(threadIdx.x & 31u); }
 __device__ __forceinline__ void zb_mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zb_smem_addr(bar)), "r"(count) : "memory");
 }
+// orders this thread's earlier generic-proxy accesses of shared memory before its later async-proxy (bulk copy) ones
+__device__ __forceinline__ void zb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void zb_fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -107,19 +109,21 @@ struct ZbCheck {
   uint32_t crc_raw;
   uint64_t a_sum, b_sum;
 };
+// FULL = the piece size with the fast path, QOFF = where its quarter shifts x^(8 * FULL/4 * k), k = 0..3, sit in lane_mul.
+template <uint32_t FULL = ZB_SUB_BYTES, int QOFF = 41>
 __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32_t off, uint32_t n,
                                                      const uint32_t *tab, const uint32_t *lane_mul, uint32_t ts = 1u) {
   const int lane = zb_lane();
   if (ts != 1u) tab += lane;
-  if (n == (uint32_t)ZB_SUB_BYTES && ts == 1u) {
-    // Full 8 KiB piece (the common case): four independent Horner chains of 16 rows each, so the
+  if (n == FULL && ts == 1u) {
+    // Full piece (the common case): four independent Horner chains of FULL/512 rows each, so the
     // table-lookup latency of one chain hides behind the other three; they are joined with the
-    // quarter shifts lane_mul[41 + k] = x^(8 * 2048 * k).
+    // quarter shifts lane_mul[QOFF + k] = x^(8 * FULL/4 * k).
     uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, a = 0;
     uint64_t b = 0;
     const uint32_t o = off + 4u * (uint32_t)lane, rel0 = 4u * (uint32_t)lane;
-    constexpr uint32_t QR = ZB_SUB_BYTES / 512;  // rows of 128 B per quarter
-    constexpr uint32_t QB = ZB_SUB_BYTES / 4;    // bytes per quarter
+    constexpr uint32_t QR = FULL / 512;  // rows of 128 B per quarter
+    constexpr uint32_t QB = FULL / 4;    // bytes per quarter
 #pragma unroll 2
     for (uint32_t k = 0; k < QR; k++) {
       const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (QR + k));
@@ -143,7 +147,7 @@ __device__ __forceinline__ ZbCheck zb_warp_checksums(const uint8_t *base, uint32
       b -= (uint64_t)(__dp4a(w0, 0x03020100u, 0u) + __dp4a(w1, 0x03020100u, 0u) + __dp4a(w2, 0x03020100u, 0u) +
                       __dp4a(w3, 0x03020100u, 0u));
     }
-    uint32_t r = zb_gf2_mul(r0, lane_mul[41 + 3]) ^ zb_gf2_mul(r1, lane_mul[41 + 2]) ^ zb_gf2_mul(r2, lane_mul[41 + 1]) ^ r3;
+    uint32_t r = zb_gf2_mul(r0, lane_mul[QOFF + 3]) ^ zb_gf2_mul(r1, lane_mul[QOFF + 2]) ^ zb_gf2_mul(r2, lane_mul[QOFF + 1]) ^ r3;
     r = zb_gf2_mul(r, lane_mul[32 - lane]);
     ZbCheck out;
     out.crc_raw = zb_warp_xor(r);
