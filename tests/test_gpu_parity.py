@@ -332,12 +332,17 @@ def test_launch_groups_and_tight_capacity(z, o, corpus, monkeypatch):
     ctx.close()
 
 
-def test_host_uncompress_member_groups(z, o, corpus, monkeypatch):
+@pytest.mark.parametrize("gated", ["1", "0"])
+def test_host_uncompress_member_groups(z, o, corpus, monkeypatch, gated):
     """The host-buffer uncompress runs member groups through a copy-in / inflate / copy-out
-    pipeline; force tiny groups (many groups, groups of one oversized member, empty members)."""
+    pipeline; force tiny groups (many groups, groups of one oversized member, empty members).
+    gated=1: one inflate launch walks the whole batch behind the copy-in and the copy-out stream waits
+    on per-group done counts; gated=0: one launch per group."""
     monkeypatch.setenv("ZB200_UNC_GROUP_BYTES", "150000")
+    monkeypatch.setenv("ZB200_UNC_GATED", gated)
     ctx = z.Context()
     monkeypatch.delenv("ZB200_UNC_GROUP_BYTES")
+    monkeypatch.delenv("ZB200_UNC_GATED")
     rng = random.Random(5)
     raws = [corpus["alice29.txt"], b"", corpus["html"], corpus["urls.10K"], b"q" * 300000, corpus["geo.protodata"],
             bytes(rng.randrange(256) for _ in range(100000)), b"abc", corpus["lcet10.txt"], b""]

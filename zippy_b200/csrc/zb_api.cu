@@ -2,6 +2,7 @@
 // staging and the launch sequences.  No codec logic lives here and nothing here falls
 // back to the CPU: every data byte is produced by the kernels in zb_deflate.cu /
 // zb_inflate.cu.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <execinfo.h>
 #include <signal.h>
@@ -29,6 +30,29 @@ struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
 };
+
+// Stream memory operations (driver API, fetched at run time: the library links the runtime only).  A wait on a
+// device word lets the D2H stream follow the progress of ONE persistent inflate launch, group by group.
+struct StreamMemOps {
+  CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  bool ok = false;
+};
+StreamMemOps load_stream_memops() {
+  StreamMemOps m;
+  void *f1 = nullptr, *f2 = nullptr;
+  cudaDriverEntryPointQueryResult q1, q2;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f1, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+      cudaGetDriverEntryPoint("cuStreamWriteValue32", &f2, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess &&
+      f1 && f2) {
+    m.wait32 = reinterpret_cast<decltype(m.wait32)>(f1);
+    m.write32 = reinterpret_cast<decltype(m.write32)>(f2);
+    m.ok = true;
+  } else {
+    (void)cudaGetLastError();
+  }
+  return m;
+}
 
 constexpr size_t kMaxChunksPerGroup = 32768;  // device-resident batches: 2 GiB of input per launch group
 constexpr size_t kHostGroupChunks = 4096;     // host batches: 256 MiB groups so transfers overlap the kernels
@@ -137,6 +161,9 @@ struct zb200_ctx {
   DevBuf seg_src, seg_dst, seg_len, seg_status, seg_kind, seg_expect, seg_cand, skip_mask;  // large-member segments
   DevBuf mark_scratch, mark_segs, seg_bits;  // speculative segments of a large member (uint16 symbols, descriptors)
   DevBuf order;             // work-queue order of an inflate launch (longest members first)
+  DevBuf gate;              // gated inflate launch: [0] groups copied in, [1 .. ng] members done per group, then the group starts
+  StreamMemOps memops;      // stream wait / write on device words (null: group-by-group launches instead)
+  bool gated_unc = true;    // env ZB200_UNC_GATED=0 forces the group-by-group launches
   StageRing ring_in, ring_out;   // pinned slots for pageable callers (allocated on first use)
   CopyPool pool;
   uint64_t pending_len = 0;     // zb200_decode_begin's result, waiting in out_stage for zb200_decode_finish
@@ -1125,6 +1152,9 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
                               int data_format, uint8_t *h_dst, const std::vector<uint64_t> &dreb, uint64_t *dst_lens,
                               int *statuses, const std::vector<size_t> &gb) {
   const size_t ng = gb.size() - 1;
+  // gated: ONE inflate launch walks the whole batch behind the copy-in (no per-group launch tails), the D2H
+  // stream waits on the per-group done counts; otherwise one launch per group, chained with events
+  const bool gated = ctx->memops.ok && ctx->gated_unc && n < 0xffffffffull;
   cudaStream_t s = ctx->stream, sh = ctx->h2d_stream, sd = ctx->d2h_stream;
   const uint8_t *d_src = (const uint8_t *)ctx->in_stage.p;
   uint8_t *d_dst = (uint8_t *)ctx->out_stage.p;
@@ -1139,23 +1169,27 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
     piece0[gi] = pieces.size();
     first0[gi] = first.size();
     for (size_t i = m0; i < m1; i++) {
-      first.push_back((uint32_t)(pieces.size() - piece0[gi]));
+      first.push_back((uint32_t)(pieces.size() - (gated ? 0 : piece0[gi])));
       const uint64_t cap = dreb[i + 1] - dreb[i];
       uint64_t rel = 0;
       do {
         ZbPiece pc;
         pc.rel = rel;
-        pc.buf = (uint32_t)(i - m0);
+        pc.buf = (uint32_t)(i - (gated ? 0 : m0));
         pc.pad = 0;
         pieces.push_back(pc);
         rel += ZB_CK_PIECE_BYTES;
       } while (rel < cap);
     }
-    first.push_back((uint32_t)(pieces.size() - piece0[gi]));
+    if (!gated || gi + 1 == ng) first.push_back((uint32_t)(pieces.size() - (gated ? 0 : piece0[gi])));
     std::vector<uint32_t> o;
     if (longest_first_order(reb.data() + m0, m1 - m0, o)) {
       has_order[gi] = 1;
       std::copy(o.begin(), o.end(), order.begin() + m0);
+      if (gated)
+        for (size_t i = m0; i < m1; i++) order[i] += (uint32_t)m0;
+    } else if (gated) {
+      for (size_t i = m0; i < m1; i++) order[i] = (uint32_t)i;
     }
   }
   piece0[ng] = pieces.size();
@@ -1191,7 +1225,93 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
   CK(cudaEventRecord(ctx->ev[8], sd));
   const bool src_pageable = is_pageable(h_src), dst_pageable = h_dst && is_pageable(h_dst);
   CK(cudaEventRecord(ctx->ev[0], s));
-  for (size_t gi = 0; gi < ng; gi++) {
+  if (gated) {
+    // nothing that may synchronise the device (allocations, registrations) can happen while the gated kernel waits
+    // for input: the staging rings of pageable callers are set up first
+    if (src_pageable) {
+      int rc = ring_ready(ctx, ctx->ring_in);
+      if (rc) return rc;
+    }
+    if (dst_pageable) {
+      int rc = ring_ready(ctx, ctx->ring_out);
+      if (rc) return rc;
+    }
+    // gate words: [0] = groups copied in, [1 + g] = members of group g done, [1 + ng + g] = first queue position of group g
+    std::vector<uint32_t> gate(2 * ng + 2, 0u);
+    for (size_t gi = 0; gi <= ng; gi++) gate[1 + ng + gi] = (uint32_t)gb[gi];
+    ENSURE(ctx->gate, gate.size() * sizeof(uint32_t));
+    uint32_t *d_gate = (uint32_t *)ctx->gate.p;
+    CK(cudaMemcpyAsync(d_gate, gate.data(), gate.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // `gate` is pageable: the copy has read it; and the zeroed words are in place before
+                                   // the H2D stream's first write of d_gate[0]
+    ZbInflateWork w;
+    memset(&w, 0, sizeof(w));
+    w.src = d_src;
+    w.src_off = (const uint64_t *)ctx->src_off.p;
+    w.dst = d_dst;
+    w.dst_off = (const uint64_t *)ctx->dst_off.p;
+    w.out_len = (uint64_t *)ctx->out_len.p;
+    w.status = (int *)ctx->status.p;
+    w.expect = (uint32_t *)ctx->expect.p;
+    w.kind = (uint32_t *)ctx->kind.p;
+    w.counter = (uint32_t *)ctx->counter.p + 16;
+    w.tabs = ctx->d_tabs;
+    w.n = (uint32_t)n;
+    w.data_format = data_format;
+    w.order = (const uint32_t *)ctx->order.p;
+    w.gate_ready = d_gate;
+    w.gate_done = d_gate + 1;
+    w.gate_first = d_gate + 1 + ng;
+    w.n_gates = (uint32_t)ng;
+    CK(zb_launch_inflate(w, s));
+    // gzip.nim:80-88 / zippy.nim:154-162: checksum, then size, of every member that inflated (after the whole
+    // launch: 2.4 ms per 4 GiB, under the last groups' copy-out)
+    ZbChecksumWork cw;
+    memset(&cw, 0, sizeof(cw));
+    cw.src = d_dst;
+    cw.off = w.dst_off;
+    cw.lens = w.out_len;
+    cw.pieces = (const ZbPiece *)ctx->ck_pieces.p;
+    cw.first = (const uint32_t *)ctx->ck_first.p;
+    cw.piece_out = (ZbChunkCheck *)ctx->ck_piece_out.p;
+    cw.status = w.status;
+    cw.expect = w.expect;
+    cw.kinds = w.kind;
+    cw.isize_src = d_src;
+    cw.isize_off = w.src_off;
+    cw.tabs = ctx->d_tabs;
+    cw.n = (uint32_t)n;
+    cw.n_pieces = (uint32_t)pieces.size();
+    CK(zb_launch_checksum(cw, s));
+    ctx->timing.kernel_launches += 3;
+    auto copy_in = [&](size_t gi) -> int {
+      const uint64_t b0 = reb[gb[gi]], b1 = reb[gb[gi + 1]];
+      int rc = h2d_copy(ctx, (uint8_t *)ctx->in_stage.p + b0, h_src + b0, (size_t)(b1 - b0), sh, src_pageable);
+      if (rc) return rc;
+      if (ctx->memops.write32((CUstream)sh, (CUdeviceptr)(uintptr_t)d_gate, (cuuint32_t)(gi + 1), 0) != CUDA_SUCCESS) return ZB200_ERR_CUDA;
+      if (gi + 1 == ng) CK(cudaEventRecord(ctx->ev[7], sh));
+      return ZB200_OK;
+    };
+    {
+      int rc = copy_in(0);
+      if (rc) return rc;
+    }
+    for (size_t gi = 0; gi < ng; gi++) {
+      if (gi + 1 < ng) {  // the next group's copy-in is queued before this thread may block on a pageable copy-out
+        int rc = copy_in(gi + 1);
+        if (rc) return rc;
+      }
+      const size_t m0 = gb[gi], m1 = gb[gi + 1];
+      const uint64_t o0 = dreb[m0], o1 = dreb[m1];
+      if (o1 > o0 && h_dst) {
+        if (ctx->memops.wait32((CUstream)sd, (CUdeviceptr)(uintptr_t)(d_gate + 1 + gi), (cuuint32_t)(m1 - m0), CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+          return ZB200_ERR_CUDA;
+        int rc = d2h_copy(ctx, h_dst + o0, d_dst + o0, (size_t)(o1 - o0), sd, dst_pageable);
+        if (rc) return rc;
+      }
+    }
+  }
+  for (size_t gi = 0; gi < ng && !gated; gi++) {
     const size_t m0 = gb[gi], m1 = gb[gi + 1], nm = m1 - m0;
     {
       const uint64_t b0 = reb[m0], b1 = reb[m1];
@@ -1391,6 +1511,8 @@ int zb200_init(int device, zb200_ctx **out) {
       ctx->big_env = true;
     }
   }
+  ctx->memops = load_stream_memops();
+  if (const char *e = getenv("ZB200_UNC_GATED")) ctx->gated_unc = atoi(e) != 0;  // test hook: 0 = one launch per group
   if (const char *e = getenv("ZB200_UNC_GROUP_BYTES")) {  // test hook: small pipelined groups in the host uncompress
     long long v = atoll(e);
     if (v > 0) ctx->unc_group_out_bytes = (uint64_t)v;
@@ -1430,7 +1552,7 @@ void zb200_shutdown(zb200_ctx *ctx) {
                     &ctx->cb, &ctx->chunk_off, &ctx->member_off, &ctx->member_check, &ctx->member_isize,
                     &ctx->src_off, &ctx->dst_off, &ctx->out_len, &ctx->status, &ctx->expect, &ctx->kind,
                     &ctx->counter, &ctx->ck_out, &ctx->ck_pieces, &ctx->ck_first, &ctx->ck_piece_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables,
-                    &ctx->seg_src, &ctx->seg_dst, &ctx->seg_len, &ctx->seg_status, &ctx->seg_kind, &ctx->seg_expect, &ctx->seg_cand, &ctx->skip_mask, &ctx->order, &ctx->mark_scratch, &ctx->mark_segs, &ctx->seg_bits};
+                    &ctx->seg_src, &ctx->seg_dst, &ctx->seg_len, &ctx->seg_status, &ctx->seg_kind, &ctx->seg_expect, &ctx->seg_cand, &ctx->skip_mask, &ctx->order, &ctx->mark_scratch, &ctx->mark_segs, &ctx->seg_bits, &ctx->gate};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_tabs) cudaFree(ctx->d_tabs);
@@ -1699,6 +1821,10 @@ int zb200_uncompress_batch(zb200_ctx *ctx, const uint8_t *src_base, const uint64
       uint64_t max_out = 0;
       for (size_t i = 0; i < n; i++) max_out = std::max<uint64_t>(max_out, dreb[i + 1] - dreb[i]);
       out_cap = std::max<uint64_t>(std::max<uint64_t>((hi - lo) / 8, 8192ull * max_out), 64ull << 20);
+      // one gated launch for the whole batch has no per-group tail: the groups only set the granularity of the
+      // overlap (what is exposed is the first group's copy-in and the last group's copy-out)
+      if (ctx->memops.ok && ctx->gated_unc)
+        out_cap = std::min<uint64_t>(std::max<uint64_t>((hi - lo) / 32, 32ull << 20), 256ull << 20);
     }
     const uint64_t in_cap = out_cap;
     size_t a = 0;

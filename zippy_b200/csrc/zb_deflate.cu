@@ -1187,6 +1187,12 @@ cudaError_t zb_setup_deflate_attrs() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lz2, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ2_SM_TOTAL);
+  // load the remaining kernels now rather than at their first launch (see zb_setup_inflate_attrs)
+  cudaFuncAttributes fa;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_huff);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_scan);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_member_check);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_pack);
   return e;
 }
 cudaError_t zb_launch_lz(const ZbCompressWork &w, cudaStream_t s) {

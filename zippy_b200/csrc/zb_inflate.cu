@@ -93,7 +93,8 @@ struct BitReader {
 };
 
 __device__ __forceinline__ uint32_t br_word(const BitReader &b, uint32_t idx) {
-  return idx < b.nwords ? __ldg(b.gbase + idx) : 0u;
+  return idx < b.nwords ? __ldcg(b.gbase + idx) : 0u;  // L2 only: every word is read once, and with a gated queue the
+                                                       // line may hold bytes of a member whose copy-in has not landed yet
 }
 __device__ __forceinline__ uint32_t br_load_line(const BitReader &b, uint32_t line) {
   return br_word(b, line * (uint32_t)INF_G + (uint32_t)g_lane());
@@ -430,6 +431,25 @@ __device__ __forceinline__ int flush_tokens(OutT *out, uint32_t &op, uint32_t ca
 
 // ---- per-group decoder state (identical in every lane of the group) ----
 enum { ST_FETCH = 0, ST_BLOCK = 1, ST_SYMS = 2, ST_EXIT = 3 };
+// ---- gated queue (ZbInflateWork::gate_*) ----
+__device__ __forceinline__ uint32_t gate_load(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t gate_clock() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// every lane of the group calls this after the member's last output store
+__device__ __forceinline__ void gate_member_done(const ZbInflateWork &w, uint32_t gate) {
+  if (!w.gate_done) return;
+  __threadfence();  // this lane's output bytes are visible device-wide ...
+  g_sync();
+  if (g_lane() == 0) atomicAdd(w.gate_done + gate, 1u);  // ... before the count that releases the group's copy-out
+}
+
 template <typename OutT>
 struct Grp {
   BitReader b;
@@ -438,6 +458,8 @@ struct Grp {
   OutT *out;
   uint32_t shift0, cap, op, idx, kind, expect;
   uint32_t win;         // elements in front of `out` a back-reference may reach (speculative segments: 32768)
+  uint32_t gate;        // gated queue: the copy-in group of the member in hand
+  uint32_t ready_seen;  // gated queue: copy-in groups this group knows to have landed
   int st;
   bool final_block;
 };
@@ -674,6 +696,8 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
   Grp<OutT> g;
   g.st = ST_FETCH;
   g.win = 0;
+  g.gate = 0;
+  g.ready_seen = 0;
   g.b.gbase = nullptr;
   g.b.nwords = 0;
   g.b.cur = g.b.nxt = g.b.over_word = 0;
@@ -689,11 +713,31 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
       uint32_t i = 0;
       if (lane == 0) i = atomicAdd(w.counter, 1u);
       i = g_shfl(i, 0);
+      if (i < w.n && w.gate_first) {
+        // the member's input may still be on its way: wait for its copy-in group (lane 0 polls, the group follows)
+        uint32_t gt = 0;
+        while (gt + 1u < w.n_gates && i >= w.gate_first[gt + 1u]) gt++;
+        g.gate = gt;
+        if (gt >= g.ready_seen) {
+          // (an acquire load also drops this SM's L1 lines: a line read before the copy-in landed may hold stale
+          // bytes of this member's head.  The count only grows, so a group asks once per copy-in group.)
+          uint32_t r = 0;
+          if (lane == 0) {
+            r = gate_load(w.gate_ready);
+            if (r <= gt) {
+              const uint64_t t0 = gate_clock();
+              while ((r = gate_load(w.gate_ready)) <= gt && gate_clock() - t0 < 30000000000ull) __nanosleep(500);
+            }
+          }
+          g.ready_seen = g_shfl(r, 0);
+        }
+      }
       if (i < w.n && w.order) i = w.order[i];
       if (i >= w.n) {
         g.st = ST_EXIT;
       } else if (w.skip && w.skip[i]) {
         // handled elsewhere (a large member decoded as parallel segments): fetch the next one
+        gate_member_done(w, g.gate);
       } else if ((COUNT_ONLY || MARK) && w.seg_bits) {
         // a speculative segment of one raw stream: bit-exact start and end inside w.src; bits beyond the
         // end are the next segment's (real data), so an over-read is harmless and an over-RUN is caught
@@ -777,6 +821,7 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
         w.kind[g.idx] = w.seg_mode ? (uint32_t)g.final_block : g.kind;
         w.expect[g.idx] = g.expect;
       }
+      gate_member_done(w, g.gate);
       g.st = ST_FETCH;
     }
     __syncwarp();
@@ -799,6 +844,7 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
           w.kind[g.idx] = w.seg_mode ? (uint32_t)g.final_block : g.kind;
           w.expect[g.idx] = g.expect;
         }
+        gate_member_done(w, g.gate);
         g.st = ST_FETCH;
       } else {
         g.st = ST_BLOCK;
@@ -1355,6 +1401,15 @@ cudaError_t zb_setup_inflate_attrs() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resolve_tails, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_piece_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL);
+  // Load every kernel NOW (CUDA loads a function lazily at its first launch, and that load can wait for the device
+  // to go idle): a launch queued behind the gated inflate kernel must not be the one that triggers it -- the kernel
+  // would be waiting for copies this thread has not queued yet.
+  cudaFuncAttributes fa;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_buffer_combine);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_find_sync);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_find_blocks);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_mark_prefill);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_resolve_rest);
   return e;
 }
 

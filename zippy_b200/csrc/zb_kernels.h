@@ -92,6 +92,14 @@ struct ZbInflateWork {
   int seg_mode;                // members are independently decodable SEGMENTS of one raw deflate stream:
                                // a segment also ends, successfully, when its input is used up at a block
                                // boundary; kind[i] reports whether a final block was seen
+  // Gated queue (the host pipeline: ONE launch for a whole batch whose input is still arriving).  Queue
+  // positions [gate_first[g], gate_first[g + 1]) belong to copy-in group g and are not started before
+  // *gate_ready > g (written in stream order behind the group's copy); gate_done[g] counts the group's
+  // finished members (a stream wait on it releases the group's copy-out).  Null: no gates.
+  const uint32_t *gate_first;  // device [n_gates + 1]
+  const uint32_t *gate_ready;  // device word
+  uint32_t *gate_done;         // device [n_gates], zeroed before the launch
+  uint32_t n_gates;
 };
 cudaError_t zb_launch_inflate(const ZbInflateWork &w, cudaStream_t s);
 // positions just past every byte sequence 00 00 ff ff (the empty stored block that byte-aligns a
