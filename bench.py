@@ -774,6 +774,13 @@ def measure_uncompress(e, d_comp, comp_offs, out_sizes, steps, warmup, do_e2e=Tr
                       "in_gibs": in_bytes / GIB / (ms3 / 1e3), "ms_per_step": ms3, "h2d_bytes_per_step": in_bytes,
                       "d2h_bytes_per_step": out_bytes, "h2d_ms": tb["h2d_ms"], "d2h_ms": tb["d2h_ms"],
                       "inflate_ms": tb["inflate_ms"] + tb["verify_ms"], "host_memory": "page-locked"}
+        # the same bytes as ONE plain device -> host copy into the same buffer: the floor of the copy-out leg
+        t.cuda.synchronize()
+        e.ev0.record(e.stream)
+        h_out[:out_bytes].copy_(d_out[:out_bytes], non_blocking=True)
+        e.ev1.record(e.stream)
+        t.cuda.synchronize()
+        res["e2e"]["d2h_plain_gbs"] = out_bytes / (e.ev0.elapsed_time(e.ev1) / 1e3) / 1e9
         del h_out
     return res
 

@@ -1296,6 +1296,14 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
       int rc = copy_in(0);
       if (rc) return rc;
     }
+    // ZB200_DEBUG_TIMELINE=1: per group, when its done count released the copy-out and when the copy ended (stderr)
+    static const bool timeline = getenv("ZB200_DEBUG_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> tl;
+    if (timeline) {
+      tl.resize(2 * ng + 1);
+      for (auto &ev : tl) cudaEventCreate(&ev);
+      cudaEventRecord(tl[2 * ng], sd);
+    }
     for (size_t gi = 0; gi < ng; gi++) {
       if (gi + 1 < ng) {  // the next group's copy-in is queued before this thread may block on a pageable copy-out
         int rc = copy_in(gi + 1);
@@ -1306,9 +1314,22 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
       if (o1 > o0 && h_dst) {
         if (ctx->memops.wait32((CUstream)sd, (CUdeviceptr)(uintptr_t)(d_gate + 1 + gi), (cuuint32_t)(m1 - m0), CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
           return ZB200_ERR_CUDA;
+        if (timeline) cudaEventRecord(tl[2 * gi], sd);
         int rc = d2h_copy(ctx, h_dst + o0, d_dst + o0, (size_t)(o1 - o0), sd, dst_pageable);
         if (rc) return rc;
+        if (timeline) cudaEventRecord(tl[2 * gi + 1], sd);
       }
+    }
+    if (timeline) {
+      cudaStreamSynchronize(sd);
+      for (size_t gi = 0; gi < ng; gi++) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, tl[2 * ng], tl[2 * gi]);
+        cudaEventElapsedTime(&b, tl[2 * ng], tl[2 * gi + 1]);
+        fprintf(stderr, "group %zu: members %zu, out %.1f MiB, released %.2f ms, copied %.2f ms\n", gi, gb[gi + 1] - gb[gi],
+                (double)(dreb[gb[gi + 1]] - dreb[gb[gi]]) / 1048576.0, a, b);
+      }
+      for (auto &ev : tl) cudaEventDestroy(ev);
     }
   }
   for (size_t gi = 0; gi < ng && !gated; gi++) {

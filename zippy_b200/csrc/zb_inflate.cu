@@ -19,6 +19,8 @@
 // that run through the same kernel in parallel (zb_api.cu: inflate_big_members).
 #include <type_traits>
 
+#include <algorithm>
+
 #include "zb_device.cuh"
 #include "zb_kernels.h"
 #include "zb_wrapper.h"
@@ -963,14 +965,41 @@ __device__ __forceinline__ ZbCheck ck_warp_full(const uint8_t *base, uint32_t of
 // word and runs at the copy rate; CRC-32 without a carry-less multiply is one table lookup per byte, which
 // is why the step tables are replicated per bank.
 #define CK_INFO 32
-__global__ void __launch_bounds__(CK_THREADS, 1)
+// Adler sums of a ragged piece of n bytes (no tables): lane-strided words, the last 1..3 bytes by lane 0
+__device__ __forceinline__ ZbCheck ck_warp_adler_ragged(const uint8_t *base, uint32_t off, uint32_t n) {
+  const int lane = zb_lane();
+  uint64_t a = 0, b = 0;
+  for (uint32_t i = 4u * (uint32_t)lane; i + 4u <= n; i += 128u) {
+    const uint32_t w = zb_ld32_unaligned(base, off + i);
+    const uint32_t s = __dp4a(w, 0x01010101u, 0u);
+    a += s;
+    b += (uint64_t)(n - i) * s - __dp4a(w, 0x03020100u, 0u);
+  }
+  if (lane == 0)
+    for (uint32_t i = n & ~3u; i < n; i++) {
+      a += base[off + i];
+      b += (uint64_t)(n - i) * base[off + i];
+    }
+  ZbCheck out;
+  out.crc_raw = 0;
+  out.a_sum = zb_warp_sum64(a);
+  out.b_sum = zb_warp_sum64(b);
+  return out;
+}
+
+// ADLER_ONLY: every piece wants Adler-32 (the adler32 entry points, batches of zlib members): no CRC tables in
+// shared memory, so three CTAs share an SM and three times as many bulk copies are in flight.
+#define CK_SM_TOTAL_ADLER (CK_SM_REP + 48 * 4 + CK_WARPS * 24 + 8 * CK_STAGES + 8)
+template <bool ADLER_ONLY>
+__global__ void __launch_bounds__(CK_THREADS, ADLER_ONLY ? 3 : 1)
     k_piece_checksum(ZbChecksumWork w) {
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr uint32_t LMUL_OFF = ADLER_ONLY ? CK_SM_REP : CK_SM_LMUL;
   uint32_t *rep = reinterpret_cast<uint32_t *>(smem + CK_SM_REP);
   uint32_t *qt = reinterpret_cast<uint32_t *>(smem + CK_SM_QT);
-  uint32_t *lane_mul = reinterpret_cast<uint32_t *>(smem + CK_SM_LMUL);
-  uint64_t *part = reinterpret_cast<uint64_t *>(smem + CK_SM_PART);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CK_SM_BAR);
+  uint32_t *lane_mul = reinterpret_cast<uint32_t *>(smem + LMUL_OFF);
+  uint64_t *part = reinterpret_cast<uint64_t *>(smem + LMUL_OFF + 48 * 4);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + LMUL_OFF + 48 * 4 + CK_WARPS * 24);
   __shared__ const uint8_t *info_src[CK_INFO];
   __shared__ uint32_t info_len[CK_INFO];
   __shared__ uint32_t info_kind[CK_INFO];
@@ -980,14 +1009,14 @@ __global__ void __launch_bounds__(CK_THREADS, 1)
     for (int i = 0; i < CK_STAGES; i++) zb_mbar_init(&bars[i], 1);
     zb_fence_mbar_init();
   }
-  {
+  if (!ADLER_ONLY) {
     const uint32_t *t = &w.tabs->mul1024[0][0];
     for (int i = tid; i < 1024 * 32; i += CK_THREADS) rep[i] = t[i >> 5];   // entry e, lane l at rep[e * 32 + l]
     const uint32_t *q = &w.tabs->ck_quart[0][0][0];
     for (int i = tid; i < 3 * 1024; i += CK_THREADS) qt[i] = q[i];
+    if (tid < 33) lane_mul[tid] = w.tabs->lane_mul[tid];
+    if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = w.tabs->ck_sub[tid - 64];
   }
-  if (tid < 33) lane_mul[tid] = w.tabs->lane_mul[tid];
-  if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = w.tabs->ck_sub[tid - 64];
   if (tid >= 128 && tid < 128 + CK_INFO) {  // descriptors of this CTA's first 32 pieces
     const uint32_t j = (uint32_t)tid - 128u, pid = blockIdx.x + j * stride;
     const uint8_t *src = nullptr;
@@ -1021,11 +1050,12 @@ __global__ void __launch_bounds__(CK_THREADS, 1)
     c.a_sum = c.b_sum = 0;
     if (b0 < len) {
       const uint32_t n = b1 - b0;
-      if (n == CK_WARP_BYTES) c = kind ? ck_warp_full<1>(data, mis + b0, rep_lane, qt, lane_mul) : ck_warp_full<0>(data, mis + b0, rep_lane, qt, lane_mul);
+      if (ADLER_ONLY) c = n == CK_WARP_BYTES ? ck_warp_full<1>(data, mis + b0, rep_lane, qt, lane_mul) : ck_warp_adler_ragged(data, mis + b0, n);
+      else if (n == CK_WARP_BYTES) c = kind ? ck_warp_full<1>(data, mis + b0, rep_lane, qt, lane_mul) : ck_warp_full<0>(data, mis + b0, rep_lane, qt, lane_mul);
       else c = zb_warp_checksums(data, mis + b0, n, rep, lane_mul, 32u);   // a buffer's ragged last piece
       const uint32_t after = len - b1;
       if (after) {
-        if (kind == 0)
+        if (!ADLER_ONLY && kind == 0)
           c.crc_raw = zb_gf2_mul(c.crc_raw, (after & (CK_WARP_BYTES - 1u)) == 0u ? lane_mul[33 + after / CK_WARP_BYTES] : zb_xpow8(after));
         else c.b_sum += (uint64_t)after * c.a_sum;
       }
@@ -1400,7 +1430,9 @@ cudaError_t zb_setup_inflate_attrs() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_inflate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resolve_tails, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_piece_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_piece_checksum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_piece_checksum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SM_TOTAL_ADLER);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_piece_checksum<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   // Load every kernel NOW (CUDA loads a function lazily at its first launch, and that load can wait for the device
   // to go idle): a launch queued behind the gated inflate kernel must not be the one that triggers it -- the kernel
   // would be waiting for copies this thread has not queued yet.
@@ -1438,8 +1470,13 @@ cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (w.n_pieces) {
-    uint32_t grid = (uint32_t)sms < w.n_pieces ? (uint32_t)sms : w.n_pieces;
-    k_piece_checksum<<<grid, CK_THREADS, CK_SM_TOTAL, s>>>(w);
+    if (!w.kinds && w.kind == 1) {  // Adler-32 throughout: the table-free instantiation, three CTAs per SM
+      const uint32_t grid = std::min<uint32_t>(3u * (uint32_t)sms, w.n_pieces);
+      k_piece_checksum<true><<<grid, CK_THREADS, CK_SM_TOTAL_ADLER, s>>>(w);
+    } else {
+      const uint32_t grid = std::min<uint32_t>((uint32_t)sms, w.n_pieces);
+      k_piece_checksum<false><<<grid, CK_THREADS, CK_SM_TOTAL, s>>>(w);
+    }
   }
   k_buffer_combine<<<(w.n + 3) / 4, 128, 0, s>>>(w);
   return cudaGetLastError();
