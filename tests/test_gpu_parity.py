@@ -256,6 +256,21 @@ def test_checksums(z, corpus):
     assert z.adler32(corpus["html"]) == zlib.adler32(corpus["html"])
 
 
+def test_checksums_of_large_buffers(z):
+    """One very large input (more than 2048 pieces of 32 KiB) is folded by a whole CTA, next to small ones folded
+    by one warp each; ragged last pieces; both checksums against zlib."""
+    rng = np.random.default_rng(11)
+    big1 = rng.integers(0, 256, (64 << 20) + 12345, dtype=np.uint8).tobytes()     # 2049 pieces
+    big2 = rng.integers(0, 256, (150 << 20) + 7, dtype=np.uint8).tobytes()
+    xs = [b"tiny", big1, b"", big2, big1[:70000]]
+    crcs = z.checksum_batch(xs, "crc32")
+    ads = z.checksum_batch(xs, "adler32")
+    for x, c, a in zip(xs, crcs, ads):
+        assert int(c) == zlib.crc32(x), len(x)
+        assert int(a) == zlib.adler32(x), len(x)
+    assert z.crc32(big2) == zlib.crc32(big2) and z.adler32(big2) == zlib.adler32(big2)
+
+
 def test_seam_deflate_inflate(z, o, corpus):
     # deflate.nim:207 / inflate.nim:268 signatures: raw stream, inflate from byte `pos`
     for name in ("alice29.txt", "html", "empty.gold", "fireworks.jpg"):

@@ -609,6 +609,9 @@ int upload_pieces(zb200_ctx *ctx, const uint64_t *offs, size_t n, ZbChecksumWork
     } while (rel < cap);
   }
   first[n] = (uint32_t)pieces.size();
+  w.big_pieces = 0;
+  for (size_t i = 0; i < n; i++)
+    if (first[i + 1] - first[i] > ZB_CK_BIG_PIECES) w.big_pieces = ZB_CK_BIG_PIECES;
   ENSURE(ctx->ck_pieces, pieces.size() * sizeof(ZbPiece));
   ENSURE(ctx->ck_first, (n + 1) * sizeof(uint32_t));
   ENSURE(ctx->ck_piece_out, pieces.size() * sizeof(ZbChunkCheck));

@@ -1095,6 +1095,21 @@ __global__ void __launch_bounds__(CK_THREADS, ADLER_ONLY ? 3 : 1)
   }
 }
 
+// raw CRC (init 0) / Adler sums of a whole buffer -> the checksum value; store and, in verify mode, compare
+__device__ __forceinline__ void ck_finish(const ZbChecksumWork &w, uint32_t i, int kind, uint32_t r, uint64_t a, uint64_t b,
+                                          uint64_t buflen) {
+  const uint32_t v = kind == 0 ? ~(zb_gf2_mul(buflen == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8(buflen), 0xffffffffu) ^ r)
+                               : zb_adler_from_sums(a % ZB_ADLER_MOD, b % ZB_ADLER_MOD, buflen);
+  if (w.out) w.out[i] = v;
+  if (w.expect) {
+    if (v != w.expect[i]) w.status[i] = ZB_ERR_CHECKSUM;
+    else if (kind == 0 && w.isize_src) {
+      const uint8_t *t = w.isize_src + w.isize_off[i + 1] - 4;
+      if (zb_ld_le32(t) != (uint32_t)buflen) w.status[i] = ZB_ERR_SIZE;
+    }
+  }
+}
+
 // One warp per buffer: lane j folds pieces j, j+32, ... (Horner in x^(8 * 32 * 64 KiB)), the lane
 // results are shifted to the end of the buffer and XOR-reduced; Adler sums add up directly.
 __global__ void __launch_bounds__(128)
@@ -1113,6 +1128,7 @@ __global__ void __launch_bounds__(128)
   const uint64_t buflen = w.lens ? w.lens[i] : w.off[i + 1] - w.off[i];
   const uint32_t p0 = w.first[i];
   const uint32_t np = (uint32_t)((buflen + CK_PIECE - 1) / CK_PIECE);  // pieces that hold data
+  if (w.big_pieces && np > w.big_pieces) return;  // k_buffer_combine_big's
   uint32_t r = 0;
   uint64_t a = 0, b = 0, end = 0;  // end = bytes from the buffer start to the end of this lane's last piece
   if (kind == 0) {
@@ -1146,16 +1162,78 @@ __global__ void __launch_bounds__(128)
     b = zb_warp_sum64(b);
   }
   if (lane != 0) return;
-  const uint32_t v = kind == 0 ? ~(zb_gf2_mul(buflen == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8(buflen), 0xffffffffu) ^ r)
-                               : zb_adler_from_sums(a % ZB_ADLER_MOD, b % ZB_ADLER_MOD, buflen);
-  if (w.out) w.out[i] = v;
-  if (w.expect) {
-    if (v != w.expect[i]) w.status[i] = ZB_ERR_CHECKSUM;
-    else if (kind == 0 && w.isize_src) {
-      const uint8_t *t = w.isize_src + w.isize_off[i + 1] - 4;
-      if (zb_ld_le32(t) != (uint32_t)buflen) w.status[i] = ZB_ERR_SIZE;
-    }
+  ck_finish(w, i, kind, r, a, b, buflen);
+}
+
+// The same fold for a buffer of very many pieces (one multi-GiB input of crc32 / adler32): 1024 threads, thread t
+// folds pieces t, t + 1024, ... (Horner in x^(8 * 1024 * 32 KiB)), shifts to the end of the buffer, block XOR / sum.
+// (One warp per buffer spent 1.5 ms folding the 131072 pieces of a 4 GiB buffer, longer than the pieces took.)
+#define CKB_THREADS 1024
+__global__ void __launch_bounds__(CKB_THREADS)
+    k_buffer_combine_big(ZbChecksumWork w) {
+  const uint32_t i = blockIdx.x;
+  __shared__ uint32_t red_r[CKB_THREADS / 32];
+  __shared__ uint64_t red_a[CKB_THREADS / 32], red_b[CKB_THREADS / 32];
+  if (w.status && w.status[i] != ZB_OK) return;
+  int kind = w.kind;
+  if (w.kinds) {
+    const uint32_t kd = w.kinds[i];
+    if (kd == ZB_DF_GZIP) kind = 0;
+    else if (kd == ZB_DF_ZLIB) kind = 1;
+    else return;
   }
+  const uint64_t buflen = w.lens ? w.lens[i] : w.off[i + 1] - w.off[i];
+  const uint32_t p0 = w.first[i];
+  const uint32_t np = (uint32_t)((buflen + CK_PIECE - 1) / CK_PIECE);
+  if (np <= w.big_pieces) return;  // k_buffer_combine's
+  const uint32_t t = threadIdx.x;
+  uint32_t r = 0;
+  uint64_t a = 0, b = 0, end = 0;
+  if (kind == 0) {
+    uint32_t step = 0;
+    for (uint32_t k = t; k < np; k += CKB_THREADS) {
+      const uint32_t l = piece_len(buflen, (uint64_t)k * CK_PIECE);
+      const uint32_t raw = w.piece_out[p0 + k].crc_raw;
+      if (k >= CKB_THREADS) {
+        if (l == CK_PIECE) {
+          if (!step) step = zb_xpow8((uint64_t)CKB_THREADS * CK_PIECE);
+          r = zb_gf2_mul(r, step);
+        } else {
+          r = zb_gf2_mul(r, zb_xpow8((uint64_t)(CKB_THREADS - 1) * CK_PIECE + l));
+        }
+      }
+      r ^= raw;
+      end = (uint64_t)k * CK_PIECE + l;
+    }
+    if (t < np && end < buflen) r = zb_gf2_mul(r, zb_xpow8(buflen - end));
+    r = zb_warp_xor(r);
+  } else {
+    for (uint32_t k = t; k < np; k += CKB_THREADS) {
+      const uint32_t l = piece_len(buflen, (uint64_t)k * CK_PIECE);
+      const uint32_t ab = w.piece_out[p0 + k].adler;
+      const uint64_t ak = ab & 0xffffu, bk = ab >> 16;
+      const uint64_t after = (buflen - ((uint64_t)k * CK_PIECE + l)) % ZB_ADLER_MOD;
+      a += ak;
+      b = (b + bk + after * ak) % ZB_ADLER_MOD;
+    }
+    a = zb_warp_sum64(a % ZB_ADLER_MOD);
+    b = zb_warp_sum64(b);
+  }
+  if ((t & 31u) == 0) {
+    red_r[t >> 5] = r;
+    red_a[t >> 5] = a;
+    red_b[t >> 5] = b;
+  }
+  __syncthreads();
+  if (t != 0) return;
+  r = 0;
+  a = b = 0;
+  for (int j = 0; j < CKB_THREADS / 32; j++) {
+    r ^= red_r[j];
+    a += red_a[j];
+    b += red_b[j];
+  }
+  ck_finish(w, i, kind, r, a, b, buflen);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1438,6 +1516,7 @@ cudaError_t zb_setup_inflate_attrs() {
   // would be waiting for copies this thread has not queued yet.
   cudaFuncAttributes fa;
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_buffer_combine);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_buffer_combine_big);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_find_sync);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_find_blocks);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_mark_prefill);
@@ -1479,5 +1558,6 @@ cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s) {
     }
   }
   k_buffer_combine<<<(w.n + 3) / 4, 128, 0, s>>>(w);
+  if (w.big_pieces) k_buffer_combine_big<<<w.n, CKB_THREADS, 0, s>>>(w);
   return cudaGetLastError();
 }

@@ -148,5 +148,8 @@ struct ZbChecksumWork {
   const ZbCrcTables *tabs;
   uint32_t n, n_pieces;
   int kind;                    // 0 crc32, 1 adler32 when kinds == null
+  uint32_t big_pieces;         // 0, or: buffers of more pieces than this are folded by a whole CTA (k_buffer_combine_big)
+                               //   instead of one warp (the host sets it when some buffer's capacity is that large)
 };
+#define ZB_CK_BIG_PIECES 2048u  // 64 MiB
 cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s);
