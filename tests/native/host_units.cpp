@@ -63,6 +63,35 @@ uint32_t t_crc32_lane_model(const uint8_t *data, uint64_t n) {
   return zb_crc32_finalize(raw, n);
 }
 
+// the checksum kernel's CRC path for a full 32 KiB piece (zb_inflate.cu: ck_warp_crc_rows + k_piece_fold): 64 chains
+// of four rows with the 64-row step, four chains of a warp joined by table multiplications, then the 16 x 32
+// partial words folded like a 2 KiB message
+static uint32_t mul_tab(const uint32_t t[4][256], uint32_t r) {
+  return t[0][r & 255] ^ t[1][(r >> 8) & 255] ^ t[2][(r >> 16) & 255] ^ t[3][r >> 24];
+}
+uint32_t t_crc32_piece_model(const uint8_t *data) {
+  static ZbCrcTables T;
+  static int init = 0;
+  if (!init) { zb_crc_build_tables(&T); init = 1; }
+  uint32_t total = 0;
+  for (int lane = 0; lane < 32; lane++) {
+    uint32_t f = 0;
+    for (int warp = 0; warp < 16; warp++) {
+      uint32_t r[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 4; k++)
+        for (int c = 0; c < 4; c++) {
+          if (k) r[c] = mul_tab(T.mul64r, r[c]);
+          r[c] ^= ld32(data + 128 * (64 * k + warp + 16 * c) + 4 * lane);
+        }
+      const uint32_t m = mul_tab(T.ck_join[2], r[0]) ^ mul_tab(T.ck_join[1], r[1]) ^ mul_tab(T.ck_join[0], r[2]) ^ r[3];
+      if (warp) f = mul_tab(T.mul1024, f);
+      f ^= m;
+    }
+    total ^= zb_gf2_mul(f, T.lane_mul[32 - lane]);
+  }
+  return zb_crc32_finalize(total, 32768);
+}
+
 uint32_t t_adler32_model(const uint8_t *data, uint64_t n) {
   // per-4-byte-word sums exactly as the device does: A += sum(b), B += (n-o)*sum(b) - (b1+2*b2+3*b3)
   uint64_t A = 0, B = 0;

@@ -20,7 +20,7 @@ def hu():
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", SO, SRC])
     L = ctypes.CDLL(SO)
-    for f in ("t_gf2_mul", "t_xpow8", "t_crc_combine", "t_adler_combine", "t_crc32_lane_model", "t_adler32_model",
+    for f in ("t_gf2_mul", "t_xpow8", "t_crc_combine", "t_adler_combine", "t_crc32_lane_model", "t_crc32_piece_model", "t_adler32_model",
               "t_dist_base", "t_len_base"):
         getattr(L, f).restype = ctypes.c_uint32
     L.t_xpow8.argtypes = [ctypes.c_uint64]
@@ -28,6 +28,7 @@ def hu():
     L.t_adler_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
     L.t_crc32_lane_model.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
     L.t_adler32_model.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
+    L.t_crc32_piece_model.argtypes = [ctypes.c_char_p]
     return L
 
 
@@ -198,6 +199,9 @@ def test_crc_math(hu):
         assert hu.t_adler32_model(x, n) == zlib.adler32(x), n
     x = b"\xff" * 70000
     assert hu.t_adler32_model(x, len(x)) == zlib.adler32(x)
+    for _ in range(3):   # the checksum kernel's full-piece CRC path (chains, joins, the fold of the partial words)
+        x = bytes(rng.randrange(256) for _ in range(32768))
+        assert hu.t_crc32_piece_model(x) == zlib.crc32(x)
     for _ in range(50):
         a = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 3000)))
         b = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 3000)))

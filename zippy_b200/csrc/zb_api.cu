@@ -156,7 +156,7 @@ struct zb200_ctx {
   cudaStream_t own_stream = nullptr;
   ZbCrcTables *d_tabs = nullptr;
   DevBuf desc, member_first, fname, masks, recs, hist, chk, cb, chunk_off, member_off, member_check, member_isize;
-  DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out, ck_pieces, ck_first, ck_piece_out;
+  DevBuf src_off, dst_off, out_len, status, expect, kind, counter, ck_out, ck_pieces, ck_first, ck_piece_out, ck_partials;
   DevBuf in_stage, out_stage, lz2_tables;
   DevBuf seg_src, seg_dst, seg_len, seg_status, seg_kind, seg_expect, seg_cand, skip_mask;  // large-member segments
   DevBuf mark_scratch, mark_segs, seg_bits;  // speculative segments of a large member (uint16 symbols, descriptors)
@@ -615,6 +615,8 @@ int upload_pieces(zb200_ctx *ctx, const uint64_t *offs, size_t n, ZbChecksumWork
   ENSURE(ctx->ck_pieces, pieces.size() * sizeof(ZbPiece));
   ENSURE(ctx->ck_first, (n + 1) * sizeof(uint32_t));
   ENSURE(ctx->ck_piece_out, pieces.size() * sizeof(ZbChunkCheck));
+  ENSURE(ctx->ck_partials, pieces.size() * (size_t)ZB_CK_PARTIAL_BYTES);
+  w.partials = (uint32_t *)ctx->ck_partials.p;
   CK(cudaMemcpyAsync(ctx->ck_pieces.p, pieces.data(), pieces.size() * sizeof(ZbPiece), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->ck_first.p, first.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
@@ -1209,6 +1211,7 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
   ENSURE(ctx->ck_pieces, pieces.size() * sizeof(ZbPiece));
   ENSURE(ctx->ck_first, first.size() * sizeof(uint32_t));
   ENSURE(ctx->ck_piece_out, pieces.size() * sizeof(ZbChunkCheck));
+  ENSURE(ctx->ck_partials, pieces.size() * (size_t)ZB_CK_PARTIAL_BYTES);
   {
     int rc = ensure_group_events(ctx, 2 * ng + 2);
     if (rc) return rc;
@@ -1277,6 +1280,7 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
     cw.pieces = (const ZbPiece *)ctx->ck_pieces.p;
     cw.first = (const uint32_t *)ctx->ck_first.p;
     cw.piece_out = (ZbChunkCheck *)ctx->ck_piece_out.p;
+    cw.partials = (uint32_t *)ctx->ck_partials.p;
     cw.status = w.status;
     cw.expect = w.expect;
     cw.kinds = w.kind;
@@ -1370,6 +1374,7 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
     cw.pieces = (const ZbPiece *)ctx->ck_pieces.p + piece0[gi];
     cw.first = (const uint32_t *)ctx->ck_first.p + first0[gi];
     cw.piece_out = (ZbChunkCheck *)ctx->ck_piece_out.p + piece0[gi];
+    cw.partials = (uint32_t *)ctx->ck_partials.p + piece0[gi] * (size_t)(ZB_CK_PARTIAL_BYTES / 4);
     cw.status = w.status;
     cw.expect = w.expect;
     cw.kinds = w.kind;
@@ -1575,7 +1580,7 @@ void zb200_shutdown(zb200_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->desc, &ctx->member_first, &ctx->fname, &ctx->masks, &ctx->recs, &ctx->hist, &ctx->chk,
                     &ctx->cb, &ctx->chunk_off, &ctx->member_off, &ctx->member_check, &ctx->member_isize,
                     &ctx->src_off, &ctx->dst_off, &ctx->out_len, &ctx->status, &ctx->expect, &ctx->kind,
-                    &ctx->counter, &ctx->ck_out, &ctx->ck_pieces, &ctx->ck_first, &ctx->ck_piece_out, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables,
+                    &ctx->counter, &ctx->ck_out, &ctx->ck_pieces, &ctx->ck_first, &ctx->ck_piece_out, &ctx->ck_partials, &ctx->in_stage, &ctx->out_stage, &ctx->lz2_tables,
                     &ctx->seg_src, &ctx->seg_dst, &ctx->seg_len, &ctx->seg_status, &ctx->seg_kind, &ctx->seg_expect, &ctx->seg_cand, &ctx->skip_mask, &ctx->order, &ctx->mark_scratch, &ctx->mark_segs, &ctx->seg_bits, &ctx->gate};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);

@@ -85,11 +85,12 @@ struct ZbCrcTables {
   uint32_t sub_mul[8];  // [k] = x^(8 * 8192 * k) mod P, k = 1..7: shifts a sub-chunk's CRC to the chunk end;
                         // [0] = x^(8 * 65536) mod P: shifts by one whole chunk
   uint32_t quart_mul[4];  // [k] = x^(8 * 2048 * k) mod P: shifts a quarter of a sub-chunk (16 rows of 128 B)
-  uint32_t ck_sub[8];     // [k] = x^(8 * 4096 * k) mod P: shifts a warp's 4 KiB of a checksum piece to the piece end
+  uint32_t ck_sub[16];    // [k] = x^(8 * 2048 * k) mod P: shifts a warp's 2 KiB of a (ragged) checksum piece to the piece end
   uint32_t piece_mul[16]; // [k] = x^(8 * 4096 * k) mod P: shifts the CRC of one of k_lz's 4 KiB pieces to the chunk end
   uint32_t pq_mul[4];     // [k] = x^(8 * 1024 * k) mod P: joins the four 1 KiB chains of such a piece
-  uint32_t ck_quart[3][4][256];  // multiply-by-constant tables: [k-1][j][b] = (b << 8j) * x^(8 * 1024 * k), k = 1..3:
-                                 // joins the four 1 KiB chains of the checksum kernel's 4 KiB warp pieces with lookups
+  // the checksum kernel's CRC path (zb_inflate.cu): a 32 KiB piece is 256 rows of 128 B; row q + 64 k belongs to chain q
+  uint32_t mul64r[4][256];       // [j][b] = (b << 8j) * x^(8 * 128 * 64): the Horner step of a chain (64 rows)
+  uint32_t ck_join[3][4][256];   // [k-1][j][b] = (b << 8j) * x^(8 * 128 * 16 * k), k = 1..3: joins a warp's four chains
 };
 
 inline void zb_crc_build_tables(ZbCrcTables *t) {
@@ -100,12 +101,17 @@ inline void zb_crc_build_tables(ZbCrcTables *t) {
   for (int k = 1; k < 8; k++) t->sub_mul[k] = zb_xpow8((uint64_t)ZB_SUB_BYTES * (uint64_t)k);
   t->sub_mul[0] = zb_xpow8((uint64_t)ZB_CHUNK_BYTES);
   for (int k = 0; k < 4; k++) t->quart_mul[k] = zb_xpow8((uint64_t)(ZB_SUB_BYTES / 4) * (uint64_t)k);
-  for (int k = 0; k < 8; k++) t->ck_sub[k] = zb_xpow8(4096ull * (uint64_t)k);
+  for (int k = 0; k < 16; k++) t->ck_sub[k] = zb_xpow8(2048ull * (uint64_t)k);
+  {
+    const uint32_t c = zb_xpow8(128ull * 64ull);
+    for (int j = 0; j < 4; j++)
+      for (uint32_t b = 0; b < 256; b++) t->mul64r[j][b] = zb_gf2_mul(b << (8 * j), c);
+  }
   for (int k = 0; k < 16; k++) t->piece_mul[k] = zb_xpow8(4096ull * (uint64_t)k);
   for (int k = 0; k < 4; k++) t->pq_mul[k] = zb_xpow8(1024ull * (uint64_t)k);
   for (int k = 1; k <= 3; k++) {
-    const uint32_t c = zb_xpow8(1024ull * (uint64_t)k);
+    const uint32_t c = zb_xpow8(128ull * 16ull * (uint64_t)k);
     for (int j = 0; j < 4; j++)
-      for (uint32_t b = 0; b < 256; b++) t->ck_quart[k - 1][j][b] = zb_gf2_mul(b << (8 * j), c);
+      for (uint32_t b = 0; b < 256; b++) t->ck_join[k - 1][j][b] = zb_gf2_mul(b << (8 * j), c);
   }
 }

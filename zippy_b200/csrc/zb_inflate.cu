@@ -863,18 +863,25 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
 // zb_device.cuh), k_buffer_combine folds a buffer's pieces with x^(8*len) multiplications /
 // the closed-form Adler merge, and in verify mode compares with the trailer.
 #define CK_PIECE ZB_CK_PIECE_BYTES
-#define CK_THREADS 256
+#define CK_THREADS 512
 #define CK_WARPS (CK_THREADS / 32)
-#define CK_WARP_BYTES (CK_PIECE / CK_WARPS)          // 4 KiB per warp and piece
+#define CK_WARP_BYTES (CK_PIECE / CK_WARPS)          // 2 KiB per warp and piece (Adler, ragged pieces)
+#define CK_ROWS (CK_PIECE / 128)                      // a full piece is 256 rows of 128 B
+#define CK_CHAINS (CK_WARPS * 4)                      // CRC of a full piece: row q + 64 k belongs to chain q, warp w owns chains w + 16 c
+#define CK_PARTIAL_WORDS (CK_WARPS * 32)              // what the CRC path leaves per full piece: one word per warp and lane
 #define CK_STAGES 2
 #define CK_STAGE_BYTES (CK_PIECE + 128)
-#define CK_SM_REP (CK_STAGES * CK_STAGE_BYTES)        // x^1024 step tables, one copy per lane (bank): 4 x 256 x 32 words
-#define CK_SM_QT (CK_SM_REP + 4 * 256 * 32 * 4)       // multiply-by-x^(8*1024*k) tables, k = 1..3
+#define CK_SM_REP (CK_STAGES * CK_STAGE_BYTES)        // chain step tables (x^(8*128*64)), one copy per lane (bank): 4 x 256 x 32 words
+#define CK_SM_T1024 (CK_SM_REP + 4 * 256 * 32 * 4)    // x^1024 step table (ragged pieces)
+#define CK_SM_QT (CK_SM_T1024 + 4 * 256 * 4)          // chain join tables: multiply by x^(8*128*16*k), k = 1..3
 #define CK_SM_LMUL (CK_SM_QT + 3 * 4 * 256 * 4)
-#define CK_SM_PART (CK_SM_LMUL + 48 * 4)
+#define CK_LMUL_WORDS 52
+#define CK_SM_PART (CK_SM_LMUL + CK_LMUL_WORDS * 4)
 #define CK_SM_BAR (CK_SM_PART + CK_WARPS * 24)
 #define CK_SM_TOTAL (CK_SM_BAR + 8 * CK_STAGES + 8)
 static_assert(CK_SM_TOTAL <= 232448, "one CTA per SM");
+static_assert(CK_ROWS == 4 * CK_CHAINS, "four rows per chain");
+static_assert(CK_PARTIAL_WORDS * 4 == ZB_CK_PARTIAL_BYTES, "scratch size");
 
 __device__ __forceinline__ uint32_t piece_len(uint64_t buflen, uint64_t rel) {
   return rel < buflen ? (uint32_t)min((uint64_t)CK_PIECE, buflen - rel) : 0u;
@@ -893,9 +900,10 @@ __device__ __forceinline__ uint32_t ck_piece_info(const ZbChecksumWork &w, uint3
   return piece_len(buflen, pc.rel);
 }
 
-// x^1024 step with the lane's own copy of the tables: entry (j, b) of lane l at rep[((j * 256 + b) * 32) + l],
-// i.e. always in bank l -- four conflict-free lookups (the shared 4 KiB table cost ~3.5 wavefronts per lookup)
-__device__ __forceinline__ uint32_t ck_mul1024(const uint32_t *rep_lane, uint32_t r) {
+// multiply by the chain step with the lane's own copy of the tables: entry (j, b) of lane l at
+// rep[((j * 256 + b) * 32) + l], i.e. always in bank l -- four conflict-free lookups (a shared 4 KiB table
+// cost ~3.5 wavefronts per lookup)
+__device__ __forceinline__ uint32_t ck_mul_rep(const uint32_t *rep_lane, uint32_t r) {
   return rep_lane[(r & 255u) * 32u] ^ rep_lane[(256u + ((r >> 8) & 255u)) * 32u] ^ rep_lane[(512u + ((r >> 16) & 255u)) * 32u] ^
          rep_lane[(768u + (r >> 24)) * 32u];
 }
@@ -903,68 +911,63 @@ __device__ __forceinline__ uint32_t ck_mul_tab(const uint32_t *t /*[4][256]*/, u
   return t[r & 255u] ^ t[256 + ((r >> 8) & 255u)] ^ t[512 + ((r >> 16) & 255u)] ^ t[768 + (r >> 24)];
 }
 
-// Raw CRC-32 (KIND 0) or the Adler sums (KIND 1) of one warp's 4 KiB of a staged piece: lane i takes word i
-// of every 128-byte row; four independent chains (1 KiB each) hide the lookup latency and are joined with
-// table multiplications; one generic GF(2) multiplication per warp shifts the lanes into place.
-template <int KIND>
-__device__ __forceinline__ ZbCheck ck_warp_full(const uint8_t *base, uint32_t off, const uint32_t *rep_lane, const uint32_t *qt,
-                                                const uint32_t *lane_mul) {
+// CRC-32 of a FULL staged piece, this warp's share: lane i takes word i of the rows of four chains (row q + 64 k,
+// q = warp + 16 c), Horner inside a chain with the 64-row step, then the four chains are joined with table
+// multiplications.  What is left per warp and lane is one word whose weight is x^(1024 * (15 - warp)) * x^(32 * (31 -
+// lane)): the 16 x 32 words of a piece are a 2 KiB message with the piece's raw CRC, folded by k_piece_fold -- no
+// generic GF(2) multiplication and no cross-warp exchange here (both together were 36 % of this kernel's instructions).
+template <bool ALIGNED>
+__device__ __forceinline__ uint32_t ck_warp_crc_rows(const uint8_t *data, uint32_t mis, int warp, const uint32_t *rep_lane,
+                                                     const uint32_t *jt) {
+  const uint32_t o = mis + 4u * (uint32_t)zb_lane() + 128u * (uint32_t)warp;
+  uint32_t r[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (uint32_t k = 0; k < CK_ROWS / CK_CHAINS; k++) {
+    uint32_t wv[4];
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+      const uint32_t off = o + 128u * (CK_CHAINS * k + CK_WARPS * c);
+      wv[c] = ALIGNED ? *reinterpret_cast<const uint32_t *>(data + off) : zb_ld32_unaligned(data, off);
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+      if (k) r[c] = ck_mul_rep(rep_lane, r[c]);
+      r[c] ^= wv[c];
+    }
+  }
+  return ck_mul_tab(jt + 2 * 1024, r[0]) ^ ck_mul_tab(jt + 1024, r[1]) ^ ck_mul_tab(jt, r[2]) ^ r[3];
+}
+
+// Adler sums of one warp's WB bytes (2 or 4 KiB) of a staged piece: lane i takes word i of every 128-byte row, four
+// rows per step.
+template <uint32_t WB>
+__device__ __forceinline__ ZbCheck ck_warp_adler(const uint8_t *base, uint32_t off) {
   const int lane = zb_lane();
-  constexpr uint32_t QR = CK_WARP_BYTES / 512;   // rows per chain (8)
-  constexpr uint32_t QB = CK_WARP_BYTES / 4;     // bytes per chain (1024)
+  constexpr uint32_t QR = WB / 512;   // steps
+  constexpr uint32_t QB = WB / 4;     // bytes per quarter
   const uint32_t o = off + 4u * (uint32_t)lane, rel0 = 4u * (uint32_t)lane;
+  uint32_t a = 0;
+  uint64_t b = 0;
+#pragma unroll 2
+  for (uint32_t k = 0; k < QR; k++) {
+    const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (QR + k));
+    const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (2u * QR + k)), w3 = zb_ld32_unaligned(base, o + 128u * (3u * QR + k));
+    const uint32_t s0 = __dp4a(w0, 0x01010101u, 0u), s1 = __dp4a(w1, 0x01010101u, 0u);
+    const uint32_t s2 = __dp4a(w2, 0x01010101u, 0u), s3 = __dp4a(w3, 0x01010101u, 0u);
+    a += s0 + s1 + s2 + s3;
+    const uint32_t rel = rel0 + 128u * k;
+    // (WB - position) * byte sums fit in 32 bits per row: 4096 * 4 * 1020 < 2^32
+    b += (uint64_t)((4u * QB - rel) * s0 + (3u * QB - rel) * s1) + (uint64_t)((2u * QB - rel) * s2 + (QB - rel) * s3);
+    b -= (uint64_t)(__dp4a(w0, 0x03020100u, 0u) + __dp4a(w1, 0x03020100u, 0u) + __dp4a(w2, 0x03020100u, 0u) +
+                    __dp4a(w3, 0x03020100u, 0u));
+  }
   ZbCheck out;
   out.crc_raw = 0;
-  out.a_sum = out.b_sum = 0;
-  if (KIND == 0) {
-    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-#pragma unroll 2
-    for (uint32_t k = 0; k < QR; k++) {
-      const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (QR + k));
-      const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (2u * QR + k)), w3 = zb_ld32_unaligned(base, o + 128u * (3u * QR + k));
-      if (k) {
-        r0 = ck_mul1024(rep_lane, r0);
-        r1 = ck_mul1024(rep_lane, r1);
-        r2 = ck_mul1024(rep_lane, r2);
-        r3 = ck_mul1024(rep_lane, r3);
-      }
-      r0 ^= w0;
-      r1 ^= w1;
-      r2 ^= w2;
-      r3 ^= w3;
-    }
-    uint32_t r = ck_mul_tab(qt + 2 * 1024, r0) ^ ck_mul_tab(qt + 1024, r1) ^ ck_mul_tab(qt, r2) ^ r3;
-    r = zb_gf2_mul(r, lane_mul[32 - lane]);
-    out.crc_raw = zb_warp_xor(r);
-  } else {
-    uint32_t a = 0;
-    uint64_t b = 0;
-#pragma unroll 2
-    for (uint32_t k = 0; k < QR; k++) {
-      const uint32_t w0 = zb_ld32_unaligned(base, o + 128u * k), w1 = zb_ld32_unaligned(base, o + 128u * (QR + k));
-      const uint32_t w2 = zb_ld32_unaligned(base, o + 128u * (2u * QR + k)), w3 = zb_ld32_unaligned(base, o + 128u * (3u * QR + k));
-      const uint32_t s0 = __dp4a(w0, 0x01010101u, 0u), s1 = __dp4a(w1, 0x01010101u, 0u);
-      const uint32_t s2 = __dp4a(w2, 0x01010101u, 0u), s3 = __dp4a(w3, 0x01010101u, 0u);
-      a += s0 + s1 + s2 + s3;
-      const uint32_t rel = rel0 + 128u * k;
-      // (4 KiB - position) * byte sums fit in 32 bits per row: 4096 * 4 * 1020 < 2^32
-      b += (uint64_t)((4u * QB - rel) * s0 + (3u * QB - rel) * s1) + (uint64_t)((2u * QB - rel) * s2 + (QB - rel) * s3);
-      b -= (uint64_t)(__dp4a(w0, 0x03020100u, 0u) + __dp4a(w1, 0x03020100u, 0u) + __dp4a(w2, 0x03020100u, 0u) +
-                      __dp4a(w3, 0x03020100u, 0u));
-    }
-    out.a_sum = zb_warp_sum64((uint64_t)a);
-    out.b_sum = zb_warp_sum64(b);
-  }
+  out.a_sum = zb_warp_sum64((uint64_t)a);
+  out.b_sum = zb_warp_sum64(b);
   return out;
 }
 
-// Persistent CTAs (one per SM), a ring of 32 KiB shared-memory stages filled by TMA bulk copies: while the
-// 8 warps checksum stage k, the copy for k+1 is in flight.  Piece descriptors (source pointer, length, kind:
-// dependent global loads) are fetched 16..32 pieces ahead into a small shared ring so they never sit on the
-// critical path.  CRC-32 and Adler-32 are separate paths (a piece needs one of them): Adler is two dp4a per
-// word and runs at the copy rate; CRC-32 without a carry-less multiply is one table lookup per byte, which
-// is why the step tables are replicated per bank.
-#define CK_INFO 32
 // Adler sums of a ragged piece of n bytes (no tables): lane-strided words, the last 1..3 bytes by lane 0
 __device__ __forceinline__ ZbCheck ck_warp_adler_ragged(const uint8_t *base, uint32_t off, uint32_t n) {
   const int lane = zb_lane();
@@ -987,19 +990,31 @@ __device__ __forceinline__ ZbCheck ck_warp_adler_ragged(const uint8_t *base, uin
   return out;
 }
 
-// ADLER_ONLY: every piece wants Adler-32 (the adler32 entry points, batches of zlib members): no CRC tables in
-// shared memory, so three CTAs share an SM and three times as many bulk copies are in flight.
-#define CK_SM_TOTAL_ADLER (CK_SM_REP + 48 * 4 + CK_WARPS * 24 + 8 * CK_STAGES + 8)
+// Persistent CTAs, a ring of 32 KiB shared-memory stages filled by TMA bulk copies: while the 16 warps checksum
+// stage k, the copy for k+1 is in flight.  Piece descriptors (source pointer, length, kind: dependent global
+// loads) are fetched 16..32 pieces ahead into a small shared ring so they never sit on the critical path.
+// CRC-32 and Adler-32 are separate paths (a piece needs one of them): Adler is two dp4a per word and runs at the
+// copy rate; CRC-32 without a carry-less multiply is one table lookup per byte, which is why the step tables are
+// replicated per bank (one CTA per SM).  A full CRC piece leaves 16 x 32 partial words (ck_warp_crc_rows) in
+// w.partials for k_piece_fold; every other piece (Adler, ragged, empty) gets its piece_out entry here.
+// ADLER_ONLY: every piece wants Adler-32 (the adler32 entry points): no CRC tables in shared memory, so three
+// CTAs share an SM and three times as many bulk copies are in flight.
+#define CK_SM_TOTAL_ADLER (CK_SM_REP + CK_LMUL_WORDS * 4 + CK_WARPS * 24 + 8 * CK_STAGES + 8)
+#define CK_INFO 32
+#define CK_THREADS_ADLER 256   // the Adler-only CTAs: 8 warps x 4 KiB (three CTAs per SM)
 template <bool ADLER_ONLY>
-__global__ void __launch_bounds__(CK_THREADS, ADLER_ONLY ? 3 : 1)
+__global__ void __launch_bounds__(ADLER_ONLY ? CK_THREADS_ADLER : CK_THREADS, ADLER_ONLY ? 3 : 1)
     k_piece_checksum(ZbChecksumWork w) {
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int NT = ADLER_ONLY ? CK_THREADS_ADLER : CK_THREADS, NW = NT / 32;
+  constexpr uint32_t WB = CK_PIECE / NW;   // bytes per warp and piece on the Adler / ragged paths
   constexpr uint32_t LMUL_OFF = ADLER_ONLY ? CK_SM_REP : CK_SM_LMUL;
   uint32_t *rep = reinterpret_cast<uint32_t *>(smem + CK_SM_REP);
+  uint32_t *t1024 = reinterpret_cast<uint32_t *>(smem + CK_SM_T1024);
   uint32_t *qt = reinterpret_cast<uint32_t *>(smem + CK_SM_QT);
   uint32_t *lane_mul = reinterpret_cast<uint32_t *>(smem + LMUL_OFF);
-  uint64_t *part = reinterpret_cast<uint64_t *>(smem + LMUL_OFF + 48 * 4);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + LMUL_OFF + 48 * 4 + CK_WARPS * 24);
+  uint64_t *part = reinterpret_cast<uint64_t *>(smem + LMUL_OFF + CK_LMUL_WORDS * 4);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + LMUL_OFF + CK_LMUL_WORDS * 4 + CK_WARPS * 24);
   __shared__ const uint8_t *info_src[CK_INFO];
   __shared__ uint32_t info_len[CK_INFO];
   __shared__ uint32_t info_kind[CK_INFO];
@@ -1010,12 +1025,14 @@ __global__ void __launch_bounds__(CK_THREADS, ADLER_ONLY ? 3 : 1)
     zb_fence_mbar_init();
   }
   if (!ADLER_ONLY) {
-    const uint32_t *t = &w.tabs->mul1024[0][0];
-    for (int i = tid; i < 1024 * 32; i += CK_THREADS) rep[i] = t[i >> 5];   // entry e, lane l at rep[e * 32 + l]
-    const uint32_t *q = &w.tabs->ck_quart[0][0][0];
-    for (int i = tid; i < 3 * 1024; i += CK_THREADS) qt[i] = q[i];
+    const uint32_t *t = &w.tabs->mul64r[0][0];
+    for (int i = tid; i < 1024 * 32; i += NT) rep[i] = t[i >> 5];   // entry e, lane l at rep[e * 32 + l]
+    const uint32_t *t1 = &w.tabs->mul1024[0][0];
+    for (int i = tid; i < 1024; i += NT) t1024[i] = t1[i];
+    const uint32_t *q = &w.tabs->ck_join[0][0][0];
+    for (int i = tid; i < 3 * 1024; i += NT) qt[i] = q[i];
     if (tid < 33) lane_mul[tid] = w.tabs->lane_mul[tid];
-    if (tid >= 64 && tid < 72) lane_mul[33 + tid - 64] = w.tabs->ck_sub[tid - 64];
+    if (tid >= 64 && tid < 80) lane_mul[33 + tid - 64] = w.tabs->ck_sub[tid - 64];
   }
   if (tid >= 128 && tid < 128 + CK_INFO) {  // descriptors of this CTA's first 32 pieces
     const uint32_t j = (uint32_t)tid - 128u, pid = blockIdx.x + j * stride;
@@ -1044,26 +1061,31 @@ __global__ void __launch_bounds__(CK_THREADS, ADLER_ONLY ? 3 : 1)
       zb_mbar_wait(&bars[stage], (phases >> stage) & 1u);
       phases ^= 1u << stage;
     }
-    const uint32_t b0 = (uint32_t)warp * CK_WARP_BYTES, b1 = min(b0 + CK_WARP_BYTES, len);
-    ZbCheck c;
-    c.crc_raw = 0;
-    c.a_sum = c.b_sum = 0;
-    if (b0 < len) {
-      const uint32_t n = b1 - b0;
-      if (ADLER_ONLY) c = n == CK_WARP_BYTES ? ck_warp_full<1>(data, mis + b0, rep_lane, qt, lane_mul) : ck_warp_adler_ragged(data, mis + b0, n);
-      else if (n == CK_WARP_BYTES) c = kind ? ck_warp_full<1>(data, mis + b0, rep_lane, qt, lane_mul) : ck_warp_full<0>(data, mis + b0, rep_lane, qt, lane_mul);
-      else c = zb_warp_checksums(data, mis + b0, n, rep, lane_mul, 32u);   // a buffer's ragged last piece
-      const uint32_t after = len - b1;
-      if (after) {
-        if (!ADLER_ONLY && kind == 0)
-          c.crc_raw = zb_gf2_mul(c.crc_raw, (after & (CK_WARP_BYTES - 1u)) == 0u ? lane_mul[33 + after / CK_WARP_BYTES] : zb_xpow8(after));
-        else c.b_sum += (uint64_t)after * c.a_sum;
+    const bool full_crc = !ADLER_ONLY && len == CK_PIECE && kind == 0u;
+    if (full_crc) {
+      const uint32_t r = (mis & 3u) ? ck_warp_crc_rows<false>(data, mis, warp, rep_lane, qt) : ck_warp_crc_rows<true>(data, mis, warp, rep_lane, qt);
+      w.partials[(size_t)pid * CK_PARTIAL_WORDS + (uint32_t)tid] = r;
+    } else {
+      const uint32_t b0 = (uint32_t)warp * WB, b1 = min(b0 + WB, len);
+      ZbCheck c;
+      c.crc_raw = 0;
+      c.a_sum = c.b_sum = 0;
+      if (b0 < len) {
+        const uint32_t n = b1 - b0;
+        if (ADLER_ONLY || kind) c = n == WB ? ck_warp_adler<WB>(data, mis + b0) : ck_warp_adler_ragged(data, mis + b0, n);
+        else c = zb_warp_checksums(data, mis + b0, n, t1024, lane_mul);   // a buffer's ragged last piece
+        const uint32_t after = len - b1;
+        if (after) {
+          if (!ADLER_ONLY && kind == 0)
+            c.crc_raw = zb_gf2_mul(c.crc_raw, (after & (CK_WARP_BYTES - 1u)) == 0u ? lane_mul[33 + after / CK_WARP_BYTES] : zb_xpow8(after));
+          else c.b_sum += (uint64_t)after * c.a_sum;
+        }
       }
-    }
-    if (lane == 0) {
-      part[warp * 3 + 0] = c.crc_raw;
-      part[warp * 3 + 1] = c.a_sum;
-      part[warp * 3 + 2] = c.b_sum;
+      if (lane == 0) {
+        part[warp * 3 + 0] = c.crc_raw;
+        part[warp * 3 + 1] = c.a_sum;
+        part[warp * 3 + 2] = c.b_sum;
+      }
     }
     __syncthreads();  // every warp is done with this stage (and with info slot k)
     if (tid == 0) {
@@ -1071,17 +1093,19 @@ __global__ void __launch_bounds__(CK_THREADS, ADLER_ONLY ? 3 : 1)
       const uint32_t nk = k + CK_STAGES;
       if (pid + CK_STAGES * stride < w.n_pieces && info_len[nk % CK_INFO])
         zb_stage_chunk(smem + stage * CK_STAGE_BYTES, info_src[nk % CK_INFO], info_len[nk % CK_INFO], &bars[stage]);
-      uint32_t raw = 0;
-      uint64_t a = 0, b = 0;
-      for (int j = 0; j < CK_WARPS; j++) {
-        raw ^= (uint32_t)part[j * 3 + 0];
-        a += part[j * 3 + 1];
-        b += part[j * 3 + 2];
+      if (!full_crc) {
+        uint32_t raw = 0;
+        uint64_t a = 0, b = 0;
+        for (int j = 0; j < NW; j++) {
+          raw ^= (uint32_t)part[j * 3 + 0];
+          a += part[j * 3 + 1];
+          b += part[j * 3 + 2];
+        }
+        ZbChunkCheck cc;
+        cc.crc_raw = raw;
+        cc.adler = ((uint32_t)(b % ZB_ADLER_MOD) << 16) | (uint32_t)(a % ZB_ADLER_MOD);  // (B mod p, A mod p), not yet an Adler value
+        w.piece_out[pid] = cc;
       }
-      ZbChunkCheck cc;
-      cc.crc_raw = raw;
-      cc.adler = ((uint32_t)(b % ZB_ADLER_MOD) << 16) | (uint32_t)(a % ZB_ADLER_MOD);  // (B mod p, A mod p), not yet an Adler value
-      w.piece_out[pid] = cc;
     } else if (warp == 1 && (k % 16u) == 15u && lane < 16) {
       // descriptors for pieces k+17 .. k+32 go into the half of the ring that has just been used up
       const uint32_t j = k + 17u + (uint32_t)lane, npid = blockIdx.x + j * stride;
@@ -1092,6 +1116,40 @@ __global__ void __launch_bounds__(CK_THREADS, ADLER_ONLY ? 3 : 1)
       info_kind[j % CK_INFO] = kd;
     }
     __syncthreads();  // part[] and the descriptor ring are consistent for the next piece
+  }
+}
+
+// Second step of the CRC path: one warp per full piece folds its 16 x 32 partial words -- a 2 KiB message in the
+// usual lane-strided layout -- into the piece's raw CRC: 15 steps of x^1024, ONE generic GF(2) multiplication
+// per lane for the lane shifts, a warp XOR.  (6 % of the bytes of the first step, and as parallel as it.)
+__global__ void __launch_bounds__(256)
+    k_piece_fold(ZbChecksumWork w) {
+  __shared__ uint32_t tab[1024];
+  __shared__ uint32_t lmul[33];
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 1024; i += 256) tab[i] = (&w.tabs->mul1024[0][0])[i];
+  if (tid < 33) lmul[tid] = w.tabs->lane_mul[tid];
+  __syncthreads();
+  const uint32_t pid = blockIdx.x * 8u + (uint32_t)warp;
+  if (pid >= w.n_pieces) return;
+  const uint8_t *src = nullptr;
+  uint32_t kind = 0;
+  const uint32_t len = ck_piece_info(w, pid, src, kind);
+  if (len != CK_PIECE || kind != 0u) return;  // k_piece_checksum wrote this piece's entry itself
+  const uint32_t *m = w.partials + (size_t)pid * CK_PARTIAL_WORDS + (uint32_t)lane;
+  uint32_t r = 0;
+#pragma unroll 4
+  for (uint32_t row = 0; row < CK_WARPS; row++) {
+    const uint32_t v = __ldcs(m + row * 32u);
+    if (row) r = zb_mul1024(tab, r);
+    r ^= v;
+  }
+  r = zb_warp_xor(zb_gf2_mul(r, lmul[32 - lane]));
+  if (lane == 0) {
+    ZbChunkCheck cc;
+    cc.crc_raw = r;
+    cc.adler = 0;
+    w.piece_out[pid] = cc;
   }
 }
 
@@ -1516,6 +1574,7 @@ cudaError_t zb_setup_inflate_attrs() {
   // would be waiting for copies this thread has not queued yet.
   cudaFuncAttributes fa;
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_buffer_combine);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_piece_fold);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_buffer_combine_big);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_find_sync);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k_find_blocks);
@@ -1551,10 +1610,11 @@ cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s) {
   if (w.n_pieces) {
     if (!w.kinds && w.kind == 1) {  // Adler-32 throughout: the table-free instantiation, three CTAs per SM
       const uint32_t grid = std::min<uint32_t>(3u * (uint32_t)sms, w.n_pieces);
-      k_piece_checksum<true><<<grid, CK_THREADS, CK_SM_TOTAL_ADLER, s>>>(w);
+      k_piece_checksum<true><<<grid, CK_THREADS_ADLER, CK_SM_TOTAL_ADLER, s>>>(w);
     } else {
       const uint32_t grid = std::min<uint32_t>((uint32_t)sms, w.n_pieces);
       k_piece_checksum<false><<<grid, CK_THREADS, CK_SM_TOTAL, s>>>(w);
+      if (!(w.kinds == nullptr && w.kind == 1)) k_piece_fold<<<(w.n_pieces + 7) / 8, 256, 0, s>>>(w);
     }
   }
   k_buffer_combine<<<(w.n + 3) / 4, 128, 0, s>>>(w);

@@ -138,6 +138,7 @@ struct ZbChecksumWork {
   const ZbPiece *pieces;       // device [n_pieces]: ZB_CK_PIECE_BYTES pieces covering every buffer's capacity
   const uint32_t *first;       // device [n+1]: first piece of each buffer
   ZbChunkCheck *piece_out;     // device [n_pieces] scratch
+  uint32_t *partials;          // device [n_pieces * 512] scratch: the CRC path's per-warp, per-lane words of full pieces
   uint32_t *out;               // device [n] checksums, or null
   int *status;                 // device [n] or null: buffers with a non-zero status are skipped;
                                //   verify mode writes ZB_ERR_CHECKSUM / ZB_ERR_SIZE here
@@ -152,4 +153,5 @@ struct ZbChecksumWork {
                                //   instead of one warp (the host sets it when some buffer's capacity is that large)
 };
 #define ZB_CK_BIG_PIECES 2048u  // 64 MiB
+#define ZB_CK_PARTIAL_BYTES 2048  // per piece in ZbChecksumWork::partials
 cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s);
