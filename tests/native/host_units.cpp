@@ -14,6 +14,12 @@ void t_build_codebook(const uint16_t *hist, uint32_t chunk_len, int is_final, in
 }
 uint32_t t_gf2_mul(uint32_t a, uint32_t b) { return zb_gf2_mul(a, b); }
 uint32_t t_xpow8(uint64_t n) { return zb_xpow8(n); }
+uint32_t t_xpow8_t(uint64_t n) {
+  static ZbCrcTables T;
+  static int init = 0;
+  if (!init) { zb_crc_build_tables(&T); init = 1; }
+  return zb_xpow8_t(T.pow2, n);
+}
 uint32_t t_crc_combine(uint32_t a, uint32_t b, uint64_t lb) { return zb_crc32_combine(a, b, lb); }
 uint32_t t_adler_combine(uint32_t a, uint32_t b, uint64_t lb) { return zb_adler32_combine(a, b, lb); }
 int t_dist_code(uint32_t d) { return zb_dist_code(d); }

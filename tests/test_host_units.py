@@ -20,10 +20,11 @@ def hu():
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", SO, SRC])
     L = ctypes.CDLL(SO)
-    for f in ("t_gf2_mul", "t_xpow8", "t_crc_combine", "t_adler_combine", "t_crc32_lane_model", "t_crc32_piece_model", "t_adler32_model",
+    for f in ("t_gf2_mul", "t_xpow8", "t_xpow8_t", "t_crc_combine", "t_adler_combine", "t_crc32_lane_model", "t_crc32_piece_model", "t_adler32_model",
               "t_dist_base", "t_len_base"):
         getattr(L, f).restype = ctypes.c_uint32
     L.t_xpow8.argtypes = [ctypes.c_uint64]
+    L.t_xpow8_t.argtypes = [ctypes.c_uint64]
     L.t_crc_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
     L.t_adler_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
     L.t_crc32_lane_model.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
@@ -211,3 +212,5 @@ def test_crc_math(hu):
     big = 5 * 2 ** 32 + 12345
     assert hu.t_adler_combine(zlib.adler32(b"abc"), 1, 0) == zlib.adler32(b"abc")
     assert hu.t_xpow8(big) == hu.t_gf2_mul(hu.t_xpow8(5 * 2 ** 32), hu.t_xpow8(12345))
+    for n in [0, 1, 2, 3, 255, 32768, 65536, 65537, 100001, 2 ** 32 - 1, big, 2 ** 47 - 5]:
+        assert hu.t_xpow8_t(n) == hu.t_xpow8(n), n   # the table-driven form the kernels use

@@ -41,6 +41,19 @@ ZB_HD uint32_t zb_xpow8(uint64_t nbytes) {
   return result;
 }
 
+// The same with the squarings read from a table (ZbCrcTables::pow2): one multiplication per set bit of nbytes
+// beyond the first (zb_xpow8 spends 2 log2 n of them; a warp per 64 KiB buffer did little else).
+ZB_HD uint32_t zb_xpow8_t(const uint32_t *pow2, uint64_t nbytes) {
+  uint32_t result = 0x80000000u;  // x^0
+  bool first = true;
+  for (int j = 0; nbytes; j++, nbytes >>= 1)
+    if (nbytes & 1) {
+      result = first ? pow2[j] : zb_gf2_mul(result, pow2[j]);
+      first = false;
+    }
+  return result;
+}
+
 // raw CRC (init 0) of the single byte b followed by nothing: b(x) * x^8 mod P,
 // computed bitwise (no table) -- used only for <4-byte tails.
 ZB_HD uint32_t zb_crc_raw_byte(uint32_t state, uint32_t b) {
@@ -86,6 +99,7 @@ struct ZbCrcTables {
                         // [0] = x^(8 * 65536) mod P: shifts by one whole chunk
   uint32_t quart_mul[4];  // [k] = x^(8 * 2048 * k) mod P: shifts a quarter of a sub-chunk (16 rows of 128 B)
   uint32_t ck_sub[16];    // [k] = x^(8 * 2048 * k) mod P: shifts a warp's 2 KiB of a (ragged) checksum piece to the piece end
+  uint32_t pow2[48];      // [j] = x^(8 * 2^j) mod P: x^(8 n) as a product over the set bits of n (zb_xpow8_t)
   uint32_t piece_mul[16]; // [k] = x^(8 * 4096 * k) mod P: shifts the CRC of one of k_lz's 4 KiB pieces to the chunk end
   uint32_t pq_mul[4];     // [k] = x^(8 * 1024 * k) mod P: joins the four 1 KiB chains of such a piece
   // the checksum kernel's CRC path (zb_inflate.cu): a 32 KiB piece is 256 rows of 128 B; row q + 64 k belongs to chain q
@@ -107,6 +121,8 @@ inline void zb_crc_build_tables(ZbCrcTables *t) {
     for (int j = 0; j < 4; j++)
       for (uint32_t b = 0; b < 256; b++) t->mul64r[j][b] = zb_gf2_mul(b << (8 * j), c);
   }
+  t->pow2[0] = 0x00800000u;
+  for (int j = 1; j < 48; j++) t->pow2[j] = zb_gf2_mul(t->pow2[j - 1], t->pow2[j - 1]);
   for (int k = 0; k < 16; k++) t->piece_mul[k] = zb_xpow8(4096ull * (uint64_t)k);
   for (int k = 0; k < 4; k++) t->pq_mul[k] = zb_xpow8(1024ull * (uint64_t)k);
   for (int k = 1; k <= 3; k++) {

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 3)
       const uint32_t after = len - b1;
       if (after) {
         const uint32_t shift =
-            ((after & (LZ_PIECE_BYTES - 1)) == 0) ? lane_mul[LZ_LMUL_PIECE + after / LZ_PIECE_BYTES] : zb_xpow8(after);
+            ((after & (LZ_PIECE_BYTES - 1)) == 0) ? lane_mul[LZ_LMUL_PIECE + after / LZ_PIECE_BYTES] : zb_xpow8_t(tabs->pow2, after);
         c.crc_raw = zb_gf2_mul(c.crc_raw, shift);
         c.b_sum += (uint64_t)after * c.a_sum;
       }
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
         c = zb_warp_checksums(data, off0 + b0, n, crc_tab, lane_mul);
         const uint32_t after = len - b1;
         if (after) {
-          const uint32_t shift = ((after & (ZB_SUB_BYTES - 1)) == 0) ? lane_mul[33 + after / ZB_SUB_BYTES] : zb_xpow8(after);
+          const uint32_t shift = ((after & (ZB_SUB_BYTES - 1)) == 0) ? lane_mul[33 + after / ZB_SUB_BYTES] : zb_xpow8_t(tabs->pow2, after);
           c.crc_raw = zb_gf2_mul(c.crc_raw, shift);
           c.b_sum += (uint64_t)after * c.a_sum;
         }
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(128)
     const ZbChunkCheck cc = w.chk[c];
     if (w.data_format == ZB_DF_ZLIB) ad = zb_adler32_combine(ad, cc.adler, l);
     else if (w.data_format == ZB_DF_GZIP)
-      raw = zb_gf2_mul(raw, l == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8(l)) ^ cc.crc_raw;
+      raw = zb_gf2_mul(raw, l == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8_t(w.tabs->pow2, l)) ^ cc.crc_raw;
     bytes += l;
   }
   if (c1 - c0 > 1u) {
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(128)
       const uint64_t r_bytes = __shfl_down_sync(0xffffffffu, bytes, o);
       if ((lane & (uint32_t)(2 * o - 1)) == 0u && r_bytes) {
         if (w.data_format == ZB_DF_ZLIB) ad = zb_adler32_combine(ad, r_ad, r_bytes);
-        else if (w.data_format == ZB_DF_GZIP) raw = zb_gf2_mul(raw, zb_xpow8(r_bytes)) ^ r_raw;
+        else if (w.data_format == ZB_DF_GZIP) raw = zb_gf2_mul(raw, zb_xpow8_t(w.tabs->pow2, r_bytes)) ^ r_raw;
         bytes += r_bytes;
       }
     }
@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(128)
     uint32_t v = 0;
     if (w.data_format == ZB_DF_ZLIB) v = ad;
     else if (w.data_format == ZB_DF_GZIP)
-      v = ~(zb_gf2_mul(bytes == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8(bytes), 0xffffffffu) ^ raw);
+      v = ~(zb_gf2_mul(bytes == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8_t(w.tabs->pow2, bytes), 0xffffffffu) ^ raw);
     w.member_check[m] = v;
     w.member_isize[m] = (uint32_t)bytes;
   }

@@ -1077,7 +1077,7 @@ __global__ void __launch_bounds__(ADLER_ONLY ? CK_THREADS_ADLER : CK_THREADS, AD
         const uint32_t after = len - b1;
         if (after) {
           if (!ADLER_ONLY && kind == 0)
-            c.crc_raw = zb_gf2_mul(c.crc_raw, (after & (CK_WARP_BYTES - 1u)) == 0u ? lane_mul[33 + after / CK_WARP_BYTES] : zb_xpow8(after));
+            c.crc_raw = zb_gf2_mul(c.crc_raw, (after & (CK_WARP_BYTES - 1u)) == 0u ? lane_mul[33 + after / CK_WARP_BYTES] : zb_xpow8_t(w.tabs->pow2, after));
           else c.b_sum += (uint64_t)after * c.a_sum;
         }
       }
@@ -1130,33 +1130,32 @@ __global__ void __launch_bounds__(256)
   for (int i = tid; i < 1024; i += 256) tab[i] = (&w.tabs->mul1024[0][0])[i];
   if (tid < 33) lmul[tid] = w.tabs->lane_mul[tid];
   __syncthreads();
-  const uint32_t pid = blockIdx.x * 8u + (uint32_t)warp;
-  if (pid >= w.n_pieces) return;
-  const uint8_t *src = nullptr;
-  uint32_t kind = 0;
-  const uint32_t len = ck_piece_info(w, pid, src, kind);
-  if (len != CK_PIECE || kind != 0u) return;  // k_piece_checksum wrote this piece's entry itself
-  const uint32_t *m = w.partials + (size_t)pid * CK_PARTIAL_WORDS + (uint32_t)lane;
-  uint32_t r = 0;
-#pragma unroll 4
-  for (uint32_t row = 0; row < CK_WARPS; row++) {
-    const uint32_t v = __ldcs(m + row * 32u);
-    if (row) r = zb_mul1024(tab, r);
-    r ^= v;
-  }
-  r = zb_warp_xor(zb_gf2_mul(r, lmul[32 - lane]));
-  if (lane == 0) {
-    ZbChunkCheck cc;
-    cc.crc_raw = r;
-    cc.adler = 0;
-    w.piece_out[pid] = cc;
+  for (uint32_t pid = blockIdx.x * 8u + (uint32_t)warp; pid < w.n_pieces; pid += gridDim.x * 8u) {
+    const uint8_t *src = nullptr;
+    uint32_t kind = 0;
+    const uint32_t len = ck_piece_info(w, pid, src, kind);
+    if (len != CK_PIECE || kind != 0u) continue;  // k_piece_checksum wrote this piece's entry itself
+    const uint32_t *m = w.partials + (size_t)pid * CK_PARTIAL_WORDS + (uint32_t)lane;
+    uint32_t v[CK_WARPS];
+#pragma unroll
+    for (uint32_t row = 0; row < CK_WARPS; row++) v[row] = __ldcs(m + row * 32u);
+    uint32_t r = v[0];
+#pragma unroll
+    for (uint32_t row = 1; row < CK_WARPS; row++) r = zb_mul1024(tab, r) ^ v[row];
+    r = zb_warp_xor(zb_gf2_mul(r, lmul[32 - lane]));
+    if (lane == 0) {
+      ZbChunkCheck cc;
+      cc.crc_raw = r;
+      cc.adler = 0;
+      w.piece_out[pid] = cc;
+    }
   }
 }
 
 // raw CRC (init 0) / Adler sums of a whole buffer -> the checksum value; store and, in verify mode, compare
 __device__ __forceinline__ void ck_finish(const ZbChecksumWork &w, uint32_t i, int kind, uint32_t r, uint64_t a, uint64_t b,
                                           uint64_t buflen) {
-  const uint32_t v = kind == 0 ? ~(zb_gf2_mul(buflen == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8(buflen), 0xffffffffu) ^ r)
+  const uint32_t v = kind == 0 ? ~(zb_gf2_mul(buflen == ZB_CHUNK_BYTES ? w.tabs->sub_mul[0] : zb_xpow8_t(w.tabs->pow2, buflen), 0xffffffffu) ^ r)
                                : zb_adler_from_sums(a % ZB_ADLER_MOD, b % ZB_ADLER_MOD, buflen);
   if (w.out) w.out[i] = v;
   if (w.expect) {
@@ -1196,16 +1195,16 @@ __global__ void __launch_bounds__(128)
       const uint32_t raw = w.piece_out[p0 + k].crc_raw;
       if (k >= 32) {
         if (l == CK_PIECE) {
-          if (!step) step = zb_xpow8(32ull * CK_PIECE);
+          if (!step) step = zb_xpow8_t(w.tabs->pow2, 32ull * CK_PIECE);
           r = zb_gf2_mul(r, step);
         } else {
-          r = zb_gf2_mul(r, zb_xpow8(31ull * CK_PIECE + l));
+          r = zb_gf2_mul(r, zb_xpow8_t(w.tabs->pow2, 31ull * CK_PIECE + l));
         }
       }
       r ^= raw;
       end = (uint64_t)k * CK_PIECE + l;
     }
-    if ((uint32_t)lane < np && end < buflen) r = zb_gf2_mul(r, zb_xpow8(buflen - end));
+    if ((uint32_t)lane < np && end < buflen) r = zb_gf2_mul(r, zb_xpow8_t(w.tabs->pow2, buflen - end));
     r = zb_warp_xor(r);
   } else {
     for (uint32_t k = (uint32_t)lane; k < np; k += 32) {
@@ -1254,16 +1253,16 @@ __global__ void __launch_bounds__(CKB_THREADS)
       const uint32_t raw = w.piece_out[p0 + k].crc_raw;
       if (k >= CKB_THREADS) {
         if (l == CK_PIECE) {
-          if (!step) step = zb_xpow8((uint64_t)CKB_THREADS * CK_PIECE);
+          if (!step) step = zb_xpow8_t(w.tabs->pow2, (uint64_t)CKB_THREADS * CK_PIECE);
           r = zb_gf2_mul(r, step);
         } else {
-          r = zb_gf2_mul(r, zb_xpow8((uint64_t)(CKB_THREADS - 1) * CK_PIECE + l));
+          r = zb_gf2_mul(r, zb_xpow8_t(w.tabs->pow2, (uint64_t)(CKB_THREADS - 1) * CK_PIECE + l));
         }
       }
       r ^= raw;
       end = (uint64_t)k * CK_PIECE + l;
     }
-    if (t < np && end < buflen) r = zb_gf2_mul(r, zb_xpow8(buflen - end));
+    if (t < np && end < buflen) r = zb_gf2_mul(r, zb_xpow8_t(w.tabs->pow2, buflen - end));
     r = zb_warp_xor(r);
   } else {
     for (uint32_t k = t; k < np; k += CKB_THREADS) {
@@ -1614,7 +1613,7 @@ cudaError_t zb_launch_checksum(const ZbChecksumWork &w, cudaStream_t s) {
     } else {
       const uint32_t grid = std::min<uint32_t>((uint32_t)sms, w.n_pieces);
       k_piece_checksum<false><<<grid, CK_THREADS, CK_SM_TOTAL, s>>>(w);
-      if (!(w.kinds == nullptr && w.kind == 1)) k_piece_fold<<<(w.n_pieces + 7) / 8, 256, 0, s>>>(w);
+      k_piece_fold<<<std::min<uint32_t>((w.n_pieces + 7) / 8, 8u * (uint32_t)sms), 256, 0, s>>>(w);
     }
   }
   k_buffer_combine<<<(w.n + 3) / 4, 128, 0, s>>>(w);
