@@ -785,6 +785,40 @@ def measure_uncompress(e, d_comp, comp_offs, out_sizes, steps, warmup, do_e2e=Tr
     return res
 
 
+def run_checksums(e, args):
+    """Standalone crc32 / adler32: 65 536 x 64 KiB buffers and the same 4 GiB as ONE
+    buffer, device-resident, kernel times from the library's own CUDA events; values checked against zlib."""
+    import zlib
+    t, ctx = e.torch, e.ctx
+    n = args.blocks
+    g = t.Generator(device=e.dev)
+    g.manual_seed(1)
+    d_src = t.randint(0, 256, (n * BLOCK,), dtype=t.uint8, device=e.dev, generator=g)
+    t.cuda.synchronize()
+    head = d_src[:BLOCK].cpu().numpy().tobytes()
+    whole = d_src[:64 << 20].cpu().numpy().tobytes() if n * BLOCK >= (64 << 20) else None
+    out = {"workload": "crc32 / adler32 of %d x 64 KiB buffers and of one %d MiB buffer, device-resident" % (n, n // 16),
+           "cpu_1_thread": cpu_checksum_legs() if not args.no_cpu else None}
+    for label, offs in (("batch", np.arange(n + 1, dtype=np.uint64) * BLOCK), ("one_buffer", np.array([0, n * BLOCK], dtype=np.uint64))):
+        for kind in ("crc32", "adler32"):
+            times = []
+            for _ in range(6):   # the first calls also pay for the piece table upload and cold TLBs
+                vals = ctx.checksum_batch_device(d_src.data_ptr(), offs, kind)
+                times.append(ctx.timing()["checksum_ms"])
+            ms = float(np.median(times[2:]))
+            if label == "batch":
+                assert int(vals[0]) == (zlib.crc32(head) if kind == "crc32" else zlib.adler32(head))
+            elif whole is not None and n * BLOCK == (64 << 20):
+                assert int(vals[0]) == (zlib.crc32(whole) if kind == "crc32" else zlib.adler32(whole))
+            gbs = n * BLOCK / (ms / 1e3) / 1e9
+            out["%s_%s" % (kind, label)] = {"ms": ms, "GB_s": gbs, "roofline": {
+                "bound": "hbm", "kernel": "k_piece_checksum (+ fold / combine)", "achieved": gbs, "peak": e.hbm_peak, "unit": "GB/s",
+                "frac": gbs / e.hbm_peak, "peak_source": e.peak_source, "algorithmic_bytes_per_launch": n * BLOCK, "kernel_ms": ms,
+                "traffic": None}}
+    del d_src
+    return out
+
+
 def strip(d):
     return {k: v for k, v in d.items() if not k.startswith("_")}
 
@@ -1183,7 +1217,8 @@ def main():
                     extras["pcie"] = pcie_peaks(e)
                 for name, fn in (("c1", lambda: run_c1(e, args)), ("c3", lambda: run_c3(e, args, xs, 3)),
                                  ("c4", lambda: run_c4(e, args, xs, 3)), ("c5", lambda: run_c5(e, args, xs, 3)),
-                                 ("large_member", lambda: run_large_member(e, args))):
+                                 ("large_member", lambda: run_large_member(e, args)),
+                                 ("checksums", lambda: run_checksums(e, args))):
                     e.torch.cuda.empty_cache()
                     try:
                         extras[name] = strip(fn())
