@@ -437,7 +437,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 3)
 #define LZ2_SM_TOTAL (LZ2_SM_BAR + 16)
 static_assert(2 * (LZ2_SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
 
+#ifndef LZ2_STATIC_BITS
 #define LZ2_STATIC_BITS 13                                          // direct-mapped static tables: 8192 x u16 = one own table's size
+#endif
 // own bucket = the top 11 bits of the product, static entry = the top 13
 __device__ __forceinline__ uint32_t lz2_hash_mul(uint32_t v) { return v * 0x9E3779B1u; }
 __device__ __forceinline__ uint32_t lz2_hash(uint32_t v) { return lz2_hash_mul(v) >> (32 - LZ2_BUCKET_BITS); }
@@ -450,10 +452,10 @@ __device__ __forceinline__ uint2 lz2_push(uint2 b, uint32_t e) {
   return r;
 }
 
-__device__ __forceinline__ void lz2_clear_table(uint2 *tab) {
+__device__ __forceinline__ void lz2_clear_table(uint2 *tab, int bytes = LZ2_BUCKETS * 8) {
   const uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u);
   uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-  for (int i = zb_lane(); i < LZ2_BUCKETS / 2; i += 32) __stcg(&t4[i], ff);
+  for (int i = zb_lane(); i < bytes / 16; i += 32) __stcg(&t4[i], ff);
 }
 
 // Insert the window's positions (qwin + lane, for lanes with `can`) into a table in stream order;
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2)
       const uint32_t nseg = (rlen + LZ2_SEG_BYTES - 1) / LZ2_SEG_BYTES;  // segments of the region; the last is never history
       for (uint32_t sg = (uint32_t)warp; sg + 1 < nseg; sg += ZB_WARPS_PER_CHUNK) {
         uint2 *tab = stat + (size_t)sg * LZ2_BUCKETS;
-        lz2_clear_table(tab);
+        lz2_clear_table(tab, (1 << LZ2_STATIC_BITS) * 2);
         __syncwarp();
         uint16_t *tab16 = reinterpret_cast<uint16_t *>(tab);
         const uint32_t q0 = sg * LZ2_SEG_BYTES, q1 = q0 + LZ2_SEG_BYTES;  // a full segment (only the last one can be short)
