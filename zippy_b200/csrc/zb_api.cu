@@ -1270,6 +1270,16 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
     w.gate_first = d_gate + 1 + ng;
     w.n_gates = (uint32_t)ng;
     CK(zb_launch_inflate(w, s));
+    // from here on the kernel may be waiting for copies: if this function leaves early (a failed copy, a failed
+    // enqueue), open every gate so that the kernel drains instead of waiting out its timeout
+    struct GateRelease {
+      zb200_ctx *ctx;
+      uint32_t *word;
+      bool armed;
+      ~GateRelease() {
+        if (armed) ctx->memops.write32((CUstream)ctx->h2d_stream, (CUdeviceptr)(uintptr_t)word, 0xffffffffu, 0);
+      }
+    } gate_release{ctx, d_gate, true};
     // gzip.nim:80-88 / zippy.nim:154-162: checksum, then size, of every member that inflated (after the whole
     // launch: 2.4 ms per 4 GiB, under the last groups' copy-out)
     ZbChecksumWork cw;
@@ -1338,6 +1348,7 @@ int uncompress_host_pipelined(zb200_ctx *ctx, const uint8_t *h_src, const std::v
       }
       for (auto &ev : tl) cudaEventDestroy(ev);
     }
+    gate_release.armed = false;   // every group's copy-in (and its gate word) is queued
   }
   for (size_t gi = 0; gi < ng && !gated; gi++) {
     const size_t m0 = gb[gi], m1 = gb[gi + 1], nm = m1 - m0;
