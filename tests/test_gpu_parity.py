@@ -366,13 +366,19 @@ def test_host_uncompress_member_groups(z, o, corpus, monkeypatch, gated):
     base = np.frombuffer(b"".join(items), dtype=np.uint8)
     offs = np.zeros(len(items) + 1, dtype=np.uint64)
     offs[1:] = np.cumsum([len(x) for x in items])
-    out, do, lens, st = ctx.uncompress_batch(base, offs, z.dfDetect)
-    for i, r in enumerate(raws):
-        if i == 3:
-            assert st[i] != 0
-            continue
-        assert st[i] == 0, (i, st[i])
-        assert out[int(do[i]):int(do[i]) + int(lens[i])].tobytes() == r, i
+    for registered in (False, True):   # pageable source, then a page-locked one (the destination stays pageable)
+        if registered:
+            base = base.copy()
+            z.host_register(base.ctypes.data, base.nbytes)
+        out, do, lens, st = ctx.uncompress_batch(base, offs, z.dfDetect)
+        if registered:
+            z.host_unregister(base.ctypes.data)
+        for i, r in enumerate(raws):
+            if i == 3:
+                assert st[i] != 0
+                continue
+            assert st[i] == 0, (i, st[i])
+            assert out[int(do[i]):int(do[i]) + int(lens[i])].tobytes() == r, i
     ctx.close()
 
 

@@ -72,8 +72,10 @@ def edge_inputs(seed=1234):
     xs = [b"", b"a", b"ab", b"abc", b"abcd", b"aaaa", b"a" * 5, b"a" * 258, b"a" * 259, b"a" * 300,
           b"ab" * 200, b"abc" * 1000, bytes(range(256)), bytes(range(256)) * 20,
           b"\x00" * 65535, b"\x00" * 65536, b"\x00" * 65537, b"\xff" * 100000]
-    for n in (1, 14, 15, 16, 31, 32, 33, 63, 64, 65, 2047, 2048, 2049, 4095, 8191, 8192, 8193,
-              32767, 32768, 32769, 65535, 65536, 65537, 131072, 200001):
+    # (4 KiB = a parse piece of the level-1 matcher, 32 KiB = one of its two phases, 8 KiB = a packer sub-chunk)
+    for n in (1, 14, 15, 16, 31, 32, 33, 63, 64, 65, 2047, 2048, 2049, 4095, 4096, 4097, 8191, 8192, 8193,
+              28671, 28672, 28673, 32767, 32768, 32769, 33791, 33792, 33793, 36863, 36864, 36865, 61439, 61440, 61441,
+              65535, 65536, 65537, 131072, 200001):
         xs.append(bytes(rng.randrange(256) for _ in range(n)))                    # incompressible
         xs.append(bytes(rng.choice(b"abcdefgh ") for _ in range(n)))              # low entropy
     for _ in range(8):
