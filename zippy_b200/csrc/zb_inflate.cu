@@ -1115,7 +1115,9 @@ __global__ void __launch_bounds__(ADLER_ONLY ? CK_THREADS_ADLER : CK_THREADS, AD
       info_src[j % CK_INFO] = nsrc;
       info_kind[j % CK_INFO] = kd;
     }
-    __syncthreads();  // part[] and the descriptor ring are consistent for the next piece
+    // part[] and the descriptor ring are consistent for the next piece.  A full CRC piece touches neither (its words
+    // went to w.partials), so between descriptor refreshes the warps may run on into the next stage.
+    if (!full_crc || (k % 16u) == 15u) __syncthreads();
   }
 }
 
