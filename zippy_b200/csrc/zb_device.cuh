@@ -29,6 +29,9 @@ __device__ __forceinline__ void zb_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zb_smem_addr(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void zb_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(zb_smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void zb_mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"

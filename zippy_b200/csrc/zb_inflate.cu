@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(INF_THREADS, INF_MIN_CTAS)
 #define CK_LMUL_WORDS 52
 #define CK_SM_PART (CK_SM_LMUL + CK_LMUL_WORDS * 4)
 #define CK_SM_BAR (CK_SM_PART + CK_WARPS * 24)
-#define CK_SM_TOTAL (CK_SM_BAR + 8 * CK_STAGES + 8)
+#define CK_SM_TOTAL (CK_SM_BAR + 16 * CK_STAGES + 8)
 static_assert(CK_SM_TOTAL <= 232448, "one CTA per SM");
 static_assert(CK_ROWS == 4 * CK_CHAINS, "four rows per chain");
 static_assert(CK_PARTIAL_WORDS * 4 == ZB_CK_PARTIAL_BYTES, "scratch size");
@@ -999,7 +999,7 @@ __device__ __forceinline__ ZbCheck ck_warp_adler_ragged(const uint8_t *base, uin
 // w.partials for k_piece_fold; every other piece (Adler, ragged, empty) gets its piece_out entry here.
 // ADLER_ONLY: every piece wants Adler-32 (the adler32 entry points): no CRC tables in shared memory, so three
 // CTAs share an SM and three times as many bulk copies are in flight.
-#define CK_SM_TOTAL_ADLER (CK_SM_REP + CK_LMUL_WORDS * 4 + CK_WARPS * 24 + 8 * CK_STAGES + 8)
+#define CK_SM_TOTAL_ADLER (CK_SM_REP + CK_LMUL_WORDS * 4 + CK_WARPS * 24 + 16 * CK_STAGES + 8)
 #define CK_INFO 32
 #define CK_THREADS_ADLER 256   // the Adler-only CTAs: 8 warps x 4 KiB (three CTAs per SM)
 template <bool ADLER_ONLY>
@@ -1021,7 +1021,10 @@ __global__ void __launch_bounds__(ADLER_ONLY ? CK_THREADS_ADLER : CK_THREADS, AD
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t stride = gridDim.x;
   if (tid == 0) {
-    for (int i = 0; i < CK_STAGES; i++) zb_mbar_init(&bars[i], 1);
+    for (int i = 0; i < CK_STAGES; i++) {
+      zb_mbar_init(&bars[i], 1);
+      zb_mbar_init(&bars[CK_STAGES + i], NW);   // "stage i has been read by every warp" (full CRC pieces)
+    }
     zb_fence_mbar_init();
   }
   if (!ADLER_ONLY) {
@@ -1051,6 +1054,7 @@ __global__ void __launch_bounds__(ADLER_ONLY ? CK_THREADS_ADLER : CK_THREADS, AD
   }
   const uint32_t *rep_lane = rep + lane;
   uint32_t k = 0, phases = 0;  // bit s of `phases` = parity of the next completion of stage s
+  uint32_t ephases = 0;        // the same for the stages' "read by every warp" barriers
   for (uint32_t pid = blockIdx.x; pid < w.n_pieces; pid += stride, k++) {
     const uint32_t stage = k % CK_STAGES;
     const uint32_t len = info_len[k % CK_INFO], kind = info_kind[k % CK_INFO];
@@ -1087,7 +1091,16 @@ __global__ void __launch_bounds__(ADLER_ONLY ? CK_THREADS_ADLER : CK_THREADS, AD
         part[warp * 3 + 2] = c.b_sum;
       }
     }
-    __syncthreads();  // every warp is done with this stage (and with info slot k)
+    // every warp is done with this stage (and with info slot k) before it is refilled.  After a full CRC piece only
+    // thread 0 has to know: the warps signal an mbarrier and run on into the other stage
+    if (full_crc && (k % 16u) != 15u) {
+      __syncwarp();
+      if (lane == 0) zb_mbar_arrive(&bars[CK_STAGES + stage]);
+      if (tid == 0) zb_mbar_wait(&bars[CK_STAGES + stage], (ephases >> stage) & 1u);
+      ephases ^= 1u << stage;
+    } else {
+      __syncthreads();
+    }
     if (tid == 0) {
       // refill this stage with the piece CK_STAGES iterations ahead
       const uint32_t nk = k + CK_STAGES;
