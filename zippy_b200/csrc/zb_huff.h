@@ -64,19 +64,30 @@ ZB_HD_NOINLINE void zb_huff_lengths(const uint32_t *freq, int n, int limit, uint
     lens[s == 0 ? 1 : 0] = 1;
     return;
   }
-  // shell sort (Ciura gaps) on packed keys: deterministic tie-break by symbol index
-  const int gaps[6] = {132, 57, 23, 10, 4, 1};
-  for (int g = 0; g < 6; g++) {
-    int gap = gaps[g];
-    for (int i = gap; i < m; i++) {
-      uint32_t t = key[i];
-      int j = i;
-      while (j >= gap && key[j - gap] > t) {
-        key[j] = key[j - gap];
-        j -= gap;
+  // ascending by (frequency, symbol): the keys are in symbol order already, so a STABLE sort on the frequency
+  // alone does it -- 6-bit counting passes through `a` (frequencies are below 2^17: a chunk is 64 KiB; the
+  // code-length alphabet's below 2^9).  (A shell sort was a third of this routine's instructions.)
+  {
+    uint32_t maxf = 0;
+    for (int i = 0; i < m; i++) maxf |= key[i] >> 9;
+    uint32_t *from = key, *to = a;
+    for (int shift = 9; (maxf >> (shift - 9)) != 0u; shift += 6) {
+      uint16_t cnt6[64];
+      for (int b = 0; b < 64; b++) cnt6[b] = 0;
+      for (int i = 0; i < m; i++) cnt6[(from[i] >> shift) & 63u]++;
+      uint16_t run = 0;
+      for (int b = 0; b < 64; b++) {
+        const uint16_t c = cnt6[b];
+        cnt6[b] = run;
+        run = (uint16_t)(run + c);
       }
-      key[j] = t;
+      for (int i = 0; i < m; i++) to[cnt6[(from[i] >> shift) & 63u]++] = from[i];
+      uint32_t *t = from;
+      from = to;
+      to = t;
     }
+    if (from != key)
+      for (int i = 0; i < m; i++) key[i] = from[i];
   }
   for (int i = 0; i < m; i++) a[i] = key[i] >> 9;
   // Moffat & Katajainen, "In-place calculation of minimum-redundancy codes" (1995)
@@ -147,13 +158,18 @@ struct ZbBitSink {
   uint8_t *p;
   uint32_t nbits;
 };
-ZB_HD void zb_put_bits(ZbBitSink *s, uint32_t v, int n) {
-  for (int i = 0; i < n; i++) {
-    uint32_t pos = s->nbits + (uint32_t)i;
-    if ((pos & 7u) == 0) s->p[pos >> 3] = 0;
-    s->p[pos >> 3] |= (uint8_t)(((v >> i) & 1u) << (pos & 7u));
-  }
+ZB_HD void zb_put_bits(ZbBitSink *s, uint32_t v, int n) {  // n <= 16, LSB first; whole bytes at a time
+  uint32_t pos = s->nbits;
   s->nbits += (uint32_t)n;
+  v &= (1u << n) - 1u;
+  while (n > 0) {
+    const uint32_t sh = pos & 7u, take = 8u - sh < (uint32_t)n ? 8u - sh : (uint32_t)n;
+    const uint8_t old = sh ? s->p[pos >> 3] : (uint8_t)0;
+    s->p[pos >> 3] = (uint8_t)(old | ((v & ((1u << take) - 1u)) << sh));
+    v >>= take;
+    pos += take;
+    n -= (int)take;
+  }
 }
 
 // Build everything the packer needs for one chunk.
@@ -320,17 +336,16 @@ ZB_HD_NOINLINE void zb_build_codebook(const uint16_t *hist, uint32_t chunk_len, 
   }
   cb->hdr_bits = sink.nbits;
   // per-warp token bit ranges
+  // (one cost per symbol = code length + extra bits, in histogram order, so the eight sums are plain dot products)
+  uint8_t cost[ZB_HIST_SYMS];
+  for (int s = 0; s < ZB_NUM_LITLEN; s++) cost[s] = (uint8_t)(lens[s] + (s > 256 ? len_extra[s - 257] : 0));
+  for (int s = 0; s < ZB_NUM_DIST; s++) cost[ZB_NUM_LITLEN + s] = (uint8_t)(lens[ZB_NUM_LITLEN + s] + dist_extra[s]);
   uint32_t pos = sink.nbits;
   for (int w = 0; w < ZB_WARPS_PER_CHUNK; w++) {
     cb->warp_bit_start[w] = pos;
     const uint16_t *h = hist + w * ZB_HIST_SYMS;
     uint32_t bits = 0;
-    for (int s = 0; s < ZB_NUM_LITLEN; s++) {
-      bits += (uint32_t)h[s] * lens[s];
-      if (s > 256) bits += (uint32_t)h[s] * len_extra[s - 257];
-    }
-    for (int s = 0; s < ZB_NUM_DIST; s++)
-      bits += (uint32_t)h[ZB_NUM_LITLEN + s] * ((uint32_t)lens[ZB_NUM_LITLEN + s] + dist_extra[s]);
+    for (int s = 0; s < ZB_HIST_SYMS; s++) bits += (uint32_t)h[s] * cost[s];
     pos += bits;
   }
   cb->eob_bit_start = pos;
