@@ -1,6 +1,7 @@
 """CPU-only unit tests of the host/device-shared maths in zippy_b200/csrc/zb_huff.h,
 zb_crc.h, zb_common.h (compiled here with g++; the GPU kernels include the same code)."""
 import ctypes
+import hashlib
 import os
 import random
 import subprocess
@@ -190,6 +191,33 @@ def test_codebook_dynamic_header_decodes_with_zlib(hu):
             if not is_final:
                 out += b"\x01\x00\x00\xff\xff"  # terminate the stream for zlib
             assert zlib.decompress(bytes(out), -15) == data
+
+
+def test_codebooks_are_pinned(hu):
+    """The codebook of a histogram is part of the compressed bytes: a change to zb_huff.h that is meant to be an
+    optimisation (the counting sort, the byte-wise header writer) must leave every codebook as it was.  200 seeded
+    histograms (dense, sparse, text-like with matches, a single symbol, empty), digest of the ZbCodebook structs."""
+    nbytes = hu.t_codebook_size()
+    rng = np.random.default_rng(2024)
+    h256 = hashlib.sha256()
+    for t in range(200):
+        kind = t % 5
+        h = np.zeros((8, 316), dtype=np.uint16)
+        if kind == 0:
+            h[:, :256] = rng.integers(0, 40, (8, 256))
+        elif kind == 1:
+            h[:, rng.integers(0, 286, 20)] = rng.integers(1, 3000, (8, 20))
+        elif kind == 2:
+            h[:, 32:127] = rng.integers(0, 200, (8, 95))
+            h[:, 257:280] = rng.integers(0, 60, (8, 23))
+            h[:, 286:316] = rng.integers(0, 50, (8, 30))
+        elif kind == 3:
+            h[0, rng.integers(0, 256)] = rng.integers(1, 8000)
+        ln = min(int(h[:, :256].sum() + 3 * h[:, 257:286].sum()), 65536)
+        cb = ctypes.create_string_buffer(nbytes)
+        hu.t_build_codebook(h.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), ln, t & 1, -1, cb)
+        h256.update(cb.raw)
+    assert h256.hexdigest() == "a2273583dc12be3211016a13c0ec7138f76bd9e11c3531d6855fe4cc59ea0679"
 
 
 def test_crc_math(hu):
