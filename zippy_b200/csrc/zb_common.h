@@ -113,7 +113,15 @@ ZB_HD uint32_t zb_len_base(int code) {
 }
 
 ZB_HD uint32_t zb_brev16(uint32_t v, int len) {  // reverse the low `len` bits (len<=16)
-  uint32_t r = 0;
-  for (int i = 0; i < len; i++) r |= ((v >> i) & 1u) << (len - 1 - i);
-  return r;
+  if (len == 0) return 0u;
+#if defined(__CUDA_ARCH__)
+  return __brev(v) >> (32 - len);
+#else
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+  v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+  v = (v >> 16) | (v << 16);
+  return v >> (32 - len);
+#endif
 }

@@ -181,18 +181,22 @@ ZB_HD_NOINLINE void zb_build_codebook(const uint16_t *hist, uint32_t chunk_len, 
   const uint8_t len_extra[29] = ZB_LENGTH_EXTRA;
   const uint8_t dist_extra[30] = ZB_DIST_EXTRA;
   const uint8_t clcl_order[19] = ZB_CLCL_ORDER;
+  // (the histograms are pairs of 16-bit counters in 32-bit words -- ZB_HIST_SYMS is even and every sub-chunk's
+  // histogram starts on a word -- so they are read a word at a time)
   uint32_t llf[ZB_NUM_LITLEN], df[ZB_NUM_DIST];
-  for (int s = 0; s < ZB_NUM_LITLEN; s++) {
-    uint32_t t = 0;
-    for (int w = 0; w < ZB_WARPS_PER_CHUNK; w++) t += hist[w * ZB_HIST_SYMS + s];
-    llf[s] = t;
+  const uint32_t *hw = reinterpret_cast<const uint32_t *>(hist);
+  for (int p2 = 0; p2 < ZB_HIST_SYMS / 2; p2++) {
+    uint32_t lo = 0, hi = 0;
+    for (int w = 0; w < ZB_WARPS_PER_CHUNK; w++) {
+      const uint32_t v = hw[w * (ZB_HIST_SYMS / 2) + p2];
+      lo += v & 0xffffu;
+      hi += v >> 16;
+    }
+    const int s0 = 2 * p2;
+    if (s0 < ZB_NUM_LITLEN) llf[s0] = lo; else df[s0 - ZB_NUM_LITLEN] = lo;
+    if (s0 + 1 < ZB_NUM_LITLEN) llf[s0 + 1] = hi; else df[s0 + 1 - ZB_NUM_LITLEN] = hi;
   }
   llf[256] = 1;
-  for (int s = 0; s < ZB_NUM_DIST; s++) {
-    uint32_t t = 0;
-    for (int w = 0; w < ZB_WARPS_PER_CHUNK; w++) t += hist[w * ZB_HIST_SYMS + ZB_NUM_LITLEN + s];
-    df[s] = t;
-  }
   cb->is_final = (uint32_t)is_final;
   cb->chunk_len = chunk_len;
 
@@ -203,17 +207,19 @@ ZB_HD_NOINLINE void zb_build_codebook(const uint16_t *hist, uint32_t chunk_len, 
   int nll = ZB_NUM_LITLEN, nd = ZB_NUM_DIST;
   while (nll > 257 && lens[nll - 1] == 0) nll--;
   while (nd > 1 && lens[ZB_NUM_LITLEN + nd - 1] == 0) nd--;
-  uint64_t dyn_payload = 0, fix_payload = 0, extra = 0;
+  // (32-bit sums: at most 65 537 tokens of at most 48 bits)
+  uint32_t dyn_payload32 = 0, fix_payload32 = 0, extra32 = 0;
   for (int s = 0; s < ZB_NUM_LITLEN; s++) {
-    dyn_payload += (uint64_t)llf[s] * lens[s];
-    fix_payload += (uint64_t)llf[s] * (uint32_t)zb_fixed_ll_len(s);
-    if (s > 256) extra += (uint64_t)llf[s] * len_extra[s - 257];
+    dyn_payload32 += llf[s] * lens[s];
+    fix_payload32 += llf[s] * (uint32_t)zb_fixed_ll_len(s);
+    if (s > 256) extra32 += llf[s] * len_extra[s - 257];
   }
   for (int s = 0; s < ZB_NUM_DIST; s++) {
-    dyn_payload += (uint64_t)df[s] * lens[ZB_NUM_LITLEN + s];
-    fix_payload += (uint64_t)df[s] * 5u;
-    extra += (uint64_t)df[s] * dist_extra[s];
+    dyn_payload32 += df[s] * lens[ZB_NUM_LITLEN + s];
+    fix_payload32 += df[s] * 5u;
+    extra32 += df[s] * dist_extra[s];
   }
+  const uint64_t dyn_payload = dyn_payload32, fix_payload = fix_payload32, extra = extra32;
   // code-length sequence -> RLE symbols (RFC 1951 3.2.7)
   uint8_t seq[ZB_NUM_LITLEN + ZB_NUM_DIST];
   int nseq = 0;
@@ -343,9 +349,12 @@ ZB_HD_NOINLINE void zb_build_codebook(const uint16_t *hist, uint32_t chunk_len, 
   uint32_t pos = sink.nbits;
   for (int w = 0; w < ZB_WARPS_PER_CHUNK; w++) {
     cb->warp_bit_start[w] = pos;
-    const uint16_t *h = hist + w * ZB_HIST_SYMS;
+    const uint32_t *h2 = hw + w * (ZB_HIST_SYMS / 2);
     uint32_t bits = 0;
-    for (int s = 0; s < ZB_HIST_SYMS; s++) bits += (uint32_t)h[s] * cost[s];
+    for (int p2 = 0; p2 < ZB_HIST_SYMS / 2; p2++) {
+      const uint32_t v = h2[p2];
+      bits += (v & 0xffffu) * cost[2 * p2] + (v >> 16) * cost[2 * p2 + 1];
+    }
     pos += bits;
   }
   cb->eob_bit_start = pos;
